@@ -1,0 +1,70 @@
+"""I/O helpers with the reference's names and behaviour
+(/root/reference/derenderer/common.py:13-102).  Kept on the host: SURVEY.md 8(b)
+lists load_image / load_json as part of the drop-in surface, not of the hot path.
+"""
+
+import json
+import pickle
+
+import cv2
+
+EPS = 1e-6
+
+
+def load_image(img_filepath, grayscale=False):
+    """common.py:13-24: RGB (H,W,3) u8, or gray (H,W,1)."""
+    image = cv2.imread(img_filepath)
+    if grayscale:
+        return cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)[:, :, None]
+    return cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+
+
+def save_image(img, save_filepath, grayscale=False):
+    """common.py:27-34."""
+    code = cv2.COLOR_GRAY2BGR if grayscale else cv2.COLOR_RGB2BGR
+    cv2.imwrite(save_filepath, cv2.cvtColor(img, code))
+
+
+def save_metrics(metrics, filename):
+    with open(filename, "wb") as fid:
+        pickle.dump(metrics, fid)
+
+
+def load_metrics(filename):
+    with open(filename, "rb") as f:
+        return pickle.load(f)
+
+
+def load_yaml(filepath):
+    import yaml
+    with open(filepath, "r") as stream:
+        return yaml.safe_load(stream)
+
+
+def load_json(json_path):
+    with open(json_path, "r") as f:
+        return json.load(f)
+
+
+def save_json(json_dict, save_path):
+    with open(save_path, "w") as out:
+        json.dump(json_dict, out)
+
+
+def resize_to_height(img, height):
+    """common.py:85-93. Host cv2 (identity for the 128-px lines the configs use);
+    a GPU general-height resize is SURVEY.md 8(f) item 3."""
+    h, w = img.shape[0], img.shape[1]
+    return cv2.resize(img, (int(w * (height / h)), height))
+
+
+def normalize_image(image):
+    """common.py:96-102."""
+    return cv2.normalize(image, None, 0, 255, norm_type=cv2.NORM_MINMAX)
+
+
+def init_onnx_session(onnx_path, device=0, max_tiles=64):
+    """common.py:105-111 creates an onnxruntime CPU session; here the handle is
+    the B200 engine (only defined for the binarizer graph)."""
+    from .engine import UNetEngine
+    return UNetEngine(onnx_path, device=device, max_tiles=max_tiles)

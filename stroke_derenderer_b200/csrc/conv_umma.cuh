@@ -1,0 +1,354 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+//   D[128 px, BN] (fp32, TMEM) += A[128 px, 64 ch of one tap] (fp16, smem) x B[BN, 64]^T (fp16, smem)
+//
+// * activations are NHWC fp16; one A k-block is ONE 4-D TMA box {64 ch, bw, bh, bn}
+//   (bw*bh*bn == 128 pixels) fetched at the tap's (dx, dy) offset — the TMA unit
+//   zero-fills out-of-image coordinates, which is exactly the conv's padding=1
+//   per tile (tiles are independent images, no cross-tile halo).
+// * the box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle,
+//   i.e. the canonical K-major SWIZZLE_128B UMMA operand; weights [Cout][K] land the
+//   same way, so both operands are described by plain UMMA smem descriptors.
+// * a second source tensor continues the K loop (channel concat without a cat).
+// * nearest-x2 upsample + conv3x3 is run as 4 sub-pixel phases, each a 2x2-tap conv
+//   on the LOW-res input with pre-summed weights (2.25x fewer MACs, no upsampled
+//   tensor ever exists).
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//   warps 2..5 = epilogue (TMEM -> registers -> fused op -> global).  TMEM holds two
+//   accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * epilogues: bias+ReLU store | attention gate (ReLU, dot with psi, sigmoid, scale
+//   the skip tensor) | head (ReLU, 1x1 conv to one channel, sigmoid, threshold).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace sd {
+
+enum { EPI_STORE = 0, EPI_GATE = 1, EPI_HEAD = 2 };
+
+struct ConvParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  // geometry of the (low-res for up-convs) input grid the M tiles walk over
+  int H, W, B;                 // image dims of the A source, live batch
+  int box_w, box_h, box_n;     // pixels per M tile = box_w*box_h*box_n = 128
+  int tiles_x, tiles_y;        // W/box_w, H/box_h
+  int m_tiles, n_tiles;        // m_tiles = tiles_x*tiles_y*ceil(B/box_n)
+  int n_phases;                // 1, or 4 for the sub-pixel up-conv
+  int n_taps;                  // taps per phase (9, 4 or 1)
+  int c0_blocks, c1_blocks;    // 64-channel k-blocks per tap from source 0 / 1
+  int cout;                    // output channels (rows per phase in the weight matrix)
+  int up;                      // 1: output pixel = (2y+py, 2x+px) on a 2H x 2W grid
+  int relu;
+  int8_t dy[4][9], dx[4][9];
+  const float* bias;           // [cout]
+  __half* out;                 // NHWC fp16, channels = out_c
+  int out_c;
+  // gate epilogue
+  const float* psi_w;          // [cout] fp32
+  float psi_b;
+  const __half* gate_x;        // skip tensor to scale, NHWC with gate_c channels
+  int gate_c;
+  // head epilogue
+  const float* head_w;         // [cout]
+  float head_b, thr;
+  float* prob_f32; __half* prob_f16; uint8_t* mask_u8;
+  int* err_flag;               // set when a barrier wait times out
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor / protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < 40000000u; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  if (err_flag) atomicExch(err_flag, code);
+  __threadfence_system();
+  asm volatile("trap;");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand tile whose rows are 128 B apart and 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)   // start address  [0,14)
+         | (1ull << 16)                            // leading byte offset (unused for swizzled K-major)
+         | (64ull << 32)                           // stride byte offset = 1024 B >> 4
+         | (1ull << 46)                            // descriptor version (sm_100)
+         | (2ull << 61);                           // SWIZZLE_128B
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN> struct ConvCfg {
+  static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // 64,128,256,512: powers of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+constexpr int kConvThreads = 192;
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout (8 B each): full[S], empty[S], tfull[2], tempty[2], then the TMEM slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    if (p.c1_blocks) tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_work = p.m_tiles * p.n_tiles * p.n_phases;
+  const int kb_per_tap = p.c0_blocks + p.c1_blocks;
+  const int num_kb = p.n_taps * kb_per_tap;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int nt = w % p.n_tiles; int rest = w / p.n_tiles;
+        const int mt = rest % p.m_tiles; const int ph = rest / p.m_tiles;
+        const int tx = mt % p.tiles_x; rest = mt / p.tiles_x;
+        const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
+        const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+        const int brow = ph * p.cout + nt * BN;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int xx = x0 + p.dx[ph][tap], yy = y0 + p.dy[ph][tap];
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+            if (cb < p.c0_blocks) tma_load_4d(a_dst, &p.tmA0, full_bar(stage), cb * 64, xx, yy, n0);
+            else tma_load_4d(a_dst, &p.tmA1, full_bar(stage), (cb - p.c0_blocks) * 64, xx, yy, n0);
+            tma_load_2d(a_dst + Cfg::kABytes, &p.tmB, full_bar(stage), (tap * kb_per_tap + cb) * 64, brow);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, Cfg::kIdesc, (uint32_t)((kb | k) != 0));
+          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue (warps 2..5) =======================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // accumulator row == pixel within the M tile
+    const int lw = row % p.box_w; int rr = row / p.box_w;
+    const int lh = rr % p.box_h; const int ln = rr / p.box_h;
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int nt = w % p.n_tiles; int rest = w / p.n_tiles;
+      const int mt = rest % p.m_tiles; const int ph = rest / p.m_tiles;
+      const int tx = mt % p.tiles_x; rest = mt / p.tiles_x;
+      const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
+      const int n = tn * p.box_n + ln;
+      int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
+      int OH = p.H, OW = p.W;
+      if (p.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); OH *= 2; OW *= 2; }
+      const int64_t pix = ((int64_t)n * OH + y) * OW + x;
+      const bool live = n < p.B;
+
+      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+
+      if constexpr (EPI == EPI_STORE) {
+        __half* orow = p.out + pix * p.out_c + nt * BN;
+        const float* brow = p.bias + nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          uint4 pk[4];
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = v[2 * j] + __ldg(brow + c * 32 + 2 * j);
+            float b = v[2 * j + 1] + __ldg(brow + c * 32 + 2 * j + 1);
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            __half2 h = __floats2half2_rn(a, b);
+            pw[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (live) {
+            uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pk[j];
+          }
+        }
+      } else if constexpr (EPI == EPI_GATE) {
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = fmaxf(v[j] + __ldg(p.bias + c * 32 + j), 0.f);
+            dot = fmaf(a, __ldg(p.psi_w + c * 32 + j), dot);
+          }
+        }
+        const float s = 1.f / (1.f + expf(-(dot + p.psi_b)));
+        if (live) {
+          const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + pix * p.gate_c);
+          uint4* xo = reinterpret_cast<uint4*>(p.out + pix * p.out_c);
+          for (int c = 0; c < p.gate_c / 8; ++c) {
+            uint4 t = __ldg(xi + c);
+            __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = __half22float2(h[j]);
+              h[j] = __floats2half2_rn(f.x * s, f.y * s);
+            }
+            xo[c] = t;
+          }
+        }
+      } else {  // EPI_HEAD
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = v[j] + __ldg(p.bias + c * 32 + j);
+            if (p.relu) a = fmaxf(a, 0.f);
+            // the unfused graph stores d2 in fp16 before the 1x1 conv; keep the same rounding point
+            a = __half2float(__float2half_rn(a));
+            dot = fmaf(a, __ldg(p.head_w + c * 32 + j), dot);
+          }
+        }
+        const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));
+        if (live) {
+          if (p.prob_f32) p.prob_f32[pix] = pr;
+          if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
+          if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+}  // namespace sd

@@ -1,0 +1,813 @@
+// Attention-UNet binarizer engine: weight packing, TMA descriptors, layer schedule,
+// the CUDA-core kernels that are not GEMM-shaped (first 3->64 conv, 2x2 max-pool)
+// and a slow all-CUDA-core debug implementation (impl=1) used only to cross-check
+// the tcgen05 path during bring-up.
+//
+// Replaces onnxruntime's execution of the exported graph
+// (/root/reference/derenderer/evaluate_binarize.py:48-53, :99-100).  Topology:
+// SURVEY.md Appendix B.  All activations are NHWC fp16, accumulation fp32.
+#include "conv_umma.cuh"
+#include <vector>
+#include <string>
+#include <functional>
+#include <cmath>
+#include <cstring>
+
+namespace sd {
+
+// ---------------------------------------------------------------------------
+// first conv: 3(+5 zero) -> 64 channels, 3x3, pad 1, bias + ReLU.  K = 27 is too
+// thin for the tensor pipe (0.17 % of the network's FLOPs); one thread per pixel,
+// weights broadcast from shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_first_kernel(
+    const uint2* __restrict__ in /* NHWC8: 16 B/px, first 8 B = r,g,b,0 */, const float* __restrict__ w /* [27][64] */,
+    const float* __restrict__ bias, __half* __restrict__ out, int B, int H, int W) {
+  __shared__ float4 sw[27 * 16];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * H * W;
+  if (pix >= total) return;
+  const int x = (int)(pix % W); const int64_t r = pix / W;
+  const int y = (int)(r % H);
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = sb[j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      float c[3] = {0.f, 0.f, 0.f};
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const uint2 v = __ldg(in + (pix + (int64_t)(ky - 1) * W + (kx - 1)) * 2);
+        const __half2 rg = *reinterpret_cast<const __half2*>(&v.x);
+        const __half2 b0 = *reinterpret_cast<const __half2*>(&v.y);
+        c[0] = __low2float(rg); c[1] = __high2float(rg); c[2] = __low2float(b0);
+      }
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float4* wr = sw + ((ky * 3 + kx) * 3 + ci) * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 ww = wr[j];
+          acc[4 * j + 0] = fmaf(c[ci], ww.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(c[ci], ww.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(c[ci], ww.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(c[ci], ww.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 t;
+    uint32_t* tw = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half2 h = __floats2half2_rn(fmaxf(acc[8 * j + 2 * k], 0.f), fmaxf(acc[8 * j + 2 * k + 1], 0.f));
+      tw[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    o[j] = t;
+  }
+}
+
+// 2x2 max-pool, NHWC fp16; a thread handles 8 channels of one output pixel.
+__global__ void __launch_bounds__(256) maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                      int B, int Ho, int Wo, int C8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8); int64_t r = i / C8;
+  const int x = (int)(r % Wo); r /= Wo;
+  const int y = (int)(r % Ho); const int64_t n = r / Ho;
+  const int Wi = 2 * Wo;
+  const uint4* p = in + (((n * 2 * Ho + 2 * y) * Wi + 2 * x) * C8 + c);
+  uint4 a = __ldg(p), b = __ldg(p + C8), d = __ldg(p + (int64_t)Wi * C8), e = __ldg(p + (int64_t)Wi * C8 + C8);
+  __half2* ha = reinterpret_cast<__half2*>(&a); const __half2* hb = reinterpret_cast<const __half2*>(&b);
+  const __half2* hd = reinterpret_cast<const __half2*>(&d); const __half2* he = reinterpret_cast<const __half2*>(&e);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ha[k] = __hmax2(__hmax2(ha[k], hb[k]), __hmax2(hd[k], he[k]));
+  out[i] = a;
+}
+
+// ---------------------------------------------------------------------------
+// debug implementation (impl=1): plain CUDA-core direct conv, two sources, optional
+// nearest-x2 gather.  64 px x 64 cout per CTA, 4x4 per thread.
+// ---------------------------------------------------------------------------
+struct SimtConv {
+  const __half* in0; const __half* in1; int c0, c1;
+  const __half* w;           // [taps][c0+c1][cout]
+  const float* bias;
+  __half* out; float* out32;
+  int B, H, W, cout, ks, up, relu;
+};
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(SimtConv a) {
+  __shared__ float As[8][64 + 1];
+  __shared__ float Ws[8][64];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const int cin = a.c0 + a.c1;
+  const int IH = a.up ? a.H / 2 : a.H, IW = a.up ? a.W / 2 : a.W;
+  float acc[4][4] = {};
+  // loader roles
+  const int lp = tid >> 2, lc = (tid & 3) * 2;           // A: pixel lp, channels lc, lc+1
+  const int wc = tid >> 5, wn = (tid & 31) * 2;          // W: row wc, couts wn, wn+1
+  const int64_t pm = m0 + lp;
+  const int px = (int)(pm % a.W); const int64_t pr = pm / a.W;
+  const int py = (int)(pr % a.H); const int64_t pn = pr / a.H;
+  const int taps = a.ks * a.ks, half_k = a.ks / 2;
+  for (int t = 0; t < taps; ++t) {
+    int yy = py + t / a.ks - half_k, xx = px + t % a.ks - half_k;
+    const bool inb = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+    if (a.up) { yy >>= 1; xx >>= 1; }
+    const int64_t ip = (pn * IH + yy) * IW + xx;
+    for (int cb = 0; cb < cin; cb += 8) {
+      float2 av = make_float2(0.f, 0.f);
+      if (inb) {
+        const int c = cb + lc;
+        const __half* src = (c < a.c0) ? a.in0 + ip * a.c0 + c : a.in1 + ip * a.c1 + (c - a.c0);
+        av = __half22float2(*reinterpret_cast<const __half2*>(src));
+      }
+      As[lc][lp] = av.x; As[lc + 1][lp] = av.y;
+      float2 wv = make_float2(0.f, 0.f);
+      if (n0 + wn < a.cout) wv = __half22float2(*reinterpret_cast<const __half2*>(a.w + ((int64_t)t * cin + cb + wc) * a.cout + n0 + wn));
+      Ws[wc][wn] = wv.x; Ws[wc][wn + 1] = wv.y;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float av4[4], wv4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { av4[i] = As[k][ty * 4 + i]; wv4[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av4[i], wv4[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.cout) continue;
+      float v = acc[i][j] + a.bias[n];
+      if (a.relu) v = fmaxf(v, 0.f);
+      if (a.out32) a.out32[m * a.cout + n] = v;
+      else a.out[m * a.cout + n] = __float2half_rn(v);
+    }
+  }
+}
+
+__global__ void gate_apply_kernel(const float* __restrict__ q, const float* __restrict__ psi_w, float psi_b,
+                                  const __half* __restrict__ x, __half* __restrict__ out, int64_t M, int fint, int fl) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float dot = 0.f;
+  for (int j = 0; j < fint; ++j) dot = fmaf(q[m * fint + j], psi_w[j], dot);
+  const float s = 1.f / (1.f + expf(-(dot + psi_b)));
+  for (int c = 0; c < fl; ++c) out[m * fl + c] = __float2half_rn(__half2float(x[m * fl + c]) * s);
+}
+
+__global__ void head_kernel(const __half* __restrict__ d2, const float* __restrict__ w, float b, float thr,
+                            float* __restrict__ p32, __half* __restrict__ p16, uint8_t* __restrict__ mask, int64_t M, int c) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float dot = 0.f;
+  for (int j = 0; j < c; ++j) dot = fmaf(__half2float(d2[m * c + j]), w[j], dot);
+  const float pr = 1.f / (1.f + expf(-(dot + b)));
+  if (p32) p32[m] = pr;
+  if (p16) p16[m] = __float2half_rn(pr);
+  if (mask) mask[m] = pr > thr ? 255 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Act {
+  __half* p = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Level { int H, W, box_w, box_h, box_n; };
+
+struct Op {
+  std::string name;
+  std::function<int(int /*B*/, cudaStream_t)> run;
+  double flops_per_tile = 0;
+};
+
+}  // namespace sd
+
+using namespace sd;
+
+struct sd_engine {
+  int device = 0, max_tiles = 0, cap_tiles = 0 /* max_tiles rounded up to the largest box_n */, H = 0, W = 0, impl = -1;
+  bool finalized = false;
+  std::vector<float> hw[SD_NUM_SLOTS], hb[SD_NUM_SLOTS];
+  int cout[SD_NUM_SLOTS] = {}, cin[SD_NUM_SLOTS] = {}, ks[SD_NUM_SLOTS] = {};
+  // device weights
+  __half* w_umma[SD_NUM_SLOTS] = {};   // [phases*cout][K]
+  __half* w_simt[SD_NUM_SLOTS] = {};   // [taps][cin][cout]
+  float* w_f32[SD_NUM_SLOTS] = {};     // first conv [27][64]; psi / head vectors
+  float* bias[SD_NUM_SLOTS] = {};
+  float psi_b[4] = {}, head_b = 0.f;
+  Level lv[5];
+  Act act[SD_NUM_TAPS];                // named taps
+  Act c1a, p1, c2a, p2, c3a, p3, c4a, p4, c5a, u5a, u4a, u3a, u2a;
+  float* qbuf = nullptr;               // debug impl: gate pre-activation, fp32
+  int* err_flag = nullptr;
+  std::vector<void*> allocs;
+  std::vector<Op> ops;
+  // per-call outputs (captured by the head op)
+  const void* in_tiles = nullptr;
+  float thr = 0.5f; float* o32 = nullptr; __half* o16 = nullptr; uint8_t* omask = nullptr;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<float> last_ms;
+  PFN_tmapEncodeTiled encode = nullptr;
+  int num_sms = 148;
+};
+
+namespace sd {
+
+static int dev_alloc(sd_engine* e, void** p, size_t bytes) {
+  SD_CUDA_CHECK(cudaMalloc(p, bytes));
+  e->allocs.push_back(*p);
+  return SD_OK;
+}
+
+static int alloc_act(sd_engine* e, Act& a, int lvl, int C) {
+  a.C = C; a.H = e->lv[lvl].H; a.W = e->lv[lvl].W;
+  return dev_alloc(e, (void**)&a.p, (size_t)e->cap_tiles * a.H * a.W * C * sizeof(__half));
+}
+
+static int make_tmap_act(sd_engine* e, CUtensorMap* tm, const Act& a, const Level& box) {
+  cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)e->cap_tiles};
+  cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
+  cuuint32_t boxd[4] = {64, (cuuint32_t)box.box_w, (cuuint32_t)box.box_h, (cuuint32_t)box.box_n};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d) failed: %d", a.C, a.W, a.H, (int)r); return SD_ECUDA; }
+  return SD_OK;
+}
+
+static int make_tmap_w(sd_engine* e, CUtensorMap* tm, const __half* w, int rows, int K, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t boxd[2] = {64, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights rows=%d K=%d) failed: %d", rows, K, (int)r); return SD_ECUDA; }
+  return SD_OK;
+}
+
+template <int BN, int EPI>
+static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  conv_umma_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  SD_LAUNCH_CHECK("conv_umma_kernel");
+  return SD_OK;
+}
+
+static int dispatch_conv(const ConvParams& p, int bn, int epi, int grid, cudaStream_t s) {
+  if (epi == EPI_STORE) {
+    if (bn == 64) return launch_conv<64, EPI_STORE>(p, grid, s);
+    if (bn == 128) return launch_conv<128, EPI_STORE>(p, grid, s);
+    if (bn == 256) return launch_conv<256, EPI_STORE>(p, grid, s);
+  } else if (epi == EPI_GATE) {
+    if (bn == 32) return launch_conv<32, EPI_GATE>(p, grid, s);
+    if (bn == 64) return launch_conv<64, EPI_GATE>(p, grid, s);
+    if (bn == 128) return launch_conv<128, EPI_GATE>(p, grid, s);
+    if (bn == 256) return launch_conv<256, EPI_GATE>(p, grid, s);
+  } else if (epi == EPI_HEAD) {
+    if (bn == 64) return launch_conv<64, EPI_HEAD>(p, grid, s);
+  }
+  set_error("dispatch_conv: no kernel for BN=%d epilogue=%d", bn, epi);
+  return SD_EINVAL;
+}
+
+// which 3x3 taps collapse onto low-res offset index t (0/1) for output parity p (0/1)
+static void phase_taps(int par, int t, int& k_lo, int& k_hi, int& d) {
+  if (par == 0) { if (t == 0) { k_lo = 0; k_hi = 0; d = -1; } else { k_lo = 1; k_hi = 2; d = 0; } }
+  else          { if (t == 0) { k_lo = 0; k_hi = 1; d = 0; }  else { k_lo = 2; k_hi = 2; d = 1; } }
+}
+
+// fp32 OIHW -> fp16 [phase*cout + co][tap*cin + ci]
+static void pack_umma(const float* w, int cout, int cin, int ks, bool up, std::vector<__half>& out) {
+  if (!up) {
+    const int taps = ks * ks, K = taps * cin;
+    out.assign((size_t)cout * K, __float2half(0.f));
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < taps; ++t)
+          out[(size_t)co * K + t * cin + ci] = __float2half_rn(w[((size_t)co * cin + ci) * taps + t]);
+  } else {
+    const int K = 4 * cin;
+    out.assign((size_t)4 * cout * K, __float2half(0.f));
+    for (int ph = 0; ph < 4; ++ph)
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          int y0, y1, x0, x1, d;
+          phase_taps(ph >> 1, ty, y0, y1, d);
+          phase_taps(ph & 1, tx, x0, x1, d);
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cin; ++ci) {
+              float s = 0.f;
+              for (int ky = y0; ky <= y1; ++ky)
+                for (int kx = x0; kx <= x1; ++kx) s += w[((size_t)co * cin + ci) * 9 + ky * 3 + kx];
+              out[((size_t)ph * cout + co) * K + (ty * 2 + tx) * cin + ci] = __float2half_rn(s);
+            }
+        }
+  }
+}
+
+static int upload(sd_engine* e, void** dptr, const void* h, size_t bytes) {
+  int r = dev_alloc(e, dptr, bytes);
+  if (r) return r;
+  SD_CUDA_CHECK(cudaMemcpy(*dptr, h, bytes, cudaMemcpyHostToDevice));
+  return SD_OK;
+}
+
+// ---- op builders ------------------------------------------------------------
+struct ConvSpec {
+  const char* name;
+  int slot;
+  const Act* in0; const Act* in1;   // in1 = second concat source or null
+  const Act* out;
+  bool up;
+  int epi;                          // EPI_*
+  int att = -1;                     // gate: index 0..3 (psi slot / bias), x source = in1
+};
+
+static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
+  const int slot = cs.slot;
+  const int cin_total = cs.in0->C + (cs.in1 ? cs.in1->C : 0);
+  const int co = e->cout[slot];
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  // level of the A source
+  int lvl = -1;
+  for (int i = 0; i < 5; ++i) if (e->lv[i].H == cs.in0->H && e->lv[i].W == cs.in0->W) lvl = i;
+  SD_REQUIRE(lvl >= 0, "add_umma_conv(%s): unknown level", cs.name);
+  const Level& L = e->lv[lvl];
+  int r;
+  if ((r = make_tmap_act(e, &p.tmA0, *cs.in0, L))) return r;
+  if (cs.in1 && (r = make_tmap_act(e, &p.tmA1, *cs.in1, L))) return r;
+  const int taps = cs.up ? 4 : e->ks[slot] * e->ks[slot];
+  const int K = taps * cin_total;
+  int bn = co >= 128 ? 128 : co;
+  if (cs.epi == EPI_GATE) bn = co;
+  if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], (cs.up ? 4 : 1) * co, K, bn))) return r;
+  p.H = L.H; p.W = L.W;
+  p.box_w = L.box_w; p.box_h = L.box_h; p.box_n = L.box_n;
+  p.tiles_x = L.W / L.box_w; p.tiles_y = L.H / L.box_h;
+  p.n_tiles = co / bn;
+  p.n_phases = cs.up ? 4 : 1;
+  p.n_taps = taps;
+  p.c0_blocks = cs.in0->C / 64; p.c1_blocks = cs.in1 ? cs.in1->C / 64 : 0;
+  p.cout = co; p.up = cs.up ? 1 : 0; p.relu = 1;
+  if (cs.up) {
+    for (int ph = 0; ph < 4; ++ph)
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          int a, b, dy, dx;
+          phase_taps(ph >> 1, ty, a, b, dy);
+          phase_taps(ph & 1, tx, a, b, dx);
+          p.dy[ph][ty * 2 + tx] = (int8_t)dy; p.dx[ph][ty * 2 + tx] = (int8_t)dx;
+        }
+  } else if (e->ks[slot] == 3) {
+    for (int t = 0; t < 9; ++t) { p.dy[0][t] = (int8_t)(t / 3 - 1); p.dx[0][t] = (int8_t)(t % 3 - 1); }
+  }
+  p.bias = e->bias[slot];
+  p.err_flag = e->err_flag;
+  if (cs.epi == EPI_STORE) { p.out = cs.out->p; p.out_c = cs.out->C; }
+  if (cs.epi == EPI_GATE) {
+    p.out = cs.out->p; p.out_c = cs.out->C;
+    p.psi_w = e->w_f32[SD_ATT5_PSI + 6 * cs.att]; p.psi_b = e->psi_b[cs.att];
+    p.gate_x = cs.in1->p; p.gate_c = cs.in1->C;
+  }
+  if (cs.epi == EPI_HEAD) { p.head_w = e->w_f32[SD_HEAD]; }
+  Op op;
+  op.name = cs.name;
+  const int epi = cs.epi;
+  const int box_n = L.box_n, per_img = p.tiles_x * p.tiles_y;
+  const int nsm = e->num_sms;
+  op.flops_per_tile = 2.0 * (cs.up ? 4.0 : 1.0) * L.H * L.W * co * K;
+  op.run = [e, p, bn, epi, box_n, per_img, nsm](int B, cudaStream_t s) mutable -> int {
+    p.B = B;
+    p.m_tiles = per_img * ((B + box_n - 1) / box_n);
+    if (epi == EPI_HEAD) {
+      p.head_b = e->head_b; p.thr = e->thr;
+      p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
+    }
+    const int n_work = p.m_tiles * p.n_tiles * p.n_phases;
+    const int grid = n_work < nsm ? n_work : nsm;
+    return dispatch_conv(p, bn, epi, grid, s);
+  };
+  e->ops.push_back(op);
+  return SD_OK;
+}
+
+static void add_simt_conv(sd_engine* e, const char* name, int slot, const Act* in0, const Act* in1, const Act* out,
+                          bool up, float* out32) {
+  Op op;
+  op.name = name;
+  op.run = [e, slot, in0, in1, out, up, out32](int B, cudaStream_t s) -> int {
+    SimtConv a;
+    a.in0 = in0->p; a.c0 = in0->C; a.in1 = in1 ? in1->p : nullptr; a.c1 = in1 ? in1->C : 0;
+    a.w = e->w_simt[slot]; a.bias = e->bias[slot];
+    a.out = out ? out->p : nullptr; a.out32 = out32;
+    a.B = B; a.H = up ? in0->H * 2 : in0->H; a.W = up ? in0->W * 2 : in0->W;
+    a.cout = e->cout[slot]; a.ks = e->ks[slot]; a.up = up; a.relu = 1;
+    const int64_t M = (int64_t)B * a.H * a.W;
+    dim3 grid((unsigned)(M / 64), (unsigned)((a.cout + 63) / 64));
+    conv_simt_kernel<<<grid, 256, 0, s>>>(a);
+    SD_LAUNCH_CHECK("conv_simt_kernel");
+    return SD_OK;
+  };
+  e->ops.push_back(op);
+}
+
+static void add_pool(sd_engine* e, const char* name, const Act* in, const Act* out) {
+  Op op;
+  op.name = name;
+  op.run = [in, out](int B, cudaStream_t s) -> int {
+    const int C8 = in->C / 8;
+    const int64_t total = (int64_t)B * out->H * out->W * C8;
+    maxpool_kernel<<<ceil_div(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in->p), reinterpret_cast<uint4*>(out->p),
+                                                        B, out->H, out->W, C8);
+    SD_LAUNCH_CHECK("maxpool_kernel");
+    return SD_OK;
+  };
+  e->ops.push_back(op);
+}
+
+}  // namespace sd
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" int sd_engine_create(int device, int max_tiles, int tile_h, int tile_w, sd_engine** out) {
+  SD_REQUIRE(out, "sd_engine_create: null out");
+  SD_REQUIRE(max_tiles > 0, "sd_engine_create: max_tiles %d", max_tiles);
+  SD_REQUIRE(tile_h == SD_TILE_H && tile_w == SD_TILE_W, "sd_engine_create: only %dx%d tiles are supported (got %dx%d)",
+             SD_TILE_H, SD_TILE_W, tile_h, tile_w);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("sd_engine_create: no CUDA device (this library has no CPU fallback)");
+    return SD_ECUDA;
+  }
+  SD_REQUIRE(device >= 0 && device < ndev, "sd_engine_create: device %d of %d", device, ndev);
+  SD_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SD_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("sd_engine_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return SD_ECUDA;
+  }
+  sd_engine* e = new sd_engine();
+  e->device = device; e->max_tiles = max_tiles; e->cap_tiles = (max_tiles + 1) / 2 * 2; e->H = tile_h; e->W = tile_w;
+  e->num_sms = prop.multiProcessorCount;
+  *out = e;
+  return SD_OK;
+}
+
+extern "C" void sd_engine_destroy(sd_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  for (auto ev : e->ev) cudaEventDestroy(ev);
+  delete e;
+}
+
+extern "C" int sd_engine_set_conv(sd_engine* e, int slot, const float* w, const float* b, int cout, int cin, int k) {
+  SD_REQUIRE(e && w && b, "sd_engine_set_conv: null argument");
+  SD_REQUIRE(slot >= 0 && slot < SD_NUM_SLOTS, "sd_engine_set_conv: slot %d", slot);
+  SD_REQUIRE(!e->finalized, "sd_engine_set_conv: engine already finalized");
+  SD_REQUIRE((k == 1 || k == 3) && cout > 0 && cin > 0, "sd_engine_set_conv: bad shape");
+  e->hw[slot].assign(w, w + (size_t)cout * cin * k * k);
+  e->hb[slot].assign(b, b + cout);
+  e->cout[slot] = cout; e->cin[slot] = cin; e->ks[slot] = k;
+  return SD_OK;
+}
+
+extern "C" int sd_engine_set_head_bias(sd_engine* e, float bias) {
+  SD_REQUIRE(e, "sd_engine_set_head_bias: null engine");
+  e->head_b = bias;
+  return SD_OK;
+}
+
+extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
+  SD_REQUIRE(e && !e->finalized, "sd_engine_finalize: bad state");
+  SD_REQUIRE(impl == 0 || impl == 1, "sd_engine_finalize: impl %d", impl);
+  SD_CUDA_CHECK(cudaSetDevice(e->device));
+  // expected shapes
+  static const int exp_shape[SD_NUM_SLOTS][3] = {
+      {64, 3, 3}, {64, 64, 3}, {128, 64, 3}, {128, 128, 3}, {256, 128, 3}, {256, 256, 3}, {512, 256, 3}, {512, 512, 3},
+      {1024, 512, 3}, {1024, 1024, 3},
+      {512, 1024, 3}, {256, 512, 1}, {256, 512, 1}, {1, 256, 1}, {512, 1024, 3}, {512, 512, 3},
+      {256, 512, 3}, {128, 256, 1}, {128, 256, 1}, {1, 128, 1}, {256, 512, 3}, {256, 256, 3},
+      {128, 256, 3}, {64, 128, 1}, {64, 128, 1}, {1, 64, 1}, {128, 256, 3}, {128, 128, 3},
+      {64, 128, 3}, {32, 64, 1}, {32, 64, 1}, {1, 32, 1}, {64, 128, 3}, {64, 64, 3},
+      {1, 64, 1}};
+  for (int s = 0; s < SD_NUM_SLOTS; ++s) {
+    SD_REQUIRE(!e->hw[s].empty(), "sd_engine_finalize: slot %d has no weights", s);
+    SD_REQUIRE(e->cout[s] == exp_shape[s][0] && e->cin[s] == exp_shape[s][1] && e->ks[s] == exp_shape[s][2],
+               "sd_engine_finalize: slot %d has shape (%d,%d,%d), expected (%d,%d,%d)", s, e->cout[s], e->cin[s], e->ks[s],
+               exp_shape[s][0], exp_shape[s][1], exp_shape[s][2]);
+  }
+  e->impl = impl;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  SD_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+  e->encode = (PFN_tmapEncodeTiled)fn;
+
+  const int H = e->H, W = e->W;
+  e->lv[0] = {H, W, 128, 1, 1};
+  e->lv[1] = {H / 2, W / 2, 64, 2, 1};
+  e->lv[2] = {H / 4, W / 4, 32, 4, 1};
+  e->lv[3] = {H / 8, W / 8, 16, 8, 1};
+  e->lv[4] = {H / 16, W / 16, 8, 8, 2};
+  int r;
+  SD_CUDA_CHECK(cudaMalloc((void**)&e->err_flag, sizeof(int)));
+  e->allocs.push_back(e->err_flag);
+  SD_CUDA_CHECK(cudaMemset(e->err_flag, 0, sizeof(int)));
+
+  // ---- weights ----
+  for (int s = 0; s < SD_NUM_SLOTS; ++s) {
+    if ((r = upload(e, (void**)&e->bias[s], e->hb[s].data(), e->hb[s].size() * 4))) return r;
+    const bool is_psi = (s == SD_ATT5_PSI || s == SD_ATT4_PSI || s == SD_ATT3_PSI || s == SD_ATT2_PSI);
+    const bool is_up = (s == SD_UP5 || s == SD_UP4 || s == SD_UP3 || s == SD_UP2);
+    if (is_psi || s == SD_HEAD) {
+      if ((r = upload(e, (void**)&e->w_f32[s], e->hw[s].data(), e->hw[s].size() * 4))) return r;
+      if (is_psi) e->psi_b[(s - SD_ATT5_PSI) / 6] = e->hb[s][0];
+      else e->head_b = e->hb[s][0];
+      continue;
+    }
+    if (s == SD_CONV1_0) {
+      std::vector<float> t(27 * 64);
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int k = 0; k < 9; ++k) t[(k * 3 + ci) * 64 + co] = e->hw[s][((size_t)co * 3 + ci) * 9 + k];
+      if ((r = upload(e, (void**)&e->w_f32[s], t.data(), t.size() * 4))) return r;
+    }
+    const int co = e->cout[s], ci = e->cin[s], taps = e->ks[s] * e->ks[s];
+    if (impl == 1) {
+      const int cip = (s == SD_CONV1_0) ? 8 : ci;
+      std::vector<__half> t((size_t)taps * cip * co, __float2half(0.f));
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+          for (int k = 0; k < taps; ++k) t[((size_t)k * cip + i) * co + o] = __float2half_rn(e->hw[s][((size_t)o * ci + i) * taps + k]);
+      if ((r = upload(e, (void**)&e->w_simt[s], t.data(), t.size() * 2))) return r;
+    } else if (s != SD_CONV1_0) {
+      const bool is_gx = (s == SD_ATT5_X || s == SD_ATT4_X || s == SD_ATT3_X || s == SD_ATT2_X);
+      const bool is_gg = (s == SD_ATT5_G || s == SD_ATT4_G || s == SD_ATT3_G || s == SD_ATT2_G);
+      if (is_gx) continue;   // packed together with the G slot below
+      std::vector<__half> t;
+      if (is_gg) {
+        // gate GEMM: K = [g channels | x channels], weights [W_g | W_x], bias b_g + b_x
+        const int fg = ci, fl = e->cin[s + 1];
+        t.assign((size_t)co * (fg + fl), __float2half(0.f));
+        for (int o = 0; o < co; ++o) {
+          for (int i = 0; i < fg; ++i) t[(size_t)o * (fg + fl) + i] = __float2half_rn(e->hw[s][(size_t)o * fg + i]);
+          for (int i = 0; i < fl; ++i) t[(size_t)o * (fg + fl) + fg + i] = __float2half_rn(e->hw[s + 1][(size_t)o * fl + i]);
+        }
+      } else {
+        pack_umma(e->hw[s].data(), co, ci, e->ks[s], is_up, t);
+      }
+      if ((r = upload(e, (void**)&e->w_umma[s], t.data(), t.size() * 2))) return r;
+    }
+  }
+  // gate bias = b_g + b_x (both folded), replacing the G slot's device bias
+  for (int a = 0; a < 4; ++a) {
+    const int sg = SD_ATT5_G + 6 * a, sx = sg + 1;
+    std::vector<float> bsum(e->cout[sg]);
+    for (int i = 0; i < e->cout[sg]; ++i) bsum[i] = e->hb[sg][i] + e->hb[sx][i];
+    SD_CUDA_CHECK(cudaMemcpy(e->bias[sg], bsum.data(), bsum.size() * 4, cudaMemcpyHostToDevice));
+  }
+
+  // ---- activations ----
+  Act* A = e->act;
+  if ((r = alloc_act(e, e->c1a, 0, 64)) || (r = alloc_act(e, A[SD_TAP_X1], 0, 64)) || (r = alloc_act(e, e->p1, 1, 64)) ||
+      (r = alloc_act(e, e->c2a, 1, 128)) || (r = alloc_act(e, A[SD_TAP_X2], 1, 128)) || (r = alloc_act(e, e->p2, 2, 128)) ||
+      (r = alloc_act(e, e->c3a, 2, 256)) || (r = alloc_act(e, A[SD_TAP_X3], 2, 256)) || (r = alloc_act(e, e->p3, 3, 256)) ||
+      (r = alloc_act(e, e->c4a, 3, 512)) || (r = alloc_act(e, A[SD_TAP_X4], 3, 512)) || (r = alloc_act(e, e->p4, 4, 512)) ||
+      (r = alloc_act(e, e->c5a, 4, 1024)) || (r = alloc_act(e, A[SD_TAP_X5], 4, 1024)) ||
+      (r = alloc_act(e, A[SD_TAP_D5U], 3, 512)) || (r = alloc_act(e, A[SD_TAP_A4], 3, 512)) || (r = alloc_act(e, e->u5a, 3, 512)) ||
+      (r = alloc_act(e, A[SD_TAP_D5], 3, 512)) ||
+      (r = alloc_act(e, A[SD_TAP_D4U], 2, 256)) || (r = alloc_act(e, A[SD_TAP_A3], 2, 256)) || (r = alloc_act(e, e->u4a, 2, 256)) ||
+      (r = alloc_act(e, A[SD_TAP_D4], 2, 256)) ||
+      (r = alloc_act(e, A[SD_TAP_D3U], 1, 128)) || (r = alloc_act(e, A[SD_TAP_A2], 1, 128)) || (r = alloc_act(e, e->u3a, 1, 128)) ||
+      (r = alloc_act(e, A[SD_TAP_D3], 1, 128)) ||
+      (r = alloc_act(e, A[SD_TAP_D2U], 0, 64)) || (r = alloc_act(e, A[SD_TAP_A1], 0, 64)) || (r = alloc_act(e, e->u2a, 0, 64)))
+    return r;
+  if (impl == 1) {
+    if ((r = alloc_act(e, A[SD_TAP_D2], 0, 64))) return r;
+    if ((r = dev_alloc(e, (void**)&e->qbuf, (size_t)e->max_tiles * H * W * 32 * sizeof(float)))) return r;
+  }
+
+  // ---- schedule ----
+  Op first;
+  first.name = "Conv1.0(simt)";
+  first.flops_per_tile = 2.0 * H * W * 64 * 27;
+  if (impl == 0) {
+    first.run = [e](int B, cudaStream_t s) -> int {
+      const int64_t total = (int64_t)B * e->H * e->W;
+      conv_first_kernel<<<ceil_div(total, 128), 128, 0, s>>>(reinterpret_cast<const uint2*>(e->in_tiles), e->w_f32[SD_CONV1_0],
+                                                             e->bias[SD_CONV1_0], e->c1a.p, B, e->H, e->W);
+      SD_LAUNCH_CHECK("conv_first_kernel");
+      return SD_OK;
+    };
+  } else {
+    first.run = [e](int B, cudaStream_t s) -> int {
+      SimtConv a;
+      a.in0 = reinterpret_cast<const __half*>(e->in_tiles); a.c0 = 8; a.in1 = nullptr; a.c1 = 0;
+      a.w = e->w_simt[SD_CONV1_0]; a.bias = e->bias[SD_CONV1_0]; a.out = e->c1a.p; a.out32 = nullptr;
+      a.B = B; a.H = e->H; a.W = e->W; a.cout = 64; a.ks = 3; a.up = 0; a.relu = 1;
+      dim3 grid((unsigned)((int64_t)B * e->H * e->W / 64), 1);
+      conv_simt_kernel<<<grid, 256, 0, s>>>(a);
+      SD_LAUNCH_CHECK("conv_simt_kernel");
+      return SD_OK;
+    };
+  }
+  e->ops.push_back(first);
+
+  auto conv = [&](const char* name, int slot, const Act* i0, const Act* i1, const Act* o, bool up) -> int {
+    if (impl == 0) { ConvSpec cs{name, slot, i0, i1, o, up, EPI_STORE, -1}; return add_umma_conv(e, cs); }
+    add_simt_conv(e, name, slot, i0, i1, o, up, nullptr);
+    return SD_OK;
+  };
+  auto gate = [&](const char* name, int att, const Act* g, const Act* x, const Act* o) -> int {
+    const int sg = SD_ATT5_G + 6 * att;
+    if (impl == 0) { ConvSpec cs{name, sg, g, x, o, false, EPI_GATE, att}; return add_umma_conv(e, cs); }
+    // debug: q = relu(W_g g + W_x x + b) in fp32, then psi / scale
+    Op op;
+    op.name = name;
+    op.run = [e, sg, att, g, x, o](int B, cudaStream_t s) -> int {
+      SimtConv a;
+      a.in0 = g->p; a.c0 = g->C; a.in1 = x->p; a.c1 = x->C;
+      a.w = e->w_simt[sg]; a.bias = e->bias[sg]; a.out = nullptr; a.out32 = e->qbuf;
+      a.B = B; a.H = g->H; a.W = g->W; a.cout = e->cout[sg]; a.ks = 1; a.up = 0; a.relu = 1;
+      const int64_t M = (int64_t)B * a.H * a.W;
+      dim3 grid((unsigned)(M / 64), (unsigned)((a.cout + 63) / 64));
+      conv_simt_kernel<<<grid, 256, 0, s>>>(a);
+      SD_LAUNCH_CHECK("conv_simt_kernel(gate)");
+      gate_apply_kernel<<<ceil_div(M, 128), 128, 0, s>>>(e->qbuf, e->w_f32[sg + 2], e->psi_b[att], x->p, o->p, M, a.cout, x->C);
+      SD_LAUNCH_CHECK("gate_apply_kernel");
+      return SD_OK;
+    };
+    e->ops.push_back(op);
+    return SD_OK;
+  };
+  if (impl == 1) {
+    // debug gate weights: [1 tap][fg + fl][fint]
+    for (int a = 0; a < 4; ++a) {
+      const int sg = SD_ATT5_G + 6 * a, sx = sg + 1;
+      const int fint = e->cout[sg], fg = e->cin[sg], fl = e->cin[sx];
+      std::vector<__half> t((size_t)(fg + fl) * fint);
+      for (int o = 0; o < fint; ++o) {
+        for (int i = 0; i < fg; ++i) t[(size_t)i * fint + o] = __float2half_rn(e->hw[sg][(size_t)o * fg + i]);
+        for (int i = 0; i < fl; ++i) t[(size_t)(fg + i) * fint + o] = __float2half_rn(e->hw[sx][(size_t)o * fl + i]);
+      }
+      e->w_simt[sg] = nullptr;
+      if ((r = upload(e, (void**)&e->w_simt[sg], t.data(), t.size() * 2))) return r;
+    }
+  }
+
+  if ((r = conv("Conv1.3", SD_CONV1_1, &e->c1a, nullptr, &A[SD_TAP_X1], false))) return r;
+  add_pool(e, "pool1", &A[SD_TAP_X1], &e->p1);
+  if ((r = conv("Conv2.0", SD_CONV2_0, &e->p1, nullptr, &e->c2a, false))) return r;
+  if ((r = conv("Conv2.3", SD_CONV2_1, &e->c2a, nullptr, &A[SD_TAP_X2], false))) return r;
+  add_pool(e, "pool2", &A[SD_TAP_X2], &e->p2);
+  if ((r = conv("Conv3.0", SD_CONV3_0, &e->p2, nullptr, &e->c3a, false))) return r;
+  if ((r = conv("Conv3.3", SD_CONV3_1, &e->c3a, nullptr, &A[SD_TAP_X3], false))) return r;
+  add_pool(e, "pool3", &A[SD_TAP_X3], &e->p3);
+  if ((r = conv("Conv4.0", SD_CONV4_0, &e->p3, nullptr, &e->c4a, false))) return r;
+  if ((r = conv("Conv4.3", SD_CONV4_1, &e->c4a, nullptr, &A[SD_TAP_X4], false))) return r;
+  add_pool(e, "pool4", &A[SD_TAP_X4], &e->p4);
+  if ((r = conv("Conv5.0", SD_CONV5_0, &e->p4, nullptr, &e->c5a, false))) return r;
+  if ((r = conv("Conv5.3", SD_CONV5_1, &e->c5a, nullptr, &A[SD_TAP_X5], false))) return r;
+
+  if ((r = conv("Up5", SD_UP5, &A[SD_TAP_X5], nullptr, &A[SD_TAP_D5U], true))) return r;
+  if ((r = gate("Att5", 0, &A[SD_TAP_D5U], &A[SD_TAP_X4], &A[SD_TAP_A4]))) return r;
+  if ((r = conv("Up_conv5.0", SD_UPCONV5_0, &A[SD_TAP_A4], &A[SD_TAP_D5U], &e->u5a, false))) return r;
+  if ((r = conv("Up_conv5.3", SD_UPCONV5_1, &e->u5a, nullptr, &A[SD_TAP_D5], false))) return r;
+
+  if ((r = conv("Up4", SD_UP4, &A[SD_TAP_D5], nullptr, &A[SD_TAP_D4U], true))) return r;
+  if ((r = gate("Att4", 1, &A[SD_TAP_D4U], &A[SD_TAP_X3], &A[SD_TAP_A3]))) return r;
+  if ((r = conv("Up_conv4.0", SD_UPCONV4_0, &A[SD_TAP_A3], &A[SD_TAP_D4U], &e->u4a, false))) return r;
+  if ((r = conv("Up_conv4.3", SD_UPCONV4_1, &e->u4a, nullptr, &A[SD_TAP_D4], false))) return r;
+
+  if ((r = conv("Up3", SD_UP3, &A[SD_TAP_D4], nullptr, &A[SD_TAP_D3U], true))) return r;
+  if ((r = gate("Att3", 2, &A[SD_TAP_D3U], &A[SD_TAP_X2], &A[SD_TAP_A2]))) return r;
+  if ((r = conv("Up_conv3.0", SD_UPCONV3_0, &A[SD_TAP_A2], &A[SD_TAP_D3U], &e->u3a, false))) return r;
+  if ((r = conv("Up_conv3.3", SD_UPCONV3_1, &e->u3a, nullptr, &A[SD_TAP_D3], false))) return r;
+
+  if ((r = conv("Up2", SD_UP2, &A[SD_TAP_D3], nullptr, &A[SD_TAP_D2U], true))) return r;
+  if ((r = gate("Att2", 3, &A[SD_TAP_D2U], &A[SD_TAP_X1], &A[SD_TAP_A1]))) return r;
+  if ((r = conv("Up_conv2.0", SD_UPCONV2_0, &A[SD_TAP_A1], &A[SD_TAP_D2U], &e->u2a, false))) return r;
+  if (impl == 0) {
+    ConvSpec cs{"Up_conv2.3+head", SD_UPCONV2_1, &e->u2a, nullptr, nullptr, false, EPI_HEAD, -1};
+    if ((r = add_umma_conv(e, cs))) return r;
+  } else {
+    if ((r = conv("Up_conv2.3", SD_UPCONV2_1, &e->u2a, nullptr, &A[SD_TAP_D2], false))) return r;
+    Op op;
+    op.name = "head";
+    op.run = [e](int B, cudaStream_t s) -> int {
+      const int64_t M = (int64_t)B * e->H * e->W;
+      head_kernel<<<ceil_div(M, 256), 256, 0, s>>>(e->act[SD_TAP_D2].p, e->w_f32[SD_HEAD], e->head_b, e->thr, e->o32, e->o16,
+                                                   e->omask, M, 64);
+      SD_LAUNCH_CHECK("head_kernel");
+      return SD_OK;
+    };
+    e->ops.push_back(op);
+  }
+  e->ev.resize(e->ops.size() + 1);
+  for (auto& ev : e->ev) SD_CUDA_CHECK(cudaEventCreate(&ev));
+  e->last_ms.assign(e->ops.size(), 0.f);
+  e->finalized = true;
+  return SD_OK;
+}
+
+extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, float bin_thr, float* d_prob_f32,
+                               void* d_prob_f16, uint8_t* d_mask_u8, void* stream) {
+  SD_REQUIRE(e && e->finalized, "sd_unet_forward: engine not finalized");
+  SD_REQUIRE(n_tiles >= 0 && n_tiles <= e->max_tiles, "sd_unet_forward: n_tiles %d exceeds max_tiles %d", n_tiles, e->max_tiles);
+  if (n_tiles == 0) return SD_OK;   // evaluate_binarize.py:93-100 feeds an empty last minibatch when B % 8 == 0
+  SD_REQUIRE(d_tiles, "sd_unet_forward: null input");
+  cudaStream_t s = (cudaStream_t)stream;
+  e->in_tiles = d_tiles; e->thr = bin_thr;
+  e->o32 = d_prob_f32; e->o16 = reinterpret_cast<__half*>(d_prob_f16); e->omask = d_mask_u8;
+  for (size_t i = 0; i < e->ops.size(); ++i) {
+    if (e->timing) SD_CUDA_CHECK(cudaEventRecord(e->ev[i], s));
+    int r = e->ops[i].run(n_tiles, s);
+    if (r) return r;
+  }
+  if (e->timing) {
+    SD_CUDA_CHECK(cudaEventRecord(e->ev[e->ops.size()], s));
+    SD_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < e->ops.size(); ++i) SD_CUDA_CHECK(cudaEventElapsedTime(&e->last_ms[i], e->ev[i], e->ev[i + 1]));
+    int flag = 0;
+    SD_CUDA_CHECK(cudaMemcpy(&flag, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    SD_REQUIRE(flag == 0, "sd_unet_forward: kernel barrier timeout (code %d)", flag);
+  }
+  return SD_OK;
+}
+
+extern "C" int sd_unet_read_tap(sd_engine* e, int tap, int n_tiles, void* d_out, size_t out_bytes, int* c, int* h, int* w,
+                                void* stream) {
+  SD_REQUIRE(e && e->finalized, "sd_unet_read_tap: engine not finalized");
+  SD_REQUIRE(tap >= 0 && tap < SD_NUM_TAPS, "sd_unet_read_tap: tap %d", tap);
+  const Act& a = e->act[tap];
+  SD_REQUIRE(a.p, "sd_unet_read_tap: tap %d is not materialised by this implementation", tap);
+  if (c) *c = a.C;
+  if (h) *h = a.H;
+  if (w) *w = a.W;
+  if (!d_out) return SD_OK;
+  const size_t need = (size_t)n_tiles * a.H * a.W * a.C * sizeof(__half);
+  SD_REQUIRE(out_bytes >= need, "sd_unet_read_tap: buffer too small (%zu < %zu)", out_bytes, need);
+  SD_CUDA_CHECK(cudaMemcpyAsync(d_out, a.p, need, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SD_OK;
+}
+
+extern "C" int sd_engine_enable_timing(sd_engine* e, int on) {
+  SD_REQUIRE(e, "sd_engine_enable_timing: null engine");
+  e->timing = on != 0;
+  return SD_OK;
+}
+
+extern "C" int sd_engine_layer_times(sd_engine* e, float* h_ms, int cap, int* n_out) {
+  SD_REQUIRE(e && e->finalized && n_out, "sd_engine_layer_times: bad argument");
+  *n_out = (int)e->ops.size();
+  for (int i = 0; i < cap && i < (int)e->ops.size(); ++i) h_ms[i] = e->last_ms[i];
+  return SD_OK;
+}
+
+extern "C" const char* sd_engine_layer_name(sd_engine* e, int i) {
+  if (!e || i < 0 || i >= (int)e->ops.size()) return "";
+  return e->ops[i].name.c_str();
+}

@@ -1,0 +1,252 @@
+"""Device stages of the segmentation path and the batched line pipeline.
+
+Everything here calls the C ABI (`libsd_b200.so`); torch only owns the device
+buffers and streams.  Stage <-> reference map:
+  tile_extract_*   helper/split.py:10-86 (+ evaluate_binarize.py:99)
+  glue_*           helper/split.py:89-124 (+ evaluate_binarize.py:103, main.py:108)
+  ccl_label        helper/partition.py:14   (cv2.connectedComponentsWithStats)
+  island_stats     helper/partition.py:17-26
+  group canvases   helper/partition.py:31-87 via the stats closed form
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import TILE_H, TILE_W, CIN_PAD, UNetEngine, stream_ptr
+
+MARGIN = 2          # evaluate_strokes.py:26 / partition.py:9
+
+
+@dataclass
+class LineBatch:
+    """A planned batch of text lines (all at height 128) resident on one GPU."""
+    device: torch.device
+    lines: np.ndarray                 # structured array, _lib.LINE_DTYPE
+    plan: _lib.Plan
+    d_lines: torch.Tensor             # uint8 view of the sd_line table on the device
+    widths: list = field(default_factory=list)
+
+    @property
+    def n_lines(self): return int(self.plan.n_lines)
+    @property
+    def n_tiles(self): return int(self.plan.n_tiles)
+    @property
+    def px_total(self): return int(self.plan.px_total)
+    @property
+    def blk_total(self): return int(self.plan.blk_total)
+
+    def plane(self, buf: torch.Tensor, i: int) -> torch.Tensor:
+        """(128, W') view of line i inside a packed plane buffer."""
+        ln = self.lines[i]
+        off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
+        return buf[off:off + TILE_H * pitch].view(TILE_H, pitch)[:, :w]
+
+    # bookkeeping lists of cut_and_stack (helper/split.py:66-78)
+    def stack_indices(self):
+        return [list(range(int(l["first_tile"]), int(l["first_tile"] + l["n_tiles"]))) for l in self.lines]
+
+    def stack_widths(self):
+        out = []
+        for l in self.lines:
+            W, n, wu, ov = int(l["width"]), int(l["n_tiles"]), int(l["wu"]), int(l["overlap"])
+            out.append([W] if n == 1 else [min((i + 1) * wu + ov, W) - i * wu for i in range(n)])
+        return out
+
+
+def plan_batch(widths, device, tile_w=TILE_W, overlap=64) -> LineBatch:
+    lines, plan = _lib.plan_lines(widths, tile_w, overlap)
+    raw = torch.from_numpy(lines.view(np.uint8).reshape(-1).copy())
+    d_lines = raw.to(device, non_blocking=False)
+    return LineBatch(torch.device(device), lines, plan, d_lines, [int(w) for w in widths])
+
+
+def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True) -> torch.Tensor:
+    """Host-packs (128, W, 3) u8 images at sd_line.img_off (pinned staging)."""
+    buf = torch.empty(int(batch.plan.img_bytes), dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+    nb = buf.numpy()
+    for img, ln in zip(images, batch.lines):
+        a = np.ascontiguousarray(img, dtype=np.uint8)
+        assert a.shape == (TILE_H, int(ln["width"]), 3), (a.shape, int(ln["width"]))
+        off = int(ln["img_off"])
+        nb[off:off + a.size] = a.reshape(-1)
+    return buf
+
+
+def _s(batch): return stream_ptr(batch.device)
+
+
+def tile_extract_f16(batch: LineBatch, d_rgb: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((batch.n_tiles, TILE_H, TILE_W, CIN_PAD), dtype=torch.float16, device=batch.device)
+    _lib.check(_lib.lib().sd_tile_extract_f16(d_rgb.data_ptr(), batch.d_lines.data_ptr(), batch.n_lines, batch.n_tiles,
+                                              out.data_ptr(), _s(batch)), "sd_tile_extract_f16")
+    return out
+
+
+def tile_extract_u8(batch: LineBatch, d_rgb: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((batch.n_tiles, 3, TILE_H, TILE_W), dtype=torch.uint8, device=batch.device)
+    _lib.check(_lib.lib().sd_tile_extract_u8(d_rgb.data_ptr(), batch.d_lines.data_ptr(), batch.n_lines, batch.n_tiles,
+                                             out.data_ptr(), _s(batch)), "sd_tile_extract_u8")
+    return out
+
+
+def glue_u8(batch: LineBatch, tiles_u8: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    assert tiles_u8.dtype == torch.uint8 and tiles_u8.is_contiguous() and tiles_u8.numel() == batch.n_tiles * TILE_H * TILE_W
+    if out is None:
+        out = torch.empty(batch.px_total, dtype=torch.uint8, device=batch.device)
+    _lib.check(_lib.lib().sd_glue_u8(tiles_u8.data_ptr(), batch.n_tiles, batch.d_lines.data_ptr(), batch.n_lines,
+                                     batch.px_total, out.data_ptr(), _s(batch)), "sd_glue_u8")
+    return out
+
+
+def glue_threshold_f16(batch: LineBatch, prob16: torch.Tensor, bin_thr=0.5, on_value=255) -> torch.Tensor:
+    assert prob16.dtype == torch.float16 and prob16.is_contiguous() and prob16.numel() == batch.n_tiles * TILE_H * TILE_W
+    out = torch.empty(batch.px_total, dtype=torch.uint8, device=batch.device)
+    _lib.check(_lib.lib().sd_glue_threshold_f16(prob16.data_ptr(), batch.n_tiles, batch.d_lines.data_ptr(), batch.n_lines,
+                                                batch.px_total, float(bin_thr), int(on_value), out.data_ptr(), _s(batch)),
+               "sd_glue_threshold_f16")
+    return out
+
+
+def ccl_label(batch: LineBatch, planes: torch.Tensor, work: torch.Tensor | None = None):
+    """-> (labels int32 packed planes, num int32[n_lines] incl. background)."""
+    L = _lib.lib()
+    need = L.sd_ccl_workspace_bytes(batch.blk_total, batch.n_lines)
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=torch.uint8, device=batch.device)
+    labels = torch.empty(batch.px_total, dtype=torch.int32, device=batch.device)
+    num = torch.empty(batch.n_lines, dtype=torch.int32, device=batch.device)
+    _lib.check(L.sd_ccl_label(planes.data_ptr(), batch.d_lines.data_ptr(), batch.n_lines, batch.px_total, batch.blk_total,
+                              labels.data_ptr(), num.data_ptr(), work.data_ptr(), _s(batch)), "sd_ccl_label")
+    return labels, num
+
+
+def island_stats(batch: LineBatch, labels: torch.Tensor, num_host: np.ndarray):
+    """-> (stats int32 (rows,5) = x,y,w,h,area per label, stat_off int64[n_lines+1] host, d_stat_off)."""
+    counts = np.asarray(num_host, dtype=np.int64) - 1
+    stat_off = np.zeros(batch.n_lines + 1, np.int64)
+    np.cumsum(counts, out=stat_off[1:])
+    rows = int(stat_off[-1])
+    d_off = torch.from_numpy(stat_off[:-1].copy()).to(batch.device)
+    stats = torch.empty((max(rows, 1), 5), dtype=torch.int32, device=batch.device)
+    _lib.check(_lib.lib().sd_island_stats(labels.data_ptr(), batch.d_lines.data_ptr(), batch.n_lines, batch.px_total,
+                                          d_off.data_ptr(), rows, stats.data_ptr(), _s(batch)), "sd_island_stats")
+    return stats[:rows], stat_off, d_off
+
+
+def island_boxes(stats_line: np.ndarray, W: int, H: int = TILE_H, margin: int = MARGIN):
+    """helper/partition.py:19-24: margin-expanded boxes (xs, ys, xf, yf)."""
+    x, y, w, h = (stats_line[:, k].astype(np.int64) for k in range(4))
+    xs = np.maximum(x - margin, 0); ys = np.maximum(y - margin, 0)
+    xf = np.minimum(x + w + margin + 1, W); yf = np.minimum(y + h + margin + 1, H)
+    return xs, ys, xf, yf
+
+
+def group_line(stats_line: np.ndarray, W: int, target_w: int = TILE_H, margin: int = MARGIN):
+    """Grouping half of group_islands (helper/partition.py:38-69) from stats.
+    Returns (groups: list of member label arrays (1-based), boxes int64 (g,4) = left, top, right, bottom)."""
+    n = len(stats_line)
+    if n == 0:
+        return [], np.zeros((0, 4), np.int64)
+    xs, ys, xf, yf = island_boxes(stats_line, W, margin=margin)
+    # sort_islands (:90-98): the SAME np.argsort call on a Python list of ints (tie order)
+    order = np.argsort([int(v) for v in xs])
+    iv = np.stack([xs[order], xf[order]], axis=1)
+    groups = _lib.group_intervals(iv, target_w)
+    out_groups, boxes = [], np.zeros((len(groups), 4), np.int64)
+    for g, members in enumerate(groups):
+        idx = order[np.asarray(members, dtype=np.int64)]
+        boxes[g] = (xs[idx].min(), ys[idx].min(), xf[idx].max(), yf[idx].max())
+        out_groups.append(idx + 1)
+    return out_groups, boxes
+
+
+def group_canvases(batch: LineBatch, labels: torch.Tensor, stat_off: np.ndarray, d_stat_off: torch.Tensor,
+                   line_groups, line_boxes):
+    """Device canvases for every group of every line.
+    line_groups[l] = list of member-label arrays, line_boxes[l] = (g,4) boxes.
+    Returns list per line of [(canvas u8 (h,w), (top, left))]."""
+    rows = int(stat_off[-1])
+    n_groups = sum(len(g) for g in line_groups)
+    if n_groups == 0:
+        return [[] for _ in line_groups]
+    table = np.zeros((n_groups, 6), np.int64)
+    group_of = np.full(max(rows, 1), -1, np.int32)
+    g = 0
+    off = 0
+    for l, (groups, boxes) in enumerate(zip(line_groups, line_boxes)):
+        for members, (left, top, right, bottom) in zip(groups, boxes):
+            table[g] = (l, left, top, right, bottom, off)
+            group_of[stat_off[l] + members - 1] = g
+            off += int((right - left) * (bottom - top))
+            g += 1
+    d_table = torch.from_numpy(table).to(batch.device)
+    d_gof = torch.from_numpy(group_of).to(batch.device)
+    canvas = torch.empty(max(off, 1), dtype=torch.uint8, device=batch.device)
+    _lib.check(_lib.lib().sd_group_canvas(labels.data_ptr(), batch.d_lines.data_ptr(), d_table.data_ptr(), n_groups,
+                                          d_gof.data_ptr(), d_stat_off.data_ptr(), canvas.data_ptr(), _s(batch)),
+               "sd_group_canvas")
+    host = canvas.cpu().numpy()
+    out = [[] for _ in line_groups]
+    for row in table:
+        l, left, top, right, bottom, o = (int(v) for v in row)
+        h, w = bottom - top, right - left
+        out[l].append((host[o:o + h * w].reshape(h, w), (np.int64(top), np.int64(left))))
+    return out
+
+
+class Segmenter:
+    """Batched text segmentation of many line images on ONE GPU:
+    tile -> Attention-UNet -> glue/threshold -> CCL -> island boxes -> group canvases.
+
+    Equivalent to, per line, `BinarizationSession.binarize_image` + `main.py:108`
+    + `get_binarized_islands` + `group_islands` of the reference, but every stage
+    runs once over the whole batch."""
+
+    def __init__(self, engine: UNetEngine, bin_thr: float = 0.5, margin: int = MARGIN):
+        self.engine = engine
+        self.device = engine.device
+        self.bin_thr = bin_thr
+        self.margin = margin
+
+    def binarize(self, images, d_rgb: torch.Tensor | None = None, batch: LineBatch | None = None):
+        """-> (batch, mask planes u8 {0,255} packed on device)."""
+        with torch.cuda.device(self.device):
+            if batch is None:
+                batch = plan_batch([im.shape[1] for im in images], self.device)
+            if d_rgb is None:
+                d_rgb = pack_lines_rgb(images, batch).to(self.device, non_blocking=True)
+            tiles = tile_extract_f16(batch, d_rgb)
+            masks = torch.empty((batch.n_tiles, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+            mt = self.engine.max_tiles
+            for s in range(0, batch.n_tiles, mt):
+                self.engine.forward_into(tiles[s:s + mt], masks[s:s + mt], self.bin_thr)
+            planes = glue_u8(batch, masks)
+        return batch, planes
+
+    def partition(self, batch: LineBatch, planes: torch.Tensor, want_canvases: bool = True):
+        """mask planes -> per line dict(labels?, num, stats, groups, boxes, canvases)."""
+        with torch.cuda.device(self.device):
+            labels, num = ccl_label(batch, planes)
+            num_h = num.cpu().numpy()
+            stats, stat_off, d_off = island_stats(batch, labels, num_h)
+            stats_h = stats.cpu().numpy()
+            line_groups, line_boxes = [], []
+            for l in range(batch.n_lines):
+                g, b = group_line(stats_h[stat_off[l]:stat_off[l + 1]], batch.widths[l], TILE_H, self.margin)
+                line_groups.append(g); line_boxes.append(b)
+            canv = group_canvases(batch, labels, stat_off, d_off, line_groups, line_boxes) if want_canvases else None
+        return {"labels": labels, "num": num_h, "stats": stats_h, "stat_off": stat_off,
+                "groups": line_groups, "boxes": line_boxes, "canvases": canv}
+
+    def segment(self, images):
+        batch, planes = self.binarize(images)
+        res = self.partition(batch, planes)
+        res["batch"] = batch
+        res["planes"] = planes
+        return res

@@ -1,0 +1,225 @@
+"""GPU parity of the bandwidth-bound stages against the oracle (bit-exact)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import segmentation_ref as O
+from stroke_derenderer_b200 import segment as S
+from stroke_derenderer_b200.synth import config_widths, ink_mask, synth_dense_mask, synth_line
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _batch(images, dev=0):
+    device = torch.device("cuda", dev)
+    batch = S.plan_batch([im.shape[1] for im in images], device)
+    d_rgb = S.pack_lines_rgb(images, batch).to(device)
+    return batch, d_rgb
+
+
+WIDTHS = [1, 2, 100, 383, 384, 385, 639, 640, 1000, 1536, 3072, 3840, 6144, 16384, 20480, 21000]
+
+
+def test_tile_extract_u8_matches_reference_golden(cuda_device, golden):
+    for W in WIDTHS:
+        img = np.random.default_rng(W).integers(0, 256, (128, W, 3), dtype=np.uint8)
+        batch, d_rgb = _batch([img])
+        stack = S.tile_extract_u8(batch, d_rgb).cpu().numpy()
+        g = golden["geometry"][str(W)]
+        assert stack.shape[0] == g["n"] and batch.stack_widths()[0] == g["widths"], W
+        assert sha(stack) == g["stack_sha"], W
+
+
+def test_tile_extract_batch_vs_oracle(cuda_device):
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (128, int(w), 3), dtype=np.uint8) for w in [300, 1000, 384, 5, 2222, 777]]
+    batch, d_rgb = _batch(imgs)
+    stack = S.tile_extract_u8(batch, d_rgb).cpu().numpy()
+    ref, idx, widths, iw = O.cut_and_stack(imgs, (1, 3, 128, 384), 64)
+    assert np.array_equal(stack, ref)
+    assert batch.stack_indices() == idx and batch.stack_widths() == widths
+    # fp16 NHWC8 form == np.float16(np.float32(x / 255.)) of the same cut, channels 3..7 zero
+    t16 = S.tile_extract_f16(batch, d_rgb).cpu().numpy()
+    want = (ref / 255.).astype(np.float32).astype(np.float16).transpose(0, 2, 3, 1)
+    assert np.array_equal(t16[..., :3], want)
+    assert not t16[..., 3:].any()
+
+
+def test_u8_to_half_all_values(cuda_device):
+    img = np.zeros((128, 256, 3), np.uint8)
+    img[:, :, 0] = np.arange(256)[None, :]
+    img[:, :, 1] = np.arange(256)[None, ::-1]
+    img[:, :, 2] = 7
+    batch, d_rgb = _batch([img])
+    t16 = S.tile_extract_f16(batch, d_rgb).cpu().numpy()
+    want = (img[:, :, :] / 255.).astype(np.float32).astype(np.float16)
+    assert np.array_equal(t16[0, :, :256, :3], want)
+
+
+def test_glue_u8_matches_reference_golden(cuda_device, golden):
+    for W in WIDTHS:
+        g = golden["geometry"][str(W)]
+        out = (np.random.default_rng(W + 1).random((g["n"], 1, 128, 384)) < 0.3).astype(np.uint8) * 255
+        batch = S.plan_batch([W], torch.device("cuda", 0))
+        planes = S.glue_u8(batch, torch.from_numpy(out[:, 0]).cuda().contiguous())
+        glued = batch.plane(planes, 0).cpu().numpy()
+        assert glued.shape == (128, W)
+        assert int(glued.sum(dtype=np.int64)) == g["glue_sum"], W
+        assert sha(glued[:, :, None]) == g["glue_sha"], W
+        # pitch padding must be zero (CCL relies on it)
+        ln = batch.lines[0]
+        full = planes[:128 * int(ln["pitch"])].view(128, int(ln["pitch"])).cpu().numpy()
+        assert not full[:, W:].any()
+
+
+def test_glue_random_values_and_threshold(cuda_device):
+    rng = np.random.default_rng(11)
+    widths = [300, 1000, 384, 4321, 640]
+    batch = S.plan_batch(widths, torch.device("cuda", 0))
+    n = batch.n_tiles
+    vals = rng.integers(0, 256, (n, 1, 128, 384), dtype=np.uint8)        # arbitrary u8 -> true max semantics
+    planes = S.glue_u8(batch, torch.from_numpy(vals[:, 0]).cuda().contiguous())
+    ref = O.reconstruct_images(vals, widths, batch.stack_indices(), batch.stack_widths(), 64)
+    for i in range(len(widths)):
+        assert np.array_equal(batch.plane(planes, i).cpu().numpy(), ref[i][:, :, 0]), widths[i]
+    prob = rng.random((n, 128, 384)).astype(np.float16)
+    prob[0, 0, :8] = [0.5, 0.5005, 0.4995, 0.0, 1.0, 0.25, 0.75, 0.5]
+    pl = S.glue_threshold_f16(batch, torch.from_numpy(prob).cuda(), 0.5, 255)
+    binv = (255 * (prob.astype(np.float32) > 0.5)).astype(np.uint8)[:, None]
+    ref = O.reconstruct_images(binv, widths, batch.stack_indices(), batch.stack_widths(), 64)
+    for i in range(len(widths)):
+        assert np.array_equal(batch.plane(pl, i).cpu().numpy(), ref[i][:, :, 0]), widths[i]
+
+
+def test_cut_identity_glue_roundtrip_full_size(cuda_device):
+    """Size-independent property at BASELINE config-3 scale: cut -> identity on channel 0 -> glue == input."""
+    widths = config_widths(64)
+    rng = np.random.default_rng(5)
+    imgs = [rng.integers(0, 256, (128, int(w), 3), dtype=np.uint8) for w in widths]
+    batch, d_rgb = _batch(imgs)
+    stack = S.tile_extract_u8(batch, d_rgb)
+    planes = S.glue_u8(batch, stack[:, 0].contiguous())
+    for i, im in enumerate(imgs):
+        assert np.array_equal(batch.plane(planes, i).cpu().numpy(), im[:, :, 0])
+
+
+def _pack_masks(masks, dev=0):
+    device = torch.device("cuda", dev)
+    batch = S.plan_batch([m.shape[1] for m in masks], device)
+    host = np.zeros(batch.px_total, np.uint8)
+    for m, ln in zip(masks, batch.lines):
+        off, pitch = int(ln["px_off"]), int(ln["pitch"])
+        host[off:off + 128 * pitch].reshape(128, pitch)[:, :m.shape[1]] = m
+    return batch, torch.from_numpy(host).to(device)
+
+
+def test_ccl_labels_match_opencv_golden(cuda_device, golden, golden_arrays):
+    names = list(golden["islands"].keys())
+    masks = []
+    for nme in names:
+        shp = golden["islands"][nme]["shape"]
+        masks.append(np.unpackbits(golden_arrays[f"{nme}_mask"])[:shp[0] * shp[1]].reshape(shp))
+    batch, planes = _pack_masks(masks)
+    labels, num = S.ccl_label(batch, planes)
+    num = num.cpu().numpy()
+    for i, nme in enumerate(names):
+        assert int(num[i]) == golden["islands"][nme]["num"], nme
+        got = batch.plane(labels, i).cpu().numpy()
+        assert np.array_equal(got, golden_arrays[f"{nme}_labels"]), nme
+
+
+def test_ccl_random_masks_vs_cv2(cuda_device):
+    import cv2
+    rng = np.random.default_rng(0)
+    masks = []
+    for t in range(48):
+        W = int(rng.integers(1, 1500))
+        p = float(rng.choice([0.02, 0.1, 0.3, 0.5, 0.7]))
+        m = (rng.random((128, W)) < p).astype(np.uint8)
+        if t % 3 == 0:
+            m = cv2.dilate(m, np.ones((2, 2), np.uint8))
+        masks.append(m)
+    masks += [np.zeros((128, 33), np.uint8), np.ones((128, 17), np.uint8), np.eye(128, dtype=np.uint8),
+              np.fliplr(np.eye(128, dtype=np.uint8)).copy()]
+    batch, planes = _pack_masks(masks)
+    labels, num = S.ccl_label(batch, planes)
+    num_h = num.cpu().numpy()
+    stats, stat_off, _ = S.island_stats(batch, labels, num_h)
+    stats = stats.cpu().numpy()
+    for i, m in enumerate(masks):
+        n, ref, st, _ = cv2.connectedComponentsWithStats(m)
+        assert int(num_h[i]) == n, i
+        assert np.array_equal(batch.plane(labels, i).cpu().numpy(), ref), i
+        assert np.array_equal(stats[stat_off[i]:stat_off[i + 1]], st[1:]), i
+
+
+def test_ccl_dense_config5(cuda_device):
+    import cv2
+    masks = [synth_dense_mask(16384, 0.003, 0), synth_dense_mask(16384, 0.01, 1)]
+    batch, planes = _pack_masks(masks)
+    labels, num = S.ccl_label(batch, planes)
+    for i, m in enumerate(masks):
+        n, ref = cv2.connectedComponents(m)
+        assert int(num[i].item()) == n
+        assert np.array_equal(batch.plane(labels, i).cpu().numpy(), ref)
+
+
+def test_partition_matches_reference_golden(cuda_device, golden, golden_arrays):
+    from stroke_derenderer_b200.evaluate_strokes import StrokeEstimationSession
+    names = [k for k in golden["islands"] if golden["islands"][k]["num"] > 1]
+    masks = []
+    for nme in names:
+        shp = golden["islands"][nme]["shape"]
+        masks.append(np.unpackbits(golden_arrays[f"{nme}_mask"])[:shp[0] * shp[1]].reshape(shp))
+    se = StrokeEstimationSession()
+    parts = se.get_partitions_batch(masks)
+    batch, planes = _pack_masks(masks)
+    seg = S.Segmenter.__new__(S.Segmenter); seg.device = torch.device("cuda", 0); seg.margin = 2
+    res = seg.partition(batch, planes)
+    for i, nme in enumerate(names):
+        g = golden["islands"][nme]
+        canv = res["canvases"][i]
+        assert len(canv) == len(g["groups"]), nme
+        for (c, (top, left)), gg in zip(canv, g["groups"]):
+            assert [int(top), int(left)] == gg["pos"] and list(c.shape) == gg["shape"] and sha(c) == gg["sha"], nme
+        assert len(parts[i]) == len(g["partitions"])
+        for p, gp in zip(parts[i], g["partitions"]):
+            assert [int(p["translate1"][0]), int(p["translate1"][1])] == gp["translate1"]
+            assert p["ratio"] == gp["ratio"] and list(p["translate2"]) == gp["translate2"]
+            assert sha(p["image"]) == gp["image_sha"] and sha(p["image_input"]) == gp["input_sha"]
+
+
+def test_get_binarized_islands_dropin(cuda_device, golden, golden_arrays):
+    from stroke_derenderer_b200.helper.partition import get_binarized_islands, group_islands
+    for nme in ["line300", "line1000", "long_island", "full40", "empty64"]:
+        g = golden["islands"][nme]
+        shp = g["shape"]
+        m = np.unpackbits(golden_arrays[f"{nme}_mask"])[:shp[0] * shp[1]].reshape(shp)
+        islands, lab, num = get_binarized_islands(m, margin=2)
+        assert num == g["num"] and np.array_equal(lab, golden_arrays[f"{nme}_labels"])
+        assert len(islands) == len(g["islands"])
+        for (c, pos), gi in zip(islands, g["islands"]):
+            assert list(pos) == gi["pos"] and list(c.shape) == gi["shape"] and sha(c) == gi["sha"]
+        groups = group_islands(islands, (128, 128)) if islands else []
+        assert len(groups) == len(g["groups"])
+        for (c, pos), gg in zip(groups, g["groups"]):
+            assert [int(pos[0]), int(pos[1])] == gg["pos"] and sha(c) == gg["sha"]
+
+
+def test_split_module_dropin(cuda_device):
+    from stroke_derenderer_b200.helper.split import cut_and_stack, reconstruct_images
+    rng = np.random.default_rng(21)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(128, 300), (128, 1000), (200, 1000)]]
+    a = cut_and_stack(imgs, (1, 3, 128, 384), 64)
+    b = O.cut_and_stack(imgs, (1, 3, 128, 384), 64)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+    out = rng.integers(0, 2, (a[0].shape[0], 1, 128, 384)).astype(np.uint8) * 255
+    ra = reconstruct_images(out, a[3], a[1], a[2], 64)
+    rb = O.reconstruct_images(out, b[3], b[1], b[2], 64)
+    assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
