@@ -1,0 +1,123 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the
+header declares, host planners match the oracle, and the product path fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import segmentation_ref as O
+from stroke_derenderer_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "sd_b200.h").read_text()
+    declared = set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libsd_b200.so does not export {name}"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert L.sd_version() >= 100
+
+
+def test_line_struct_layout_matches_header():
+    hdr = (ROOT / "include" / "sd_b200.h").read_text()
+    body = hdr[hdr.index("typedef struct sd_line {"):hdr.index("} sd_line;")]
+    fields = re.findall(r"\b(int64_t|int32_t)\s+(\w+);", body)
+    assert [f for _, f in fields] == list(_lib.LINE_DTYPE.names)
+    assert sum(8 if t == "int64_t" else 4 for t, _ in fields) == _lib.LINE_DTYPE.itemsize
+
+
+def test_plan_lines_matches_oracle_geometry():
+    widths = [1, 2, 100, 383, 384, 385, 639, 640, 1000, 1536, 3072, 6144, 16384, 20480, 21000, 32768]
+    lines, plan = _lib.plan_lines(widths)
+    t = 0
+    for ln, W in zip(lines, widths):
+        starts, ws = O.tile_geometry(W)
+        assert ln["n_tiles"] == len(ws) and ln["first_tile"] == t
+        if len(ws) > 1:
+            assert ln["wu"] == starts[1]
+        assert ln["pitch"] % 16 == 0 and ln["pitch"] >= W and ln["bw"] * 2 == ln["pitch"]
+        assert ln["px_off"] % 16 == 0 and ln["blk_off"] % 2048 == 0 and ln["img_off"] % 16 == 0
+        t += len(ws)
+    assert plan.n_tiles == t and plan.n_lines == len(widths)
+    assert plan.px_total == int(sum(128 * ln["pitch"] for ln in lines))
+
+
+def test_plan_lines_rejects_bad_input():
+    with pytest.raises(_lib.SdError):
+        _lib.plan_lines([100, 0])
+    with pytest.raises(_lib.SdError):
+        _lib.plan_lines([100], tile_w=64, overlap=64)
+
+
+def test_native_group_intervals_golden(golden):
+    for case in golden["group_intervals"]:
+        assert _lib.group_intervals(case["intervals"], 128) == case["groups"]
+
+
+def test_native_group_intervals_random_vs_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        n = int(rng.integers(0, 80))
+        a = np.sort(rng.integers(0, 2000, n))
+        w = np.where(rng.random(n) < 0.2, rng.integers(129, 700, n), rng.integers(1, 100, n))
+        iv = [(int(x), int(x + y)) for x, y in zip(a, w)]
+        assert _lib.group_intervals(iv, 128) == O.group_intervals(iv, 128)
+
+
+def test_group_line_matches_oracle_group_islands(golden, golden_arrays):
+    """stats closed form == get_binarized_islands + group_islands, from cv2 stats."""
+    import cv2
+    from stroke_derenderer_b200.segment import group_line
+    for name in ["line300", "line1000", "line3072", "dense2048", "long_island"]:
+        shp = golden["islands"][name]["shape"]
+        m = np.unpackbits(golden_arrays[f"{name}_mask"])[:shp[0] * shp[1]].reshape(shp)
+        n, labels, stats, _ = cv2.connectedComponentsWithStats(m)
+        groups, boxes = group_line(stats[1:], shp[1])
+        want = golden["islands"][name]["groups"]
+        assert len(groups) == len(want)
+        for members, (l, t, r, b), g in zip(groups, boxes, want):
+            assert [int(t), int(l)] == g["pos"] and [int(b - t), int(r - l)] == g["shape"]
+            canvas = np.isin(labels[t:b, l:r], members).astype(np.uint8)
+            import hashlib
+            assert hashlib.sha256(canvas.tobytes()).hexdigest() == g["sha"]
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute entry points must fail, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    L = _lib.lib()
+    assert L.sd_cuda_available() == 0
+    h = C.c_void_p()
+    assert L.sd_engine_create(0, 8, 128, 384, C.byref(h)) == -2      # SD_ECUDA
+    assert b"no CUDA device" in L.sd_last_error()
+    from stroke_derenderer_b200.engine import UNetEngine
+    with pytest.raises(_lib.SdError):
+        UNetEngine({}, device=0)
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "stroke_derenderer_b200"
+    for p in list(pkg.rglob("*.py")) + [ROOT / "main.py"]:
+        if p.exists():
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), re.M), p
+
+
+def test_session_config_semantics(tmp_path):
+    """evaluate_binarize.py:30-45: defaults, kwargs, and JSON overriding kwargs."""
+    import json
+    from stroke_derenderer_b200.evaluate_binarize import BinarizationSession
+    bs = BinarizationSession()
+    assert (bs.height, bs.width, bs.channels, bs.overlap, bs.bin_thr, bs.minibatch) == (128, 384, 3, 64, 0.5, 8)
+    cfg = tmp_path / "c.json"
+    cfg.write_text(json.dumps({"bin_thr": 0.3}))
+    bs = BinarizationSession(configs_path=str(cfg), bin_thr=0.9, minibatch=4)
+    assert bs.bin_thr == 0.3 and bs.minibatch == 4
