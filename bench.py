@@ -163,7 +163,7 @@ def run_gpu(args):
     mine = shard_lines(widths, world)[rank]
     images = make_lines(mine, widths)
     engine = UNetEngine(parity_state(), device=local, max_tiles=args.max_tiles)
-    job = LineSegmentationJob(engine, images)
+    job = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk)
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,10 +207,11 @@ def run_gpu(args):
     # ---- per-kernel rooflines, measured live with CUDA events (instrumented pass, rank 0) ----
     roof, extra = None, {}
     if rank == 0:
-        nb = min(args.max_tiles, job.n_tiles)
+        c0 = job.chunks[0]
+        nb = min(args.max_tiles, c0.batch.n_tiles)
         engine.enable_timing(True)
-        engine.forward_into(job.tiles[:nb], job.masks[:nb], 0.5)
-        engine.forward_into(job.tiles[:nb], job.masks[:nb], 0.5)
+        engine.forward_into(c0.tiles[:nb], c0.masks[:nb], 0.5)
+        engine.forward_into(c0.tiles[:nb], c0.masks[:nb], 0.5)
         lt = engine.layer_times()
         engine.enable_timing(False)
         umma_ms = sum(ms for name, ms in lt if not name.startswith(("pool", "Conv1.0")))
@@ -234,18 +235,20 @@ def run_gpu(args):
                 fn()
             b.record(); torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
-        bt = job.batch
+        ch0 = job.chunks[0]
+        bt = ch0.batch
         sum_w = int(sum(bt.widths)); sum_wt = int(sum(sum(w) for w in bt.stack_widths()))
         px = 128 * sum_w
-        t_ext = ev_time(lambda: S.tile_extract_f16(bt, job.d_rgb, out=job.tiles))
-        t_glue = ev_time(lambda: S.glue_u8(bt, job.masks, out=job.planes))
+        t_ext = ev_time(lambda: S.tile_extract_f16(bt, ch0.d_rgb, out=ch0.tiles))
+        t_glue = ev_time(lambda: S.glue_u8(bt, ch0.masks, out=ch0.planes))
         work = torch.empty(_lib.lib().sd_ccl_workspace_bytes(bt.blk_total, bt.n_lines), dtype=torch.uint8, device="cuda")
-        t_ccl = ev_time(lambda: S.ccl_label(bt, job.planes, work))
+        t_ccl = ev_time(lambda: S.ccl_label(bt, ch0.planes, work))
         hb = peaks["hbm_gbs"]
         b_ext = 3 * 128 * sum_wt + bt.n_tiles * 128 * 384 * 16
         b_glue = 128 * sum_wt + px
         b_ccl = 5 * px
         extra["hbm_stages"] = {
+            "sample": f"chunk 0: {bt.n_lines} lines, {bt.n_tiles} tiles, {px} px",
             "tile_extract_f16": {"ms": t_ext, "GBps": b_ext / t_ext / 1e6, "frac": b_ext / t_ext / 1e6 / hb},
             "glue_u8": {"ms": t_glue, "GBps": b_glue / t_glue / 1e6, "frac": b_glue / t_glue / 1e6 / hb},
             "ccl_label(6 launches)": {"ms": t_ccl, "GBps": b_ccl / t_ccl / 1e6, "frac": b_ccl / t_ccl / 1e6 / hb},
@@ -289,6 +292,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--max-tiles", type=int, default=128)
+    ap.add_argument("--lines-per-chunk", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_gpu(args))

@@ -106,6 +106,18 @@ int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, int overlap,
 int sd_group_intervals(const int64_t* h_intervals_ab, int n, int64_t width,
                        int32_t* h_members, int32_t* h_group_start);
 
+/* Batched island clustering of many lines from cv2-layout stats (the closed form of
+ * get_binarized_islands + sort_islands + group_islands, helper/partition.py:17-26,31-69;
+ * SURVEY.md A.5).  h_order holds, per line, np.argsort of the margin-expanded left
+ * edges xs (the caller makes that exact numpy call: its tie order is observable,
+ * SURVEY.md A.4).  Outputs: h_groups [n_groups][6] = (line, left, top, right,
+ * bottom, canvas_off) in the reference's group order, h_group_of[row] = group id of
+ * each island, h_line_group_start[n_lines+1].  Returns n_groups, or < 0. */
+int64_t sd_group_lines(const int32_t* h_stats, const int64_t* h_stat_off, const int32_t* h_widths,
+                       int n_lines, const int64_t* h_order, int margin, int img_h, int64_t target_w,
+                       int64_t* h_groups, int32_t* h_group_of, int64_t* h_line_group_start,
+                       int64_t* h_canvas_bytes);
+
 /* ---- bandwidth-bound device stages --------------------------------------- */
 /* K1a: split_image + pad_image + HWC->CHW stack (helper/split.py:10-54,81-84):
  * packed RGB lines -> (n_tiles, 3, 128, tile_w) u8, bit-exact. */

@@ -48,6 +48,8 @@ EXPORTS = {
     "sd_launch_count": (C.c_int64, []),
     "sd_plan_lines": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Plan)]),
     "sd_group_intervals": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "sd_group_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_tile_extract_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_tile_extract_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_glue_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -128,3 +130,30 @@ def group_intervals(intervals, width: int):
     if ng < 0:
         check(ng, "sd_group_intervals")
     return [members[starts[g]:starts[g + 1]].tolist() for g in range(ng)]
+
+
+def group_lines(stats, stat_off, widths, margin: int = 2, img_h: int = 128, target_w: int = 128):
+    """Batched clustering of every line's islands (sd_group_lines).
+    stats: (rows,5) int32 cv2 layout; stat_off: int64[n_lines+1]; widths: per line.
+    -> (groups int64 (n_groups,6), group_of int32 (rows,), line_group_start int64[n_lines+1], canvas_bytes)."""
+    stats = np.ascontiguousarray(stats, dtype=np.int32).reshape(-1, 5)
+    stat_off = np.ascontiguousarray(stat_off, dtype=np.int64)
+    widths = np.ascontiguousarray(widths, dtype=np.int32)
+    rows, n_lines = len(stats), len(widths)
+    # sort_islands (helper/partition.py:90-98): np.argsort of the left edges, per line, default kind
+    xs = np.maximum(stats[:, 0].astype(np.int64) - margin, 0)
+    order = np.empty(rows, np.int64)
+    for l in range(n_lines):
+        a, b = stat_off[l], stat_off[l + 1]
+        if b > a:
+            order[a:b] = np.argsort(xs[a:b])
+    groups = np.zeros((max(rows, 1), 6), np.int64)
+    group_of = np.full(max(rows, 1), -1, np.int32)
+    lgs = np.zeros(n_lines + 1, np.int64)
+    cbytes = C.c_int64()
+    ng = lib().sd_group_lines(stats.ctypes.data, stat_off.ctypes.data, widths.ctypes.data, n_lines, order.ctypes.data,
+                              margin, img_h, target_w, groups.ctypes.data, group_of.ctypes.data, lgs.ctypes.data,
+                              C.byref(cbytes))
+    if ng < 0:
+        check(int(ng), "sd_group_lines")
+    return groups[:ng], group_of[:rows], lgs, int(cbytes.value)

@@ -611,15 +611,20 @@ extern "C" int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, i
   return SD_OK;
 }
 
-extern "C" int sd_group_intervals(const int64_t* iv, int n, int64_t width, int32_t* members, int32_t* group_start) {
-  SD_REQUIRE(n >= 0 && (n == 0 || (iv && members)) && group_start, "sd_group_intervals: null argument");
-  // helper/partition.py:255-281: every interval wider than `width` links to all
-  // intervals it contains (scan from the left, stop at the first a_i > b_o).
-  std::vector<std::vector<int>> adj(n);
+namespace sd {
+// group_intervals + group_connections + add_to_group (helper/partition.py:248-358).
+// iv: n pairs (a,b) sorted by a.  Appends member indices to `members`, group ends to `ends`.
+static void group_intervals_core(const int64_t* iv, int n, int64_t width, std::vector<int32_t>& members,
+                                 std::vector<int32_t>& ends) {
+  // :255-281: every interval wider than `width` links to all intervals it contains
+  // (scan from the left, stop at the first a_i > b_o).
+  std::vector<std::vector<int>> adj;
   std::vector<char> contained(n, 0);
+  bool any_long = false;
   for (int o = 0; o < n; ++o) {
     const int64_t ao = iv[2 * o], bo = iv[2 * o + 1];
     if (bo - ao <= width) continue;
+    if (!any_long) { adj.resize(n); any_long = true; }
     for (int k = 0; k < n; ++k) {
       if (k == o) continue;
       const int64_t ai = iv[2 * k], bi = iv[2 * k + 1];
@@ -630,53 +635,112 @@ extern "C" int sd_group_intervals(const int64_t* iv, int n, int64_t width, int32
       }
     }
   }
-  int ng = 0, nm = 0;
-  group_start[0] = 0;
-  // group_connections / add_to_group (:321-358): pre-order DFS in adjacency
-  // order from each not-yet-grouped node, in index order; the start node is
-  // appended when first reached back from a neighbour.
-  std::vector<char> done(n, 0), seen(n, 0);
-  std::vector<std::pair<int, size_t>> stack;
-  for (int f = 0; f < n; ++f) {
-    if (adj[f].empty() || done[f]) continue;
-    const int g0 = nm;
-    stack.clear();
-    stack.emplace_back(f, 0);
-    while (!stack.empty()) {
-      auto& top = stack.back();
-      if (top.second >= adj[top.first].size()) { stack.pop_back(); continue; }
-      const int nxt = adj[top.first][top.second++];
-      if (!seen[nxt]) {
-        seen[nxt] = 1;
-        members[nm++] = nxt;
-        stack.emplace_back(nxt, 0);
+  // group_connections / add_to_group (:321-358): pre-order DFS in adjacency order from each
+  // not-yet-grouped node, in index order; the start node is appended when first reached back
+  // from a neighbour.
+  if (any_long) {
+    std::vector<char> done(n, 0), seen(n, 0);
+    std::vector<std::pair<int, size_t>> stack;
+    for (int f = 0; f < n; ++f) {
+      if (adj[f].empty() || done[f]) continue;
+      const size_t g0 = members.size();
+      stack.clear();
+      stack.emplace_back(f, 0);
+      while (!stack.empty()) {
+        auto& top = stack.back();
+        if (top.second >= adj[top.first].size()) { stack.pop_back(); continue; }
+        const int nxt = adj[top.first][top.second++];
+        if (!seen[nxt]) {
+          seen[nxt] = 1;
+          members.push_back(nxt);
+          stack.emplace_back(nxt, 0);
+        }
       }
+      for (size_t i = g0; i < members.size(); ++i) { done[members[i]] = 1; seen[members[i]] = 0; }
+      done[f] = 1;
+      if (members.size() > g0) ends.push_back((int32_t)members.size());
     }
-    for (int i = g0; i < nm; ++i) { done[members[i]] = 1; seen[members[i]] = 0; }
-    // `seen` must persist as group membership only within this DFS; members of
-    // earlier groups are excluded through `done` (they are unreachable anyway).
-    for (int i = g0; i < nm; ++i) seen[members[i]] = 0;
-    done[f] = 1;
-    if (nm > g0) group_start[++ng] = nm;
   }
   // greedy packing of the remaining intervals (:287-310)
   int64_t w = 0, left = 0;
-  int cur0 = nm;
+  size_t cur0 = members.size();
   for (int i = 0; i < n; ++i) {
     if (contained[i]) continue;
     const int64_t a = iv[2 * i], b = iv[2 * i + 1];
     const int64_t new_w = std::max(b - left, w);
     if (new_w > width) {
-      if (nm > cur0) group_start[++ng] = nm;
-      cur0 = nm;
-      members[nm++] = i;
+      if (members.size() > cur0) ends.push_back((int32_t)members.size());
+      cur0 = members.size();
+      members.push_back(i);
       w = b - a; left = a;
     } else {
-      members[nm++] = i;
+      members.push_back(i);
       w = new_w;
     }
   }
-  if (nm > cur0) group_start[++ng] = nm;
+  if (members.size() > cur0) ends.push_back((int32_t)members.size());
+}
+}  // namespace sd
+
+extern "C" int sd_group_intervals(const int64_t* iv, int n, int64_t width, int32_t* members, int32_t* group_start) {
+  SD_REQUIRE(n >= 0 && (n == 0 || (iv && members)) && group_start, "sd_group_intervals: null argument");
+  std::vector<int32_t> mem, ends;
+  group_intervals_core(iv, n, width, mem, ends);
+  for (size_t i = 0; i < mem.size(); ++i) members[i] = mem[i];
+  group_start[0] = 0;
+  for (size_t g = 0; g < ends.size(); ++g) group_start[g + 1] = ends[g];
+  return (int)ends.size();
+}
+
+extern "C" int64_t sd_group_lines(const int32_t* stats, const int64_t* stat_off, const int32_t* widths, int n_lines,
+                                  const int64_t* order, int margin, int img_h, int64_t target_w, int64_t* groups,
+                                  int32_t* group_of, int64_t* line_group_start, int64_t* canvas_bytes) {
+  SD_REQUIRE(stat_off && widths && line_group_start && canvas_bytes && n_lines >= 0, "sd_group_lines: null argument");
+  int64_t ng = 0, off = 0;
+  std::vector<int64_t> iv, xs, ys, xf, yf;
+  std::vector<int32_t> mem, ends;
+  line_group_start[0] = 0;
+  for (int l = 0; l < n_lines; ++l) {
+    const int64_t r0 = stat_off[l];
+    const int n = (int)(stat_off[l + 1] - r0);
+    if (n > 0) {
+      SD_REQUIRE(stats && order && groups && group_of, "sd_group_lines: null argument");
+      const int W = widths[l];
+      xs.resize(n); ys.resize(n); xf.resize(n); yf.resize(n); iv.resize(2 * (size_t)n);
+      for (int k = 0; k < n; ++k) {
+        // helper/partition.py:19-24 (2 px before, 3 px after, clipped to the image)
+        const int32_t* st = stats + (r0 + k) * 5;
+        xs[k] = std::max<int64_t>(st[0] - margin, 0);
+        ys[k] = std::max<int64_t>(st[1] - margin, 0);
+        xf[k] = std::min<int64_t>((int64_t)st[0] + st[2] + margin + 1, W);
+        yf[k] = std::min<int64_t>((int64_t)st[1] + st[3] + margin + 1, img_h);
+      }
+      for (int k = 0; k < n; ++k) {
+        const int64_t o = order[r0 + k];
+        SD_REQUIRE(o >= 0 && o < n, "sd_group_lines: order[%lld] out of range", (long long)(r0 + k));
+        iv[2 * k] = xs[o]; iv[2 * k + 1] = xf[o];          // intervals (xs, xs + crop_w), partition.py:42-46
+      }
+      mem.clear(); ends.clear();
+      group_intervals_core(iv.data(), n, target_w, mem, ends);
+      size_t m0 = 0;
+      for (size_t g = 0; g < ends.size(); ++g) {
+        int64_t left = INT64_MAX, top = INT64_MAX, right = INT64_MIN, bottom = INT64_MIN;
+        for (size_t i = m0; i < (size_t)ends[g]; ++i) {
+          const int64_t k = order[r0 + mem[i]];             // label - 1 of this member
+          left = std::min(left, xs[k]); top = std::min(top, ys[k]);
+          right = std::max(right, xf[k]); bottom = std::max(bottom, yf[k]);
+          group_of[r0 + k] = (int32_t)ng;
+        }
+        int64_t* G = groups + ng * 6;
+        G[0] = l; G[1] = left; G[2] = top; G[3] = right; G[4] = bottom; G[5] = off;
+        off += (right - left) * (bottom - top);
+        ++ng;
+        m0 = ends[g];
+      }
+    }
+    line_group_start[l + 1] = ng;
+  }
+  *canvas_bytes = off;
   return ng;
 }
 

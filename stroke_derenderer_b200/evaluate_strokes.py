@@ -65,10 +65,9 @@ class StrokeEstimationSession:
                 off, pitch = int(ln["px_off"]), int(ln["pitch"])
                 host[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)[:, :m.shape[1]] = np.asarray(m) != 0
             planes = torch.from_numpy(host).to(dev)
-            seg = _seg.Segmenter.__new__(_seg.Segmenter)
-            seg.device, seg.margin = dev, self.margin
-            res = seg.partition(batch, planes)
-        return [self.partitions_from_canvases(c) for c in res["canvases"]]
+            res = _seg.Segmenter(None, margin=self.margin, device=dev).partition(batch, planes)
+            canv = res.canvases
+        return [self.partitions_from_canvases(c) for c in canv]
 
     def load_orts(self, filepaths):
         raise NotImplementedError("stroke-estimator graphs are outside the B200 segmentation path (SURVEY.md 2)")

@@ -52,55 +52,93 @@ def gather_in_order(local_results, local_indices, n_total, world, rank, group=No
     return out
 
 
-class LineSegmentationJob:
-    """One rank's share of a job.  `resident_step` times the hot path with inputs already
-    in HBM; `host_step` is the same call a user makes with host buffers (H2D + D2H inside)."""
+class _Chunk:
+    pass
 
-    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5):
+
+class LineSegmentationJob:
+    """One rank's share of a job, cut into chunks of lines that flow through three streams:
+    copy (H2D of packed lines) -> unet (tile_extract, Attention-UNet, glue) -> part (CCL, stats,
+    host grouping, canvases, D2H).  The UNet stream never waits for the host: while the host
+    clusters the islands of chunk k, the tensor cores are already on chunk k+1.
+
+    `resident_step` times the hot path with inputs already in HBM; `host_step` is the call a
+    user makes with (pinned) host buffers: H2D of the lines and D2H of masks, stats and group
+    canvases are inside it."""
+
+    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 64):
         self.engine = engine
         self.device = engine.device
         self.seg = S.Segmenter(engine, bin_thr=bin_thr)
-        self.images = images
+        self.chunks = []
         with torch.cuda.device(self.device):
-            self.batch = S.plan_batch([im.shape[1] for im in images], self.device)
-            self.h_rgb = S.pack_lines_rgb(images, self.batch, pinned=True)
-            self.d_rgb = self.h_rgb.to(self.device)
-            nt = self.batch.n_tiles
-            self.tiles = torch.empty((nt, TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
-            self.masks = torch.empty((nt, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
-            self.planes = torch.empty(self.batch.px_total, dtype=torch.uint8, device=self.device)
-            self.h_planes = torch.empty(self.batch.px_total, dtype=torch.uint8, pin_memory=True)
+            self.s_copy, self.s_unet, self.s_part = (torch.cuda.Stream(self.device) for _ in range(3))
+            for c0 in range(0, len(images), lines_per_chunk):
+                imgs = images[c0:c0 + lines_per_chunk]
+                ch = _Chunk()
+                ch.index = len(self.chunks)
+                ch.batch = S.plan_batch([im.shape[1] for im in imgs], self.device)
+                ch.h_rgb = S.pack_lines_rgb(imgs, ch.batch, pinned=True)
+                ch.d_rgb = ch.h_rgb.to(self.device)
+                ch.d_rgb_in = torch.empty_like(ch.d_rgb)
+                nt = ch.batch.n_tiles
+                ch.tiles = torch.empty((nt, TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
+                ch.masks = torch.empty((nt, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+                ch.planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, device=self.device)
+                ch.h_planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, pin_memory=True)
+                self.chunks.append(ch)
+        self.n_tiles = sum(c.batch.n_tiles for c in self.chunks)
+        self.n_lines = sum(c.batch.n_lines for c in self.chunks)
 
-    @property
-    def n_tiles(self): return self.batch.n_tiles
-    @property
-    def n_lines(self): return self.batch.n_lines
-
-    def _device_binarize(self, d_rgb):
-        S.tile_extract_f16(self.batch, d_rgb, out=self.tiles)
+    def _binarize(self, ch, d_rgb):
+        S.tile_extract_f16(ch.batch, d_rgb, out=ch.tiles)
         mt = self.engine.max_tiles
-        for s in range(0, self.batch.n_tiles, mt):
-            self.engine.forward_into(self.tiles[s:s + mt], self.masks[s:s + mt], self.seg.bin_thr)
-        S.glue_u8(self.batch, self.masks, out=self.planes)
+        for s in range(0, ch.batch.n_tiles, mt):
+            self.engine.forward_into(ch.tiles[s:s + mt], ch.masks[s:s + mt], self.seg.bin_thr)
+        S.glue_u8(ch.batch, ch.masks, out=ch.planes)
+
+    def _run(self, from_host: bool, canvases: str):
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            for st in (self.s_copy, self.s_unet, self.s_part):
+                st.wait_stream(cur)
+            ready = []
+            for ch in self.chunks:
+                src = ch.d_rgb
+                if from_host:
+                    with torch.cuda.stream(self.s_copy):
+                        ch.d_rgb_in.copy_(ch.h_rgb, non_blocking=True)
+                        ev = torch.cuda.Event(); ev.record(self.s_copy)
+                    self.s_unet.wait_event(ev)
+                    src = ch.d_rgb_in
+                with torch.cuda.stream(self.s_unet):
+                    self._binarize(ch, src)
+                    ev = torch.cuda.Event(); ev.record(self.s_unet)
+                ready.append(ev)
+            results = []
+            with torch.cuda.stream(self.s_part):
+                for ch, ev in zip(self.chunks, ready):
+                    self.s_part.wait_event(ev)
+                    if from_host:
+                        ch.h_planes.copy_(ch.planes, non_blocking=True)
+                    results.append(self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=("chunk", ch.index),
+                                                      zero_copy=True))
+            cur.wait_stream(self.s_unet)
+            cur.wait_stream(self.s_part)
+            if from_host:
+                cur.synchronize()
+        return results
 
     def resident_step(self):
-        with torch.cuda.device(self.device):
-            self._device_binarize(self.d_rgb)
-            return self.seg.partition(self.batch, self.planes, want_canvases=True)
+        return self._run(False, "device")
 
     def host_step(self):
-        """Host buffers in, host results out."""
-        with torch.cuda.device(self.device):
-            d_rgb = self.h_rgb.to(self.device, non_blocking=True)
-            self._device_binarize(d_rgb)
-            self.h_planes.copy_(self.planes, non_blocking=True)
-            res = self.seg.partition(self.batch, self.planes, want_canvases=True)   # D2H of counts, stats, canvases inside
-            torch.cuda.current_stream(self.device).synchronize()
-        return res
+        return self._run(True, "host")
 
-    def h2d_bytes(self): return int(self.batch.plan.img_bytes)
+    def h2d_bytes(self):
+        return int(sum(c.batch.plan.img_bytes for c in self.chunks))
 
-    def d2h_bytes(self, res):
-        n = self.batch.px_total + res["num"].nbytes + res["stats"].nbytes
-        n += sum(c.size for line in res["canvases"] for c, _ in line)
+    def d2h_bytes(self, results):
+        n = sum(c.batch.px_total for c in self.chunks)
+        n += sum(r["num"].nbytes + r["stats"].nbytes + r["canvas_bytes"] for r in results)
         return int(n)

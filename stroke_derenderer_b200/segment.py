@@ -200,6 +200,40 @@ def group_canvases(batch: LineBatch, labels: torch.Tensor, stat_off: np.ndarray,
     return out
 
 
+_PINNED = {}
+
+
+def pinned_buffer(key, nbytes: int) -> torch.Tensor:
+    """Grow-only pinned host staging buffers (one per purpose), reused across calls."""
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        _PINNED[key] = buf
+    return buf
+
+
+class PartitionResult(dict):
+    """Result of `Segmenter.partition`: labels / canvas stay on the device, tables on the host."""
+
+    def line_canvases(self, l: int):
+        """[(canvas u8 {0,1} (h,w), (top, left))] of line l, in the reference's group order."""
+        host = self["canvas_host"]
+        if host is None:
+            host = self["canvas"].cpu().numpy()
+            self["canvas_host"] = host
+        a, b = int(self["line_group_start"][l]), int(self["line_group_start"][l + 1])
+        out = []
+        for row in self["groups"][a:b]:
+            _, left, top, right, bottom, o = (int(v) for v in row)
+            h, w = bottom - top, right - left
+            out.append((host[o:o + h * w].reshape(h, w), (np.int64(top), np.int64(left))))
+        return out
+
+    @property
+    def canvases(self):
+        return [self.line_canvases(l) for l in range(len(self["line_group_start"]) - 1)]
+
+
 class Segmenter:
     """Batched text segmentation of many line images on ONE GPU:
     tile -> Attention-UNet -> glue/threshold -> CCL -> island boxes -> group canvases.
@@ -208,9 +242,9 @@ class Segmenter:
     + `get_binarized_islands` + `group_islands` of the reference, but every stage
     runs once over the whole batch."""
 
-    def __init__(self, engine: UNetEngine, bin_thr: float = 0.5, margin: int = MARGIN):
+    def __init__(self, engine: UNetEngine | None, bin_thr: float = 0.5, margin: int = MARGIN, device=None):
         self.engine = engine
-        self.device = engine.device
+        self.device = engine.device if engine is not None else torch.device(device)
         self.bin_thr = bin_thr
         self.margin = margin
 
@@ -229,20 +263,47 @@ class Segmenter:
             planes = glue_u8(batch, masks)
         return batch, planes
 
-    def partition(self, batch: LineBatch, planes: torch.Tensor, want_canvases: bool = True):
-        """mask planes -> per line dict(labels?, num, stats, groups, boxes, canvases)."""
+    def partition(self, batch: LineBatch, planes: torch.Tensor, canvases: str = "host", key="part",
+                  zero_copy: bool = False) -> PartitionResult:
+        """mask planes -> labels, island stats, groups and group canvases for every line.
+        canvases: "host" (copied to pinned host memory), "device" (left in HBM) or "none".
+        zero_copy: host arrays alias the reusable pinned staging buffers of `key` (valid until
+        the next call with the same key) instead of being copied out."""
         with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
             labels, num = ccl_label(batch, planes)
-            num_h = num.cpu().numpy()
+            h_num = pinned_buffer((key, "num"), batch.n_lines * 4)[:batch.n_lines * 4].view(torch.int32)
+            h_num.copy_(num, non_blocking=True)
+            stream.synchronize()
+            num_h = h_num.numpy().copy()
             stats, stat_off, d_off = island_stats(batch, labels, num_h)
-            stats_h = stats.cpu().numpy()
-            line_groups, line_boxes = [], []
-            for l in range(batch.n_lines):
-                g, b = group_line(stats_h[stat_off[l]:stat_off[l + 1]], batch.widths[l], TILE_H, self.margin)
-                line_groups.append(g); line_boxes.append(b)
-            canv = group_canvases(batch, labels, stat_off, d_off, line_groups, line_boxes) if want_canvases else None
-        return {"labels": labels, "num": num_h, "stats": stats_h, "stat_off": stat_off,
-                "groups": line_groups, "boxes": line_boxes, "canvases": canv}
+            rows = int(stat_off[-1])
+            h_stats = pinned_buffer((key, "stats"), max(rows, 1) * 20)[:rows * 20].view(torch.int32).view(rows, 5)
+            h_stats.copy_(stats, non_blocking=True)
+            stream.synchronize()
+            stats_h = h_stats.numpy().copy()
+            groups, group_of, lgs, cbytes = _lib.group_lines(stats_h, stat_off, batch.widths, self.margin, TILE_H, TILE_H)
+            res = PartitionResult(labels=labels, num=num_h, stats=stats_h, stat_off=stat_off, groups=groups,
+                                  group_of=group_of, line_group_start=lgs, canvas=None, canvas_host=None,
+                                  canvas_bytes=cbytes)
+            if canvases != "none" and len(groups):
+                d_table = torch.from_numpy(groups).to(self.device, non_blocking=True)
+                d_gof = torch.from_numpy(group_of).to(self.device, non_blocking=True)
+                canvas = torch.empty(max(cbytes, 1), dtype=torch.uint8, device=self.device)
+                _lib.check(_lib.lib().sd_group_canvas(labels.data_ptr(), batch.d_lines.data_ptr(), d_table.data_ptr(),
+                                                      len(groups), d_gof.data_ptr(), d_off.data_ptr(), canvas.data_ptr(),
+                                                      _s(batch)), "sd_group_canvas")
+                res["canvas"] = canvas[:cbytes]
+                res["_keep"] = (d_table, d_gof, d_off)
+                if canvases == "host":
+                    hb = pinned_buffer((key, "canvas"), cbytes)[:cbytes]
+                    hb.copy_(res["canvas"], non_blocking=True)
+                    stream.synchronize()
+                    res["canvas_host"] = hb.numpy() if zero_copy else hb.numpy().copy()
+            elif canvases != "none":
+                res["canvas"] = torch.empty(0, dtype=torch.uint8, device=self.device)
+                res["canvas_host"] = np.zeros(0, np.uint8)
+        return res
 
     def segment(self, images):
         batch, planes = self.binarize(images)

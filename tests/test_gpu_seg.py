@@ -180,11 +180,10 @@ def test_partition_matches_reference_golden(cuda_device, golden, golden_arrays):
     se = StrokeEstimationSession()
     parts = se.get_partitions_batch(masks)
     batch, planes = _pack_masks(masks)
-    seg = S.Segmenter.__new__(S.Segmenter); seg.device = torch.device("cuda", 0); seg.margin = 2
-    res = seg.partition(batch, planes)
+    res = S.Segmenter(None, device=torch.device("cuda", 0)).partition(batch, planes)
     for i, nme in enumerate(names):
         g = golden["islands"][nme]
-        canv = res["canvases"][i]
+        canv = res.line_canvases(i)
         assert len(canv) == len(g["groups"]), nme
         for (c, (top, left)), gg in zip(canv, g["groups"]):
             assert [int(top), int(left)] == gg["pos"] and list(c.shape) == gg["shape"] and sha(c) == gg["sha"], nme
