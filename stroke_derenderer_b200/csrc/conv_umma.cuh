@@ -28,6 +28,7 @@ enum { EPI_STORE = 0, EPI_GATE = 1, EPI_HEAD = 2 };
 
 struct ConvParams {
   CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmOut[4];        // store epilogue: one output map per sub-pixel phase
   // geometry of the (low-res for up-convs) input grid the M tiles walk over
   int H, W, B;                 // image dims of the A source, live batch
   int box_w, box_h, box_n;     // pixels per M tile = box_w*box_h*box_n = 128
@@ -137,31 +138,55 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN> struct ConvCfg {
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier for the 4 epilogue warps only (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int kMiscBytes = 4096;       // barriers | tmem slot | bias | psi/head vector | gate scale | pixel index
+constexpr int kMaxSmem = 232448;       // 227 KB opt-in limit per CTA
+
+template <int BN, int EPI> struct ConvCfg {
   static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * BN * 2 : 0;   // swizzled staging for the TMA store
+  static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // 64,128,256,512: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + kMiscBytes;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(EPI != EPI_STORE || BN % 64 == 0, "store epilogue writes 64-channel boxes");
 };
 
 constexpr int kConvThreads = 192;
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barrier layout (8 B each): full[S], empty[S], tfull[2], tempty[2], then the TMEM slot
+  const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;            // 1024-aligned
+  uint8_t* misc = smem_al + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes;
+  const uint32_t bar_base = out_base + Cfg::kOutBytes;
+  // misc layout: [0,256) barriers (8 B each): full[S], empty[S], tfull[2], tempty[2]; [248] TMEM slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
+  float* s_bias = reinterpret_cast<float*>(misc + 256);        // up to 256 floats
+  float* s_vec = reinterpret_cast<float*>(misc + 1280);        // psi / head weights, up to 256 floats
+  float* s_scale = reinterpret_cast<float*>(misc + 2304);      // gate: per-row sigmoid(psi), 128 floats
+  int* s_pix = reinterpret_cast<int*>(misc + 2816);            // gate: per-row output pixel index (-1 = dead), 128 ints
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -169,6 +194,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     tma_prefetch_desc(&p.tmA0);
     if (p.c1_blocks) tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmB);
+    if (EPI == EPI_STORE) for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.tmOut[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -180,6 +206,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (EPI != EPI_STORE && warp >= 2) {
+    // whole-N vectors used by the gate / head epilogues (n_tiles == 1 there)
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < BN; i += 128) {
+      s_bias[i] = p.bias[i];
+      s_vec[i] = (EPI == EPI_GATE) ? p.psi_w[i] : p.head_w[i];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -246,49 +280,70 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     // ======================= epilogue (warps 2..5) =======================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // accumulator row == pixel within the M tile
+    const int et = threadIdx.x - 64;              // 0..127 within the epilogue group
     const int lw = row % p.box_w; int rr = row / p.box_w;
     const int lh = rr % p.box_h; const int ln = rr / p.box_h;
     int as = 0; uint32_t aphase = 0;
+    int cur_nt = -1;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int nt = w % p.n_tiles; int rest = w / p.n_tiles;
       const int mt = rest % p.m_tiles; const int ph = rest / p.m_tiles;
       const int tx = mt % p.tiles_x; rest = mt / p.tiles_x;
       const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-      const int n = tn * p.box_n + ln;
-      int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
-      int OH = p.H, OW = p.W;
-      if (p.up) { y = 2 * y + (ph >> 1); x = 2 * x + (ph & 1); OH *= 2; OW *= 2; }
-      const int64_t pix = ((int64_t)n * OH + y) * OW + x;
-      const bool live = n < p.B;
-
-      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
       if constexpr (EPI == EPI_STORE) {
-        __half* orow = p.out + pix * p.out_c + nt * BN;
-        const float* brow = p.bias + nt * BN;
+        if (nt != cur_nt) {                       // bias slice of this N tile -> smem (uniform branch)
+          epi_bar();                              // everybody is done reading the previous slice
+          if (et < BN) s_bias[et] = __ldg(p.bias + nt * BN + et);
+          cur_nt = nt;
+          epi_bar();
+        }
+        mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
+        tc_fence_after();
+        // the previous tile's TMA store must have finished READING the staging buffer
+        if (et == 0) tma_store_wait_read();
+        epi_bar();
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
-          uint4 pk[4];
-          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+          // 128 rows x 128 B per 64-channel half, 16-B chunk j of row r lives at chunk (j ^ (r & 7))
+          const uint32_t half_base = out_base + (uint32_t)(c >> 1) * 16384u + (uint32_t)row * 128u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = v[2 * j] + __ldg(brow + c * 32 + 2 * j);
-            float b = v[2 * j + 1] + __ldg(brow + c * 32 + 2 * j + 1);
-            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            __half2 h = __floats2half2_rn(a, b);
-            pw[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if (live) {
-            uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = pk[j];
+            for (int j = 0; j < 4; ++j) {
+              const int col = j4 * 8 + j * 2;
+              float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __half2 h = __floats2half2_rn(a, b);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t chunk = (uint32_t)((c & 1) * 4 + j4);
+            const uint32_t addr = half_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           }
         }
-      } else if constexpr (EPI == EPI_GATE) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));              // TMEM stage free: the next tile's MMAs may start
+        fence_async_smem();                       // generic-proxy smem writes -> visible to the TMA unit
+        epi_bar();
+        if (et == 0) {
+          const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+#pragma unroll
+          for (int hb = 0; hb < BN / 64; ++hb)
+            tma_store_4d(&p.tmOut[ph], out_base + hb * 16384u, nt * BN + hb * 64, x0, y0, n0);
+          tma_store_commit();
+        }
+      } else {
+        const int n = tn * p.box_n + ln;
+        int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
+        const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;     // gate / head never upsample
+        const bool live = n < p.B;
+        mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
+        tc_fence_after();
         float dot = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -296,51 +351,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = fmaxf(v[j] + __ldg(p.bias + c * 32 + j), 0.f);
-            dot = fmaf(a, __ldg(p.psi_w + c * 32 + j), dot);
+            float a = v[j] + s_bias[c * 32 + j];
+            if (EPI == EPI_GATE || p.relu) a = fmaxf(a, 0.f);
+            // head: the unfused graph stores d2 in fp16 before the 1x1 conv; keep that rounding point
+            if (EPI == EPI_HEAD) a = __half2float(__float2half_rn(a));
+            dot = fmaf(a, s_vec[c * 32 + j], dot);
           }
         }
-        const float s = 1.f / (1.f + expf(-(dot + p.psi_b)));
-        if (live) {
-          const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + pix * p.gate_c);
-          uint4* xo = reinterpret_cast<uint4*>(p.out + pix * p.out_c);
-          for (int c = 0; c < p.gate_c / 8; ++c) {
-            uint4 t = __ldg(xi + c);
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        if constexpr (EPI == EPI_GATE) {
+          epi_bar();                              // previous tile's scaling pass has finished with s_scale / s_pix
+          s_scale[row] = 1.f / (1.f + expf(-(dot + p.psi_b)));
+          s_pix[row] = live ? (int)pix : -1;
+          epi_bar();
+          // coalesced pass: 128 threads sweep the tile's rows, consecutive threads -> consecutive 16-B chunks
+          const int cpr = p.gate_c >> 3;          // 16-B chunks per pixel row
+          const int total = 128 * cpr;
+          for (int i = et; i < total; i += 128) {
+            const int r = i / cpr, ch = i - r * cpr;
+            const int px = s_pix[r];
+            if (px < 0) continue;
+            const float sc = s_scale[r];
+            uint4 t = __ldg(reinterpret_cast<const uint4*>(p.gate_x + (int64_t)px * p.gate_c) + ch);
             __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f = __half22float2(h[j]);
-              h[j] = __floats2half2_rn(f.x * s, f.y * s);
+              h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
             }
-            xo[c] = t;
+            reinterpret_cast<uint4*>(p.out + (int64_t)px * p.out_c)[ch] = t;
           }
-        }
-      } else {  // EPI_HEAD
-        float dot = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = v[j] + __ldg(p.bias + c * 32 + j);
-            if (p.relu) a = fmaxf(a, 0.f);
-            // the unfused graph stores d2 in fp16 before the 1x1 conv; keep the same rounding point
-            a = __half2float(__float2half_rn(a));
-            dot = fmaf(a, __ldg(p.head_w + c * 32 + j), dot);
+        } else {
+          const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));
+          if (live) {
+            if (p.prob_f32) p.prob_f32[pix] = pr;
+            if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
+            if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
           }
-        }
-        const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));
-        if (live) {
-          if (p.prob_f32) p.prob_f32[pix] = pr;
-          if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
-          if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (EPI == EPI_STORE && et == 0) tma_store_wait_all();   // all output bytes written before the CTA retires
   }
 
   tc_fence_before();

@@ -278,9 +278,31 @@ static int make_tmap_w(sd_engine* e, CUtensorMap* tm, const __half* w, int rows,
   return SD_OK;
 }
 
+// output map of a store-epilogue conv.  For the sub-pixel up-conv, phase (py, px) writes pixel
+// (2y+py, 2x+px) of a 2H x 2W tensor: a strided view indexed by the LOW-res (x, y).
+static int make_tmap_out(sd_engine* e, CUtensorMap* tm, const Act& o, const Level& box, bool up, int ph) {
+  const uint64_t C = o.C;
+  cuuint64_t dims[4], strides[3];
+  char* base = reinterpret_cast<char*>(o.p);
+  if (!up) {
+    dims[0] = C; dims[1] = o.W; dims[2] = o.H; dims[3] = e->cap_tiles;
+    strides[0] = C * 2; strides[1] = (uint64_t)o.W * C * 2; strides[2] = (uint64_t)o.H * o.W * C * 2;
+  } else {
+    dims[0] = C; dims[1] = o.W / 2; dims[2] = o.H / 2; dims[3] = e->cap_tiles;
+    strides[0] = 2 * C * 2; strides[1] = 2 * (uint64_t)o.W * C * 2; strides[2] = (uint64_t)o.H * o.W * C * 2;
+    base += ((uint64_t)(ph >> 1) * o.W + (ph & 1)) * C * 2;
+  }
+  cuuint32_t boxd[4] = {64, (cuuint32_t)box.box_w, (cuuint32_t)box.box_h, (cuuint32_t)box.box_n};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out C=%d W=%d H=%d up=%d) failed: %d", o.C, o.W, o.H, (int)up, (int)r); return SD_ECUDA; }
+  return SD_OK;
+}
+
 template <int BN, int EPI>
 static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
     SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -402,7 +424,11 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   }
   p.bias = e->bias[slot];
   p.err_flag = e->err_flag;
-  if (cs.epi == EPI_STORE) { p.out = cs.out->p; p.out_c = cs.out->C; }
+  if (cs.epi == EPI_STORE) {
+    p.out = cs.out->p; p.out_c = cs.out->C;
+    for (int ph = 0; ph < p.n_phases; ++ph)
+      if ((r = make_tmap_out(e, &p.tmOut[ph], *cs.out, L, cs.up, ph))) return r;
+  }
   if (cs.epi == EPI_GATE) {
     p.out = cs.out->p; p.out_c = cs.out->C;
     p.psi_w = e->w_f32[SD_ATT5_PSI + 6 * cs.att]; p.psi_b = e->psi_b[cs.att];
