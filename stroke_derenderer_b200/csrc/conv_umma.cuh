@@ -185,8 +185,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
   float* s_bias = reinterpret_cast<float*>(misc + 256);        // up to 256 floats
   float* s_vec = reinterpret_cast<float*>(misc + 1280);        // psi / head weights, up to 256 floats
-  float* s_scale = reinterpret_cast<float*>(misc + 2304);      // gate: per-row sigmoid(psi), 128 floats
-  int* s_pix = reinterpret_cast<int*>(misc + 2816);            // gate: per-row output pixel index (-1 = dead), 128 ints
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -361,26 +359,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
         if constexpr (EPI == EPI_GATE) {
-          epi_bar();                              // previous tile's scaling pass has finished with s_scale / s_pix
-          s_scale[row] = 1.f / (1.f + expf(-(dot + p.psi_b)));
-          s_pix[row] = live ? (int)pix : -1;
-          epi_bar();
-          // coalesced pass: 128 threads sweep the tile's rows, consecutive threads -> consecutive 16-B chunks
-          const int cpr = p.gate_c >> 3;          // 16-B chunks per pixel row
-          const int total = 128 * cpr;
-          for (int i = et; i < total; i += 128) {
-            const int r = i / cpr, ch = i - r * cpr;
-            const int px = s_pix[r];
-            if (px < 0) continue;
-            const float sc = s_scale[r];
-            uint4 t = __ldg(reinterpret_cast<const uint4*>(p.gate_x + (int64_t)px * p.gate_c) + ch);
-            __half2* h = reinterpret_cast<__half2*>(&t);
+          // thread == pixel row: stream this pixel's skip-tensor row (gate_c halves, contiguous), scale, store.
+          // (A 128-thread "coalesced" sweep over the tile measured slower: each row is a whole number of
+          // 128-B lines, so the per-row walk already moves full lines.)
+          const float sc = 1.f / (1.f + expf(-(dot + p.psi_b)));
+          if (live) {
+            const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + pix * p.gate_c);
+            uint4* xo = reinterpret_cast<uint4*>(p.out + pix * p.out_c);
+            for (int c = 0; c < p.gate_c / 8; ++c) {
+              uint4 t = __ldg(xi + c);
+              __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = __half22float2(h[j]);
-              h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
+              }
+              xo[c] = t;
             }
-            reinterpret_cast<uint4*>(p.out + (int64_t)px * p.out_c)[ch] = t;
           }
         } else {
           const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));

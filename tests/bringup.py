@@ -16,7 +16,7 @@ rc_all = 0
 for f in files:
     t0 = time.time()
     cmd = [sys.executable, "-m", "pytest", f, "-m", "gpu", "-q", "-s", "-x" if os.environ.get("SD_X") else "-q",
-           "--timeout", "600", "-p", "no:cacheprovider"] + (["-k", sys.argv[1]] if len(sys.argv) > 1 else [])
+           "--timeout", "600", "-p", "no:cacheprovider"] + (["-k", " ".join(sys.argv[1:])] if len(sys.argv) > 1 else [])
     log = OUT / (Path(f).stem + ".log")
     with open(log, "w") as fh:
         try:
