@@ -12,6 +12,7 @@
 #include <functional>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace sd {
 
@@ -241,6 +242,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int row_mode = 0;                    // 0: generic kernel everywhere; 1/2: conv_row_kernel on level-1 64-ch layers
 };
 
 namespace sd {
@@ -256,7 +258,7 @@ static int alloc_act(sd_engine* e, Act& a, int lvl, int C) {
   return dev_alloc(e, (void**)&a.p, (size_t)e->cap_tiles * a.H * a.W * C * sizeof(__half));
 }
 
-static int make_tmap_act(sd_engine* e, CUtensorMap* tm, const Act& a, const Level& box) {
+static int make_tmap_act(sd_engine* e, CUtensorMap* tm, const Act& a, const Level& box) {  // box.box_* only
   cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)e->cap_tiles};
   cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
   cuuint32_t boxd[4] = {64, (cuuint32_t)box.box_w, (cuuint32_t)box.box_h, (cuuint32_t)box.box_n};
@@ -311,6 +313,27 @@ static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
   conv_umma_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_umma_kernel");
   return SD_OK;
+}
+
+template <int CB, int EPI>
+static int launch_row(const ConvParams& p, int grid, cudaStream_t s) {
+  using Cfg = RowCfg<CB, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_row_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  conv_row_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  SD_LAUNCH_CHECK("conv_row_kernel");
+  return SD_OK;
+}
+
+static int dispatch_row(const ConvParams& p, int cb, int epi, int grid, cudaStream_t s) {
+  if (cb == 1 && epi == EPI_STORE) return launch_row<1, EPI_STORE>(p, grid, s);
+  if (cb == 2 && epi == EPI_STORE) return launch_row<2, EPI_STORE>(p, grid, s);
+  if (cb == 1 && epi == EPI_HEAD) return launch_row<1, EPI_HEAD>(p, grid, s);
+  set_error("dispatch_row: no kernel for CB=%d epilogue=%d", cb, epi);
+  return SD_EINVAL;
 }
 
 static int dispatch_conv(const ConvParams& p, int bn, int epi, int grid, cudaStream_t s) {
@@ -395,6 +418,39 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   SD_REQUIRE(lvl >= 0, "add_umma_conv(%s): unknown level", cs.name);
   const Level& L = e->lv[lvl];
   int r;
+  const bool row_ok = e->row_mode > 0 && lvl == 0 && L.W % 128 == 0 && co == 64 && !cs.up && e->ks[slot] == 3 &&
+                      cs.in0->C == 64 && (!cs.in1 || cs.in1->C == 64) && (cs.epi == EPI_STORE || cs.epi == EPI_HEAD) &&
+                      !(cs.in1 && cs.epi == EPI_HEAD);
+  if (row_ok) {
+    const int cb = cs.in1 ? 2 : 1;
+    Level halo = L; halo.box_w = 130; halo.box_h = 1; halo.box_n = 1;
+    if ((r = make_tmap_act(e, &p.tmA0, *cs.in0, halo))) return r;
+    if (cs.in1 && (r = make_tmap_act(e, &p.tmA1, *cs.in1, halo))) return r;
+    if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], co, 9 * cin_total, 64))) return r;
+    p.H = L.H; p.W = L.W; p.cout = co; p.relu = 1; p.n_phases = 1;
+    p.bias = e->bias[slot]; p.err_flag = e->err_flag; p.desc_mode = e->row_mode - 1;
+    if (cs.epi == EPI_STORE) {
+      p.out = cs.out->p; p.out_c = cs.out->C;
+      if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
+    } else {
+      p.head_w = e->w_f32[SD_HEAD];
+    }
+    Op op;
+    op.name = std::string(cs.name) + "[row]";
+    const int epi = cs.epi, nsm = e->num_sms, segs = L.W / 128, H = L.H;
+    op.flops_per_tile = 2.0 * L.H * L.W * co * 9 * cin_total;
+    op.run = [e, p, cb, epi, nsm, segs, H](int B, cudaStream_t s) mutable -> int {
+      p.B = B;
+      if (epi == EPI_HEAD) {
+        p.head_b = e->head_b; p.thr = e->thr;
+        p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
+      }
+      const int n_work = B * H * segs;
+      return dispatch_row(p, cb, epi, n_work < nsm ? n_work : nsm, s);
+    };
+    e->ops.push_back(op);
+    return SD_OK;
+  }
   if ((r = make_tmap_act(e, &p.tmA0, *cs.in0, L))) return r;
   if (cs.in1 && (r = make_tmap_act(e, &p.tmA1, *cs.in1, L))) return r;
   const int taps = cs.up ? 4 : e->ks[slot] * e->ks[slot];
@@ -566,6 +622,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
                exp_shape[s][0], exp_shape[s][1], exp_shape[s][2]);
   }
   e->impl = impl;
+  if (const char* rm = getenv("SD_ROWCONV")) e->row_mode = atoi(rm);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
