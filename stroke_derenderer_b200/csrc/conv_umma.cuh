@@ -54,7 +54,6 @@ struct ConvParams {
   float head_b, thr;
   float* prob_f32; __half* prob_f16; uint8_t* mask_u8;
   int* err_flag;               // set when a barrier wait times out
-  int desc_mode;               // conv_row_kernel: how row-shifted UMMA descriptors encode their start
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -341,6 +340,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
         const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;     // gate / head never upsample
         const bool live = n < p.B;
+        // gate: the skip-tensor row does not depend on the GEMM -> issue its first loads now so
+        // their latency hides behind the wait for the accumulator
+        uint4 xpre[8];
+        if constexpr (EPI == EPI_GATE) {
+          const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + (live ? pix : 0) * p.gate_c);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) xpre[c] = __ldg(xi + c);
+        }
         mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
         tc_fence_after();
         float dot = 0.f;
@@ -367,15 +374,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
           if (live) {
             const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + pix * p.gate_c);
             uint4* xo = reinterpret_cast<uint4*>(p.out + pix * p.out_c);
-            for (int c = 0; c < p.gate_c / 8; ++c) {
-              uint4 t = __ldg(xi + c);
-              __half2* h = reinterpret_cast<__half2*>(&t);
+            const int nchunk = p.gate_c >> 3;            // 16-B chunks per row: 8, 16, 32 or 64
+            for (int c0 = 0; c0 < nchunk; c0 += 8) {
+              uint4 nxt[8];
+              const bool more = c0 + 8 < nchunk;
+              if (more) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]);
-                h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
+                for (int c = 0; c < 8; ++c) nxt[c] = __ldg(xi + c0 + 8 + c);   // next batch in flight while this one is scaled
               }
-              xo[c] = t;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 t = xpre[c];
+                __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = __half22float2(h[j]);
+                  h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
+                }
+                xo[c0 + c] = t;
+              }
+              if (more) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xpre[c] = nxt[c];
+              }
             }
           }
         } else {
@@ -424,12 +445,9 @@ template <int CB, int EPI> struct RowCfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-// mode 0: base_offset field left 0; mode 1: base_offset = (addr >> 7) & 7 (start not 1024-B aligned)
-__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int mode) {
-  uint64_t d = umma_desc_sw128(smem_addr);
-  if (mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
+// Row-shifted operand: start address = buffer + dx * 128 B, base_offset field left 0.  Measured on B200:
+// the 128-B swizzle is applied on absolute shared-memory address bits, so a start that is not 1024-B
+// aligned needs no correction (setting base_offset = (addr >> 7) & 7 gives wrong results).
 
 template <int CB, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
@@ -520,7 +538,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_row_kernel(const __grid_
             const uint32_t a_addr = smem_base + stage * kRowStageBytes;
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint64_t adesc = umma_desc_sw128_shifted(a_addr + dx * 128, p.desc_mode);
+              const uint64_t adesc = umma_desc_sw128(a_addr + dx * 128);
               const uint64_t bdesc = umma_desc_sw128(w_base + ((dy * 3 + dx) * CB + cb) * 8192);
 #pragma unroll
               for (int k = 0; k < 4; ++k)

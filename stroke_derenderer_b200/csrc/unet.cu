@@ -242,7 +242,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
-  int row_mode = 0;                    // 0: generic kernel everywhere; 1/2: conv_row_kernel on level-1 64-ch layers
+  int row_mode = 1;                    // 1: conv_row_kernel on the level-1 64-channel layers; 0 (SD_ROWCONV=0): generic kernel everywhere
 };
 
 namespace sd {
@@ -428,7 +428,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     if (cs.in1 && (r = make_tmap_act(e, &p.tmA1, *cs.in1, halo))) return r;
     if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], co, 9 * cin_total, 64))) return r;
     p.H = L.H; p.W = L.W; p.cout = co; p.relu = 1; p.n_phases = 1;
-    p.bias = e->bias[slot]; p.err_flag = e->err_flag; p.desc_mode = e->row_mode - 1;
+    p.bias = e->bias[slot]; p.err_flag = e->err_flag;
     if (cs.epi == EPI_STORE) {
       p.out = cs.out->p; p.out_c = cs.out->C;
       if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
