@@ -38,7 +38,7 @@ extern "C" {
 #define SD_TILE_W 384          /* evaluate_binarize.py:20 WIDTH    */
 #define SD_OVERLAP 64          /* evaluate_binarize.py:22 OVERLAP  */
 #define SD_CIN_PAD 8           /* RGB padded to 8 halves (16 B) per pixel */
-#define SD_CCL_CHUNK 2048      /* 2x2-block space of a line is padded to this */
+#define SD_CCL_CHUNK 4096      /* CCL strip: 64 x 64 blocks of 2x2 px; a line is a whole number of strips */
 
 /* One text line of a batch (all lines already at height 128). */
 typedef struct sd_line {
@@ -51,7 +51,7 @@ typedef struct sd_line {
   int32_t first_tile; /* index of the line's first tile in the batch tile stack                   */
   int32_t tile_w;     /* 384 */
   int32_t overlap;    /* 64  */
-  int32_t pitch;      /* row pitch (elements) of the line's mask / label planes: round_up(W',16);
+  int32_t pitch;      /* row pitch (elements) of the line's mask / label planes: round_up(W',128);
                          columns [W', pitch) of a mask plane must be zero                        */
   int32_t bw;         /* pitch / 2: 2x2-block columns (padded)                                    */
 } sd_line;

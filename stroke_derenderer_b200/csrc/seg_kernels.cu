@@ -189,54 +189,79 @@ __device__ __forceinline__ uint32_t range_mask(int wi, int lo, int hi) {
   return m;
 }
 
+// one CTA per (line, row): no offset search, every thread walks 16-px units of that row.
 template <bool kProb>
 __global__ void __launch_bounds__(256) glue_kernel(
-    const void* __restrict__ tiles, const sd_line* __restrict__ L, int n_lines, int64_t n_units,
-    int64_t tile_elems_total, float thr, uint32_t on_rep, uint4* __restrict__ out) {
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // 16-px unit in packed space
-  const int64_t cta_first = (int64_t)blockIdx.x * blockDim.x * 16;
-  const int64_t mine = (unit < n_units ? unit : n_units - 1) * 16;
-  const int l = find_line_cta<false>(L, n_lines, cta_first, mine);
-  if (unit >= n_units) return;
+    const void* __restrict__ tiles, const sd_line* __restrict__ L, int64_t tile_elems_total, float thr,
+    uint32_t on_rep, uint4* __restrict__ out) {
+  const int l = blockIdx.x >> 7, row = blockIdx.x & 127;
   const sd_line ln = L[l];
-  const int64_t rel = unit * 16 - ln.px_off;
-  const int row = (int)(rel / ln.pitch);
-  const int x0 = (int)(rel - (int64_t)row * ln.pitch);
-  uint32_t acc[4] = {0u, 0u, 0u, 0u};
-  if (x0 < ln.width) {
-    const int xl = min(x0 + 15, ln.width - 1);
-    const int iA = (ln.n_tiles == 1) ? 0 : min(xl / ln.wu, ln.n_tiles - 1);
+  uint4* dst = out + ((ln.px_off + (int64_t)row * ln.pitch) >> 4);
+  const int units = ln.pitch >> 4;
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    const int x0 = u * 16;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    if (x0 < ln.width) {
+      const int xl = min(x0 + 15, ln.width - 1);
+      const int iA = (ln.n_tiles == 1) ? 0 : min(xl / ln.wu, ln.n_tiles - 1);
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int i = iA - t;
-      if (i < 0) break;
-      const int start = (ln.n_tiles == 1) ? 0 : i * ln.wu;
-      const int wd = tile_width(ln, i);
-      // valid run positions k: 0 <= x0 + k - start < wd  and x0 + k < W
-      const int lo = max(0, start - x0), hi = min(min(16, start + wd - x0), ln.width - x0);
-      if (lo >= hi) continue;
-      const int64_t e = ((int64_t)(ln.first_tile + i) * SD_TILE_H + row) * ln.tile_w + (x0 - start);
-      uint32_t v[4];
-      if (kProb) load16_f16_thr(reinterpret_cast<const __half*>(tiles), e, tile_elems_total, thr, v);
-      else load16_u8(reinterpret_cast<const uint8_t*>(tiles), e, tile_elems_total, v);
+      for (int t = 0; t < 2; ++t) {
+        const int i = iA - t;
+        if (i < 0) break;
+        const int start = (ln.n_tiles == 1) ? 0 : i * ln.wu;
+        const int wd = tile_width(ln, i);
+        // valid run positions k: 0 <= x0 + k - start < wd  and x0 + k < W
+        const int lo = max(0, start - x0), hi = min(min(16, start + wd - x0), ln.width - x0);
+        if (lo >= hi) continue;
+        const int64_t e = ((int64_t)(ln.first_tile + i) * SD_TILE_H + row) * ln.tile_w + (x0 - start);
+        uint32_t v[4];
+        if (kProb) load16_f16_thr(reinterpret_cast<const __half*>(tiles), e, tile_elems_total, thr, v);
+        else load16_u8(reinterpret_cast<const uint8_t*>(tiles), e, tile_elems_total, v);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t m = v[k] & range_mask(k, lo, hi);
-        acc[k] = kProb ? (acc[k] | m) : __vmaxu4(acc[k], m);
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t m = v[k] & range_mask(k, lo, hi);
+          acc[k] = kProb ? (acc[k] | m) : __vmaxu4(acc[k], m);
+        }
+      }
+      if (kProb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] &= on_rep;
       }
     }
-    if (kProb) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] &= on_rep;
-    }
+    dst[u] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
   }
-  out[unit] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // ---------------------------------------------------------------------------
-// K7: connected-component labelling (block-based union-find, min-root).
-// A thread owns 8 horizontally adjacent 2x2 blocks (16 px x 2 rows).
+// K7: connected-component labelling with OpenCV's numbering, strip-resident.
+//
+// A line (128 x pitch, pitch % 128 == 0) is cut into strips of 128 x 128 px = 64 x 64 blocks of
+// 2x2 px.  Three launches, 6 B/px of traffic against the 5 B/px algorithmic minimum:
+//   1. ccl_strip_label_kernel  (CTA = strip): mask -> bits in smem, block union-find in smem with
+//      min-root unions (root = smallest block key of the strip-local component), then per block
+//      a 16-bit record (local root << 4 | 2x2 occupancy) -> HBM (0.5 B/px).  Local roots that do
+//      not touch a neighbouring strip are final roots: their bits go to the line's root bitmap
+//      (plain stores, every strip owns its words).  Boundary-touching local roots are registered
+//      in a sparse global parent array; the strip's two boundary block columns (root keys +
+//      pixel bits) are emitted for the merge.
+//   2. ccl_line_merge_kernel (CTA = line): unions across strip boundaries on the sparse global
+//      parents (8-connectivity between the two pixel columns), marks the surviving boundary roots
+//      in the bitmap, then an exclusive scan of the bitmap popcounts: label(root key g) =
+//      1 + #roots with key < g = OpenCV's label, because a component's root is its first 2x2
+//      block in raster order.
+//   3. ccl_strip_write_kernel (CTA = strip): records -> final int32 labels, 512 B per warp store.
 // ---------------------------------------------------------------------------
+constexpr int kStripBlocks = 4096;
+
+struct CclWork {
+  int* parent;          // [blk_total]   sparse: boundary-touching local roots only
+  uint16_t* rec;        // [blk_total]   (local root index << 4) | occupancy bits (p00, p01, p10, p11)
+  uint32_t* bitmap;     // [blk_total/32] bit = block is the root (first block) of a component
+  int* prefix;          // [blk_total/32] exclusive count of root bits before this word, per line
+  int* bnd_root;        // [strips][2][64] key of the local root of each boundary block, -1 if none
+  uint32_t* bnd_bits;   // [strips][2][4]  pixel column 0 / 127 of the strip, 128 rows
+};
+
 __device__ __forceinline__ uint32_t nz16(uint4 v) {   // bit k = byte k non-zero
   uint32_t w[4] = {v.x, v.y, v.z, v.w}, r = 0;
 #pragma unroll
@@ -249,27 +274,15 @@ __device__ __forceinline__ uint32_t nz16(uint4 v) {   // bit k = byte k non-zero
   return r;
 }
 
-struct RowBits {  // bit (k+1) = pixel x0 + k, bit 0 = pixel x0-1, bit 17 = pixel x0+16
-  uint32_t up, top, bot;
-};
-
-__device__ __forceinline__ uint32_t row_bits18(const uint8_t* __restrict__ rowp, int x0, int pitch) {
-  uint32_t b = nz16(__ldg(reinterpret_cast<const uint4*>(rowp + x0))) << 1;
-  if (x0 > 0) b |= (rowp[x0 - 1] != 0) ? 1u : 0u;
-  if (x0 + 16 < pitch) b |= (rowp[x0 + 16] != 0) ? (1u << 17) : 0u;
-  return b;
-}
-
+// global union-find on the sparse parents (min-root).  .cg loads: other CTAs' threads re-parent
+// nodes concurrently; a stale value would still be an ancestor, fresh ones shorten the walk.
 __device__ __forceinline__ int uf_find(const int* __restrict__ parent, int a) {
-  // .cg loads: other SMs re-parent nodes concurrently; a stale value would still
-  // be an ancestor (correct), but fresh ones shorten the walk.
   int p = __ldcg(parent + a);
   while (p != a) { a = p; p = __ldcg(parent + a); }
   return a;
 }
 
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  // min-root union (the root of a component is its smallest block key)
   while (true) {
     a = uf_find(parent, a);
     b = uf_find(parent, b);
@@ -281,223 +294,292 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-struct BlkCtx {
-  int l, br, bc0, key0;     // line, block row, first block column, key of first block
-  const sd_line* ln;
-};
-
-// maps packed block-space unit (8 blocks) -> line / block row / column.
-__device__ __forceinline__ bool blk_unit(const sd_line* __restrict__ L, int n_lines, int64_t n_units,
-                                         sd_line& ln, int& br, int& bc0) {
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t cta_first = (int64_t)blockIdx.x * blockDim.x * 8;
-  const int64_t mine = (unit < n_units ? unit : n_units - 1) * 8;
-  const int l = find_line_cta<true>(L, n_lines, cta_first, mine);
-  if (unit >= n_units) return false;
-  ln = L[l];
-  const int64_t rel = unit * 8 - ln.blk_off;
-  br = (int)(rel / ln.bw);
-  bc0 = (int)(rel - (int64_t)br * ln.bw);
-  return br < SD_TILE_H / 2;       // beyond: chunk padding
+// shared-memory union-find of one strip; entry i lives at i + i/16 so that a thread's 16
+// consecutive blocks fall into 16 different banks than its neighbour's.
+#define SD_PH(i) ((i) + ((i) >> 4))
+__device__ __forceinline__ int suf_find(volatile int* p, int a) {
+  int q = p[SD_PH(a)];
+  while (q != a) { a = q; q = p[SD_PH(a)]; }
+  return a;
 }
-
-__global__ void __launch_bounds__(256) ccl_init_kernel(
-    const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, int64_t n_units,
-    int* __restrict__ parent) {
-  sd_line ln; int br, bc0;
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = blk_unit(L, n_lines, n_units, ln, br, bc0);
-  if (unit >= n_units) return;
-  int4 p0 = make_int4(-1, -1, -1, -1), p1 = p0;
-  if (ok) {
-    const uint8_t* m = mask + ln.px_off + (int64_t)(2 * br) * ln.pitch + 2 * bc0;
-    uint32_t t = nz16(__ldg(reinterpret_cast<const uint4*>(m)));
-    uint32_t b = nz16(__ldg(reinterpret_cast<const uint4*>(m + ln.pitch)));
-    uint32_t a = t | b;
-    const int key0 = br * ln.bw + bc0;
-    int v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ((a >> (2 * k)) & 3u) ? key0 + k : -1;
-    p0 = make_int4(v[0], v[1], v[2], v[3]);
-    p1 = make_int4(v[4], v[5], v[6], v[7]);
-  }
-  int4* dst = reinterpret_cast<int4*>(parent + unit * 8);
-  dst[0] = p0; dst[1] = p1;
-}
-
-__global__ void __launch_bounds__(256) ccl_merge_kernel(
-    const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, int64_t n_units,
-    int* __restrict__ parent_all) {
-  sd_line ln; int br, bc0;
-  if (!blk_unit(L, n_lines, n_units, ln, br, bc0)) return;
-  const uint8_t* m = mask + ln.px_off + (int64_t)(2 * br) * ln.pitch;
-  const int x0 = 2 * bc0;
-  const uint32_t top = row_bits18(m, x0, ln.pitch);
-  const uint32_t bot = row_bits18(m + ln.pitch, x0, ln.pitch);
-  if (((top | bot) & 0x1FFFEu) == 0) return;
-  const uint32_t up = (br > 0) ? row_bits18(m - ln.pitch, x0, ln.pitch) : 0u;
-  int* parent = parent_all + ln.blk_off;
-  const int key0 = br * ln.bw + bc0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t p00 = (top >> (1 + 2 * k)) & 1u, p01 = (top >> (2 + 2 * k)) & 1u;
-    const uint32_t p10 = (bot >> (1 + 2 * k)) & 1u, p11 = (bot >> (2 + 2 * k)) & 1u;
-    if (!(p00 | p01 | p10 | p11)) continue;
-    const int key = key0 + k;
-    const uint32_t l01 = (top >> (2 * k)) & 1u, l11 = (bot >> (2 * k)) & 1u;
-    const uint32_t ul = (up >> (2 * k)) & 1u, u10 = (up >> (1 + 2 * k)) & 1u;
-    const uint32_t u11 = (up >> (2 + 2 * k)) & 1u, ur = (up >> (3 + 2 * k)) & 1u;
-    if ((p00 | p10) & (l01 | l11)) uf_union(parent, key, key - 1);
-    const bool cu = (p00 | p01) & (u10 | u11);
-    if (cu) uf_union(parent, key, key - ln.bw);
-    // up-left / up-right diagonals; redundant when the block above already
-    // links us and itself touches that diagonal pixel's block.
-    if ((p00 & ul) && !(cu && u10)) uf_union(parent, key, key - ln.bw - 1);
-    if ((p01 & ur) && !(cu && u11)) uf_union(parent, key, key - ln.bw + 1);
+__device__ __forceinline__ void suf_union(int* p, int a, int b) {
+  while (true) {
+    a = suf_find(p, a);
+    b = suf_find(p, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    int old = atomicMin(&p[SD_PH(a)], b);
+    if (old == a) return;
+    a = old;
   }
 }
 
-// CTA == one 2048-block chunk: flatten parents, count roots of the chunk.
-__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(
-    const sd_line* __restrict__ L, int n_lines, int* __restrict__ parent_all, int* __restrict__ chunk_count) {
-  const int64_t base = (int64_t)blockIdx.x * SD_CCL_CHUNK + threadIdx.x * 8;
+__global__ void __launch_bounds__(256) ccl_strip_label_kernel(
+    const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, CclWork w) {
+  __shared__ uint32_t s_bits[129][4];                 // row 0 = the (empty) row above the image
+  __shared__ int s_parent[kStripBlocks + kStripBlocks / 16];
+  __shared__ __align__(16) uint8_t s_touch[kStripBlocks];
   __shared__ int s_l;
-  if (threadIdx.x == 0) s_l = find_line<true>(L, n_lines, (int64_t)blockIdx.x * SD_CCL_CHUNK);
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
+  if (tid == 0) s_l = find_line<true>(L, n_lines, blk0);
+  reinterpret_cast<uint4*>(s_touch)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 4) s_bits[0][tid] = 0u;
   __syncthreads();
-  const int64_t blk_off = L[s_l].blk_off;
-  int* parent = parent_all + blk_off;
-  const int k0 = (int)(base - blk_off);
-  int4* pp = reinterpret_cast<int4*>(parent + k0);
-  int4 a = pp[0], b = pp[1];
-  int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  int roots = 0;
+  const sd_line ln = L[s_l];
+  const int ns = ln.bw >> 6;                          // strips of this line
+  const int s = (int)((blk0 - ln.blk_off) >> 12);     // this strip
+  const uint8_t* m = mask + ln.px_off + s * 128;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (v[k] >= 0) {
-      int r = v[k];
-      if (r != k0 + k) { r = uf_find(parent, r); }
-      v[k] = r;
-      roots += (r == k0 + k);
+  for (int it = 0; it < 4; ++it) {                    // a warp instruction reads 4 rows x 128 B
+    const int row = it * 32 + wp * 4 + (lane >> 3);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)row * ln.pitch) + (lane & 7));
+    const uint32_t nz = nz16(v);
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, nz, 1);
+    if (!(lane & 1)) s_bits[row + 1][(lane & 7) >> 1] = nz | (other << 16);
+  }
+  __syncthreads();
+
+  // thread = 16 horizontally adjacent blocks of one block row: one 32-bit word of three pixel rows
+  const int br = tid >> 2, q = tid & 3;
+  // bit (1 + c) = pixel column c of this word, bit 0 = the pixel left of it, bit 33 = the pixel right of it
+  uint64_t U = (uint64_t)s_bits[2 * br][q] << 1, T = (uint64_t)s_bits[2 * br + 1][q] << 1, B = (uint64_t)s_bits[2 * br + 2][q] << 1;
+  if (q > 0) {
+    U |= s_bits[2 * br][q - 1] >> 31; T |= s_bits[2 * br + 1][q - 1] >> 31; B |= s_bits[2 * br + 2][q - 1] >> 31;
+  }
+  if (q < 3) U |= (uint64_t)(s_bits[2 * br][q + 1] & 1u) << 33;
+  const int base = br * 64 + q * 16;
+
+  // phase 1: horizontal runs inside the thread resolve in registers (parent = first block of the run)
+  uint32_t occ_mask = 0, link0 = 0;
+  {
+    int start = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t t2 = (uint32_t)(T >> (1 + 2 * k)) & 3u, b2 = (uint32_t)(B >> (1 + 2 * k)) & 3u;
+      int pv = -1;
+      if (t2 | b2) {
+        const bool linked = ((t2 | b2) & 1u) && (((uint32_t)(T >> (2 * k)) | (uint32_t)(B >> (2 * k))) & 1u);
+        if (k == 0) link0 = linked ? 1u : 0u;
+        if (!linked || k == 0) start = k;
+        pv = base + start;
+        occ_mask |= 1u << k;
+      }
+      s_parent[SD_PH(base + k)] = pv;
     }
   }
-  // NOTE: other threads may still be walking through these entries; writing a
-  // shorter path (still an ancestor) keeps every walk correct.
-  pp[0] = make_int4(v[0], v[1], v[2], v[3]);
-  pp[1] = make_int4(v[4], v[5], v[6], v[7]);
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
+
+  // phase 2: unions with the previous thread's run and with the block row above
+  if (occ_mask) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) roots += __shfl_xor_sync(0xffffffffu, roots, o);
-  if ((threadIdx.x & 31) == 0 && roots) atomicAdd(&s_cnt, roots);
+    for (int k = 0; k < 16; ++k) {
+      if (!((occ_mask >> k) & 1u)) continue;
+      const int idx = base + k;
+      const uint32_t p00 = (uint32_t)(T >> (1 + 2 * k)) & 1u, p01 = (uint32_t)(T >> (2 + 2 * k)) & 1u;
+      const uint32_t ul = (uint32_t)(U >> (2 * k)) & 1u, u10 = (uint32_t)(U >> (1 + 2 * k)) & 1u;
+      const uint32_t u11 = (uint32_t)(U >> (2 + 2 * k)) & 1u, ur = (uint32_t)(U >> (3 + 2 * k)) & 1u;
+      if (k == 0 && link0) suf_union(s_parent, idx, idx - 1);
+      const bool cu = (p00 | p01) & (u10 | u11);
+      if (cu) suf_union(s_parent, idx, idx - 64);
+      // up-left / up-right diagonals; redundant when the block above already links us and itself
+      // touches that diagonal pixel's block.
+      if ((p00 & ul) && !(cu && u10)) suf_union(s_parent, idx, idx - 65);
+      if ((p01 & ur) && !(cu && u11)) suf_union(s_parent, idx, idx - 63);
+    }
+  }
   __syncthreads();
-  if (threadIdx.x == 0) chunk_count[blockIdx.x] = s_cnt;
+
+  // phase 3: records, boundary columns
+  uint32_t recw[8];
+  int r_first = 0, r_last = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    uint32_t rc = 0;
+    if ((occ_mask >> k) & 1u) {
+      const int r = suf_find(s_parent, base + k);
+      const uint32_t occ4 = ((uint32_t)(T >> (1 + 2 * k)) & 3u) | (((uint32_t)(B >> (1 + 2 * k)) & 3u) << 2);
+      rc = ((uint32_t)r << 4) | occ4;
+      if (k == 0) r_first = r;
+      if (k == 15) r_last = r;
+    }
+    if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
+  }
+  {
+    uint4* rp = reinterpret_cast<uint4*>(w.rec + ln.blk_off + (int64_t)br * ln.bw + s * 64 + q * 16);
+    rp[0] = make_uint4(recw[0], recw[1], recw[2], recw[3]);
+    rp[1] = make_uint4(recw[4], recw[5], recw[6], recw[7]);
+  }
+  if (q == 0) {
+    const bool on = s > 0 && (occ_mask & 1u);
+    if (on) s_touch[r_first] = 1;
+    w.bnd_root[((int64_t)blockIdx.x * 2 + 0) * 64 + br] = on ? (r_first >> 6) * ln.bw + s * 64 + (r_first & 63) : -1;
+  }
+  if (q == 3) {
+    const bool on = s < ns - 1 && ((occ_mask >> 15) & 1u);
+    if (on) s_touch[r_last] = 1;
+    w.bnd_root[((int64_t)blockIdx.x * 2 + 1) * 64 + br] = on ? (r_last >> 6) * ln.bw + s * 64 + (r_last & 63) : -1;
+  }
+  if (tid < 128) {
+    const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 1][0] & 1u);
+    const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 1][3] >> 31);
+    if (lane == 0) {
+      w.bnd_bits[((int64_t)blockIdx.x * 2 + 0) * 4 + wp] = m0;
+      w.bnd_bits[((int64_t)blockIdx.x * 2 + 1) * 4 + wp] = m1;
+    }
+  }
+  __syncthreads();
+
+  // roots: interior ones are final -> bitmap; boundary-touching ones register in the global parents
+  uint32_t rootbits = 0;
+  if (occ_mask) {
+    volatile int* vp = s_parent;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int idx = base + k;
+      if (((occ_mask >> k) & 1u) && vp[SD_PH(idx)] == idx) {
+        if (s_touch[idx]) {
+          const int key = br * ln.bw + s * 64 + q * 16 + k;
+          w.parent[ln.blk_off + key] = key;
+        } else {
+          rootbits |= 1u << k;
+        }
+      }
+    }
+  }
+  const uint32_t other = __shfl_xor_sync(0xffffffffu, rootbits, 1);
+  if (!(q & 1)) w.bitmap[(ln.blk_off >> 5) + (int64_t)br * (ln.bw >> 5) + s * 2 + (q >> 1)] = rootbits | (other << 16);
 }
 
-// one CTA per line: exclusive scan of the line's chunk counts.
-__global__ void __launch_bounds__(256) ccl_scan_kernel(
-    const sd_line* __restrict__ L, int n_lines, int64_t blk_total, const int* __restrict__ chunk_count,
-    int* __restrict__ chunk_base, int* __restrict__ num_out) {
-  const int l = blockIdx.x;
-  const int64_t c0 = L[l].blk_off / SD_CCL_CHUNK;
-  const int64_t c1 = ((l + 1 < n_lines) ? L[l + 1].blk_off : blk_total) / SD_CCL_CHUNK;
-  __shared__ int s_warp[8];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
+__device__ __forceinline__ uint32_t col_bit(const uint32_t* __restrict__ p, int r) { return (p[r >> 5] >> (r & 31)) & 1u; }
+
+__global__ void __launch_bounds__(512) ccl_line_merge_kernel(
+    const sd_line* __restrict__ L, CclWork w, int* __restrict__ num_out) {
+  const int l = blockIdx.x, tid = threadIdx.x;
+  const sd_line ln = L[l];
+  const int ns = ln.bw >> 6;
+  const int64_t strip0 = ln.blk_off >> 12;
+  int* parent = w.parent + ln.blk_off;
+  uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
+  int* prefix = w.prefix + (ln.blk_off >> 5);
+
+  // 1. 8-connectivity across every strip boundary: pixel column 127 of strip b-1 against pixel column 0 of strip b
+  for (int i = tid; i < (ns - 1) * 64; i += blockDim.x) {
+    const int b = 1 + (i >> 6), br = i & 63;
+    const int a = w.bnd_root[((strip0 + b - 1) * 2 + 1) * 64 + br];
+    if (a < 0) continue;
+    const int* Rr = w.bnd_root + ((strip0 + b) * 2 + 0) * 64;
+    const uint32_t* Lb = w.bnd_bits + ((strip0 + b - 1) * 2 + 1) * 4;
+    const uint32_t* Rb = w.bnd_bits + ((strip0 + b) * 2 + 0) * 4;
+    const uint32_t a0 = col_bit(Lb, 2 * br), a1 = col_bit(Lb, 2 * br + 1);
+    const uint32_t c0 = col_bit(Rb, 2 * br), c1 = col_bit(Rb, 2 * br + 1);
+    if ((a0 | a1) & (c0 | c1)) uf_union(parent, a, Rr[br]);
+    if (br > 0 && a0 && col_bit(Rb, 2 * br - 1)) uf_union(parent, a, Rr[br - 1]);
+    if (br < 63 && a1 && col_bit(Rb, 2 * br + 2)) uf_union(parent, a, Rr[br + 1]);
+  }
+  __threadfence();
   __syncthreads();
-  for (int64_t c = c0; c < c1; c += 256) {
-    const int64_t i = c + threadIdx.x;
-    const int v = (i < c1) ? chunk_count[i] : 0;
-    int inc = v;
+  // 2. boundary-touching local roots that are still roots are component roots
+  for (int i = tid; i < ns * 128; i += blockDim.x) {
+    const int k = w.bnd_root[strip0 * 128 + i];
+    if (k >= 0 && uf_find(parent, k) == k) atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+  }
+  __threadfence();
+  __syncthreads();
+  // 3. exclusive scan of the root counts per bitmap word (64 * bw / 32 words, a multiple of 128)
+  __shared__ int s_warp[16];
+  __shared__ int s_carry;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  const int words = 2 * ln.bw;
+  for (int c = 0; c < words; c += blockDim.x * 4) {
+    const int i = c + tid * 4;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i < words) v = __ldcg(reinterpret_cast<const uint4*>(bitmap + i));
+    const int n0 = __popc(v.x), n1 = __popc(v.y), n2 = __popc(v.z), n3 = __popc(v.w);
+    const int tot = n0 + n1 + n2 + n3;
+    int inc = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((tid & 31) >= o) inc += t;
     }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
     __syncthreads();
     int woff = 0;
-    for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += s_warp[w];
+    for (int k = 0; k < (tid >> 5); ++k) woff += s_warp[k];
     const int carry = s_carry;
-    if (i < c1) chunk_base[i] = carry + woff + inc - v;
+    const int ex = carry + woff + inc - tot;
+    if (i < words) *reinterpret_cast<int4*>(prefix + i) = make_int4(ex, ex + n0, ex + n0 + n1, ex + n0 + n1 + n2);
     __syncthreads();
-    if (threadIdx.x == 255) s_carry = carry + woff + inc;
+    if (tid == blockDim.x - 1) s_carry = carry + woff + inc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) num_out[l] = s_carry + 1;     // cv2 counts the background label
+  if (tid == 0) num_out[l] = s_carry + 1;             // cv2 counts the background label
 }
 
-// CTA == chunk: rank roots inside the chunk, write final label at the root's slot.
-__global__ void __launch_bounds__(256) ccl_rank_kernel(
-    const int* __restrict__ parent_all, const int* __restrict__ chunk_base, const sd_line* __restrict__ L,
-    int n_lines, int* __restrict__ rlabel_all) {
-  const int64_t base = (int64_t)blockIdx.x * SD_CCL_CHUNK + threadIdx.x * 8;
+__global__ void __launch_bounds__(256) ccl_strip_write_kernel(
+    const sd_line* __restrict__ L, int n_lines, CclWork w, int* __restrict__ labels) {
+  __shared__ __align__(16) uint16_t s_rec[kStripBlocks];
+  __shared__ int s_lab[kStripBlocks];
+  __shared__ __align__(16) uint8_t s_touch[kStripBlocks];
   __shared__ int s_l;
-  __shared__ int s_warp[8];
-  if (threadIdx.x == 0) s_l = find_line<true>(L, n_lines, (int64_t)blockIdx.x * SD_CCL_CHUNK);
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
+  if (tid == 0) s_l = find_line<true>(L, n_lines, blk0);
+  reinterpret_cast<uint4*>(s_touch)[tid] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  const int64_t blk_off = L[s_l].blk_off;
-  const int k0 = (int)(base - blk_off);
-  const int4* pp = reinterpret_cast<const int4*>(parent_all + base);
-  int4 a = pp[0], b = pp[1];
-  int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) cnt += (v[k] == k0 + k);
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((threadIdx.x & 31) >= o) inc += t;
+  const sd_line ln = L[s_l];
+  const int ns = ln.bw >> 6;
+  const int s = (int)((blk0 - ln.blk_off) >> 12);
+  const int br = tid >> 2, q = tid & 3;
+  const int base = br * 64 + q * 16;
+  uint4 ra, rb;
+  {
+    const uint4* rp = reinterpret_cast<const uint4*>(w.rec + ln.blk_off + (int64_t)br * ln.bw + s * 64 + q * 16);
+    ra = __ldcs(rp); rb = __ldcs(rp + 1);
+    reinterpret_cast<uint4*>(s_rec + base)[0] = ra;
+    reinterpret_cast<uint4*>(s_rec + base)[1] = rb;
   }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
   __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += s_warp[w];
-  int next = chunk_base[blockIdx.x] + woff + inc - cnt + 1;   // labels start at 1
-  int out[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = (v[k] == k0 + k) ? next++ : 0;
-  int4* rp = reinterpret_cast<int4*>(rlabel_all + base);
-  rp[0] = make_int4(out[0], out[1], out[2], out[3]);
-  rp[1] = make_int4(out[4], out[5], out[6], out[7]);
-}
-
-__global__ void __launch_bounds__(256) ccl_write_kernel(
-    const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, int64_t n_units,
-    const int* __restrict__ parent_all, const int* __restrict__ rlabel_all, int* __restrict__ labels) {
-  sd_line ln; int br, bc0;
-  if (!blk_unit(L, n_lines, n_units, ln, br, bc0)) return;
-  const int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t poff = ln.px_off + (int64_t)(2 * br) * ln.pitch + 2 * bc0;
-  const uint32_t t = nz16(__ldg(reinterpret_cast<const uint4*>(mask + poff)));
-  const uint32_t b = nz16(__ldg(reinterpret_cast<const uint4*>(mask + poff + ln.pitch)));
-  const int4* pp = reinterpret_cast<const int4*>(parent_all + unit * 8);
-  int lab[8];
-  if (t | b) {
-    int4 pa = pp[0], pb = pp[1];
-    int v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-    const int* rl = rlabel_all + ln.blk_off;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) lab[k] = (v[k] >= 0) ? __ldg(rl + v[k]) : 0;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) lab[k] = 0;
+  if (tid < 64) {
+    const uint32_t rc = s_rec[tid * 64];
+    if (s > 0 && (rc & 15u)) s_touch[rc >> 4] = 1;
+  } else if (tid < 128) {
+    const uint32_t rc = s_rec[(tid - 64) * 64 + 63];
+    if (s < ns - 1 && (rc & 15u)) s_touch[rc >> 4] = 1;
   }
-  int4* o0 = reinterpret_cast<int4*>(labels + poff);
-  int4* o1 = reinterpret_cast<int4*>(labels + poff + ln.pitch);
+  __syncthreads();
+  {
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    const int* parent = w.parent + ln.blk_off;
+    const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
+    const int* prefix = w.prefix + (ln.blk_off >> 5);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int4 r0, r1;
-    r0.x = ((t >> (4 * q + 0)) & 1u) ? lab[2 * q] : 0;
-    r0.y = ((t >> (4 * q + 1)) & 1u) ? lab[2 * q] : 0;
-    r0.z = ((t >> (4 * q + 2)) & 1u) ? lab[2 * q + 1] : 0;
-    r0.w = ((t >> (4 * q + 3)) & 1u) ? lab[2 * q + 1] : 0;
-    r1.x = ((b >> (4 * q + 0)) & 1u) ? lab[2 * q] : 0;
-    r1.y = ((b >> (4 * q + 1)) & 1u) ? lab[2 * q] : 0;
-    r1.z = ((b >> (4 * q + 2)) & 1u) ? lab[2 * q + 1] : 0;
-    r1.w = ((b >> (4 * q + 3)) & 1u) ? lab[2 * q + 1] : 0;
-    o0[q] = r0; o1[q] = r1;
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t rc = (rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+      const int idx = base + k;
+      if ((rc & 15u) && (int)(rc >> 4) == idx) {
+        int g = br * ln.bw + s * 64 + q * 16 + k;
+        if (s_touch[idx]) g = uf_find(parent, g);
+        s_lab[idx] = 1 + __ldg(prefix + (g >> 5)) + __popc(__ldg(bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
+      }
+    }
+  }
+  __syncthreads();
+  int* out = labels + ln.px_off + s * 128 + lane * 4;
+  const uint32_t* rec2 = reinterpret_cast<const uint32_t*>(s_rec);
+#pragma unroll 4
+  for (int it = 0; it < 16; ++it) {                   // a warp instruction writes one 512-B row segment
+    const int row = wp * 16 + it;
+    const uint32_t two = rec2[(row >> 1) * 32 + lane];
+    const uint32_t rc0 = two & 0xFFFFu, rc1 = two >> 16;
+    const int l0 = (rc0 & 15u) ? s_lab[rc0 >> 4] : 0, l1 = (rc1 & 15u) ? s_lab[rc1 >> 4] : 0;
+    const int sh = (row & 1) * 2;
+    int4 o;
+    o.x = ((rc0 >> sh) & 1u) ? l0 : 0; o.y = ((rc0 >> (sh + 1)) & 1u) ? l0 : 0;
+    o.z = ((rc1 >> sh) & 1u) ? l1 : 0; o.w = ((rc1 >> (sh + 1)) & 1u) ? l1 : 0;
+    __stcs(reinterpret_cast<int4*>(out + (int64_t)row * ln.pitch), o);
   }
 }
 
@@ -598,13 +680,13 @@ extern "C" int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, i
     else { ln.n_tiles = W / (tile_w - overlap) + 1; ln.wu = W / ln.n_tiles; }   // :25-26
     ln.first_tile = tiles;
     ln.tile_w = tile_w; ln.overlap = overlap;
-    ln.pitch = (W + 15) / 16 * 16;
+    ln.pitch = (W + 127) / 128 * 128;                 // whole 128-px CCL strips; rows start 128-B aligned
     ln.bw = ln.pitch / 2;
     ln.img_off = img; ln.px_off = px; ln.blk_off = blk;
     tiles += ln.n_tiles;
     img += ((int64_t)SD_TILE_H * W * 3 + 15) / 16 * 16;
     px += (int64_t)SD_TILE_H * ln.pitch;
-    blk += ((int64_t)(SD_TILE_H / 2) * ln.bw + SD_CCL_CHUNK - 1) / SD_CCL_CHUNK * SD_CCL_CHUNK;
+    blk += (int64_t)(SD_TILE_H / 2) * ln.bw;          // a multiple of SD_CCL_CHUNK (64 x 64 blocks per strip)
   }
   plan->img_bytes = img; plan->px_total = px; plan->blk_total = blk;
   plan->n_tiles = tiles; plan->n_lines = n_lines;
@@ -767,9 +849,8 @@ extern "C" int sd_glue_u8(const uint8_t* d_tiles, int n_tiles, const sd_line* d_
   SD_REQUIRE(d_tiles && d_lines && d_out && n_lines > 0 && n_tiles > 0 && px_total > 0 && px_total % 16 == 0,
              "sd_glue_u8: bad argument");
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;   // clamps edge loads
-  const int64_t units = px_total / 16;
-  glue_kernel<false><<<ceil_div(units, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_tiles, d_lines, n_lines, units, elems, 0.f, 0u, reinterpret_cast<uint4*>(d_out));
+  glue_kernel<false><<<n_lines * SD_TILE_H, 256, 0, (cudaStream_t)stream>>>(
+      d_tiles, d_lines, elems, 0.f, 0u, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<u8>");
   return SD_OK;
 }
@@ -780,44 +861,52 @@ extern "C" int sd_glue_threshold_f16(const void* d_prob, int n_tiles, const sd_l
              "sd_glue_threshold_f16: bad argument");
   SD_REQUIRE(on_value > 0 && on_value <= 255, "sd_glue_threshold_f16: on_value %d", on_value);
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;
-  const int64_t units = px_total / 16;
   const uint32_t rep = (uint32_t)on_value * 0x01010101u;
-  glue_kernel<true><<<ceil_div(units, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_prob, d_lines, n_lines, units, elems, bin_thr, rep, reinterpret_cast<uint4*>(d_out));
+  glue_kernel<true><<<n_lines * SD_TILE_H, 256, 0, (cudaStream_t)stream>>>(
+      d_prob, d_lines, elems, bin_thr, rep, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<f16>");
   return SD_OK;
 }
 
+namespace sd {
+static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+// carves the CCL workspace; returns the bytes used
+static size_t ccl_carve(void* base, int64_t blk_total, CclWork* w) {
+  const size_t strips = (size_t)(blk_total / kStripBlocks);
+  size_t off = 0;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += up256(bytes); return r; };
+  int* parent = reinterpret_cast<int*>(take((size_t)blk_total * 4));
+  uint16_t* rec = reinterpret_cast<uint16_t*>(take((size_t)blk_total * 2));
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(take((size_t)blk_total / 32 * 4));
+  int* prefix = reinterpret_cast<int*>(take((size_t)blk_total / 32 * 4));
+  int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
+  uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
+  if (w) { w->parent = parent; w->rec = rec; w->bitmap = bitmap; w->prefix = prefix; w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; }
+  return off;
+}
+}  // namespace sd
+
 extern "C" size_t sd_ccl_workspace_bytes(int64_t blk_total, int n_lines) {
   (void)n_lines;
-  const int64_t chunks = blk_total / SD_CCL_CHUNK;
-  return (size_t)(blk_total * 4 * 2 + chunks * 4 * 2 + 256);
+  return ccl_carve(nullptr, blk_total, nullptr) + 256;
 }
 
 extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
                             int64_t blk_total, int32_t* d_labels, int32_t* d_num, void* d_work, void* stream) {
   SD_REQUIRE(d_mask && d_lines && d_labels && d_num && d_work && n_lines > 0, "sd_ccl_label: null argument");
-  SD_REQUIRE(blk_total > 0 && blk_total % SD_CCL_CHUNK == 0 && px_total > 0, "sd_ccl_label: bad totals");
+  SD_REQUIRE(blk_total > 0 && blk_total % SD_CCL_CHUNK == 0 && px_total == blk_total * 4, "sd_ccl_label: bad totals");
+  SD_REQUIRE(((uintptr_t)d_mask & 15) == 0 && ((uintptr_t)d_labels & 15) == 0, "sd_ccl_label: planes must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  int* parent = reinterpret_cast<int*>(d_work);
-  int* rlabel = parent + blk_total;
-  const int64_t chunks = blk_total / SD_CCL_CHUNK;
-  int* chunk_count = rlabel + blk_total;
-  int* chunk_base = chunk_count + chunks;
-  const int64_t units = blk_total / 8;
-  const int grid = ceil_div(units, 256);
-  ccl_init_kernel<<<grid, 256, 0, s>>>(d_mask, d_lines, n_lines, units, parent);
-  SD_LAUNCH_CHECK("ccl_init_kernel");
-  ccl_merge_kernel<<<grid, 256, 0, s>>>(d_mask, d_lines, n_lines, units, parent);
-  SD_LAUNCH_CHECK("ccl_merge_kernel");
-  ccl_flatten_count_kernel<<<(int)chunks, 256, 0, s>>>(d_lines, n_lines, parent, chunk_count);
-  SD_LAUNCH_CHECK("ccl_flatten_count_kernel");
-  ccl_scan_kernel<<<n_lines, 256, 0, s>>>(d_lines, n_lines, blk_total, chunk_count, chunk_base, d_num);
-  SD_LAUNCH_CHECK("ccl_scan_kernel");
-  ccl_rank_kernel<<<(int)chunks, 256, 0, s>>>(parent, chunk_base, d_lines, n_lines, rlabel);
-  SD_LAUNCH_CHECK("ccl_rank_kernel");
-  ccl_write_kernel<<<grid, 256, 0, s>>>(d_mask, d_lines, n_lines, units, parent, rlabel, d_labels);
-  SD_LAUNCH_CHECK("ccl_write_kernel");
+  CclWork w;
+  ccl_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
+  const int strips = (int)(blk_total / kStripBlocks);
+  ccl_strip_label_kernel<<<strips, 256, 0, s>>>(d_mask, d_lines, n_lines, w);
+  SD_LAUNCH_CHECK("ccl_strip_label_kernel");
+  ccl_line_merge_kernel<<<n_lines, 512, 0, s>>>(d_lines, w, d_num);
+  SD_LAUNCH_CHECK("ccl_line_merge_kernel");
+  ccl_strip_write_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels);
+  SD_LAUNCH_CHECK("ccl_strip_write_kernel");
   return SD_OK;
 }
 

@@ -42,8 +42,8 @@ def test_plan_lines_matches_oracle_geometry():
         assert ln["n_tiles"] == len(ws) and ln["first_tile"] == t
         if len(ws) > 1:
             assert ln["wu"] == starts[1]
-        assert ln["pitch"] % 16 == 0 and ln["pitch"] >= W and ln["bw"] * 2 == ln["pitch"]
-        assert ln["px_off"] % 16 == 0 and ln["blk_off"] % 2048 == 0 and ln["img_off"] % 16 == 0
+        assert ln["pitch"] % 128 == 0 and ln["pitch"] >= W and ln["bw"] * 2 == ln["pitch"]
+        assert ln["px_off"] % 16 == 0 and ln["blk_off"] % 4096 == 0 and ln["img_off"] % 16 == 0
         t += len(ws)
     assert plan.n_tiles == t and plan.n_lines == len(widths)
     assert plan.px_total == int(sum(128 * ln["pitch"] for ln in lines))
