@@ -236,29 +236,33 @@ __global__ void __launch_bounds__(256) glue_kernel(
 // K7: connected-component labelling with OpenCV's numbering, strip-resident.
 //
 // A line (128 x pitch, pitch % 128 == 0) is cut into strips of 128 x 128 px = 64 x 64 blocks of
-// 2x2 px.  Three launches, 6 B/px of traffic against the 5 B/px algorithmic minimum:
-//   1. ccl_strip_label_kernel  (CTA = strip): mask -> bits in smem, block union-find in smem with
-//      min-root unions (root = smallest block key of the strip-local component), then per block
-//      a 16-bit record (local root << 4 | 2x2 occupancy) -> HBM (0.5 B/px).  Local roots that do
-//      not touch a neighbouring strip are final roots: their bits go to the line's root bitmap
-//      (plain stores, every strip owns its words).  Boundary-touching local roots are registered
-//      in a sparse global parent array; the strip's two boundary block columns (root keys +
-//      pixel bits) are emitted for the merge.
-//   2. ccl_line_merge_kernel (CTA = line): unions across strip boundaries on the sparse global
-//      parents (8-connectivity between the two pixel columns), marks the surviving boundary roots
-//      in the bitmap, then an exclusive scan of the bitmap popcounts: label(root key g) =
-//      1 + #roots with key < g = OpenCV's label, because a component's root is its first 2x2
-//      block in raster order.
-//   3. ccl_strip_write_kernel (CTA = strip): records -> final int32 labels, 512 B per warp store.
+// 2x2 px.  Five launches, 6 B/px of traffic against the 5 B/px algorithmic minimum:
+//   1. ccl_strip_label_kernel  (CTA = strip): mask -> 1 bit/px in smem.  A thread owns 16 blocks of one
+//      block row as 32-bit masks; horizontal runs of linked blocks are found with bit arithmetic, so
+//      the union-find (shared memory, min-root unions, path compression) has one node per RUN and one
+//      union per (run, upper run) contact instead of one per block.  Per block a 16-bit record
+//      (local root << 4 | 2x2 occupancy) -> HBM (0.5 B/px).  Local roots that do not touch a
+//      neighbouring strip are final: their bits go to the root bitmap (plain stores, every strip owns
+//      its words).  Boundary-touching local roots register in a sparse global parent array and the
+//      strip's two boundary block columns (root index + pixel bits) are emitted for the merge.
+//   2. ccl_boundary_merge_kernel (thread = boundary block row): unions across strip boundaries on the
+//      sparse global parents (8-connectivity between the two pixel columns).
+//   3. ccl_boundary_mark_kernel: boundary roots that are still roots -> bitmap.
+//   4. ccl_line_scan_kernel (CTA = line): exclusive scan of the bitmap popcounts: label(root g) =
+//      1 + #roots of the line with index < g = OpenCV's label, because a component's root is its
+//      first 2x2 block in raster order.
+//   5. ccl_strip_write_kernel (CTA = strip): records -> final int32 labels, 512 B per warp store.
+// Block indices are global: line.blk_off + br * bw + bc.
 // ---------------------------------------------------------------------------
 constexpr int kStripBlocks = 4096;
+constexpr uint32_t kEven = 0x55555555u;
 
 struct CclWork {
   int* parent;          // [blk_total]   sparse: boundary-touching local roots only
   uint16_t* rec;        // [blk_total]   (local root index << 4) | occupancy bits (p00, p01, p10, p11)
   uint32_t* bitmap;     // [blk_total/32] bit = block is the root (first block) of a component
   int* prefix;          // [blk_total/32] exclusive count of root bits before this word, per line
-  int* bnd_root;        // [strips][2][64] key of the local root of each boundary block, -1 if none
+  int* bnd_root;        // [strips][2][64] global index of the local root of each boundary block, -1 if none
   uint32_t* bnd_bits;   // [strips][2][4]  pixel column 0 / 127 of the strip, 128 rows
 };
 
@@ -272,6 +276,15 @@ __device__ __forceinline__ uint32_t nz16(uint4 v) {   // bit k = byte k non-zero
     r |= ((t >> 21) & 0xFu) << (4 * k);
   }
   return r;
+}
+
+// warp-cooperative line lookup: #lines whose block offset is <= off, minus one (lines are sorted)
+__device__ __forceinline__ int find_line_warp(const sd_line* __restrict__ L, int n, int64_t off, int lane) {
+  int cnt = 0;
+  for (int i = lane; i < n; i += 32) cnt += (L[i].blk_off <= off) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  return cnt - 1;
 }
 
 // global union-find on the sparse parents (min-root).  .cg loads: other CTAs' threads re-parent
@@ -294,13 +307,19 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-// shared-memory union-find of one strip; entry i lives at i + i/16 so that a thread's 16
-// consecutive blocks fall into 16 different banks than its neighbour's.
-#define SD_PH(i) ((i) + ((i) >> 4))
+// shared-memory union-find over run starts.  Parents only ever decrease (min-root), non-roots never
+// become roots again, and a compressing store writes an ancestor that is smaller than the value it
+// replaces, so the racing plain stores keep every tree valid; a union completes only when its
+// atomicMin hit a true root.
 __device__ __forceinline__ int suf_find(volatile int* p, int a) {
-  int q = p[SD_PH(a)];
-  while (q != a) { a = q; q = p[SD_PH(a)]; }
-  return a;
+  int r = a, q;
+  while ((q = p[r]) != r) r = q;
+  while (a > r) {
+    q = p[a];
+    if (q > r) p[a] = r;
+    a = q;
+  }
+  return r;
 }
 __device__ __forceinline__ void suf_union(int* p, int a, int b) {
   while (true) {
@@ -308,23 +327,32 @@ __device__ __forceinline__ void suf_union(int* p, int a, int b) {
     b = suf_find(p, b);
     if (a == b) return;
     if (a < b) { int t = a; a = b; b = t; }
-    int old = atomicMin(&p[SD_PH(a)], b);
+    int old = atomicMin(&p[a], b);
     if (old == a) return;
     a = old;
   }
 }
 
+// index (0..15) of the run start that owns block k: highest run-start bit at or below bit 2k
+__device__ __forceinline__ int run_start(uint32_t rs2, int k) {
+  return (31 - __clz(rs2 & ((2u << (2 * k)) - 1u))) >> 1;
+}
+
 __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
     const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, CclWork w) {
-  __shared__ uint32_t s_bits[129][4];                 // row 0 = the (empty) row above the image
-  __shared__ int s_parent[kStripBlocks + kStripBlocks / 16];
-  __shared__ __align__(16) uint8_t s_touch[kStripBlocks];
+  __shared__ uint32_t s_bits[131][4];                 // [2 + r] = pixel row r; rows -2, -1 are empty
+  __shared__ int s_parent[kStripBlocks];              // only run starts are live
+  __shared__ uint32_t s_rs[64][4];                    // run-start masks (bit 2k = block k of the thread starts a run)
+  __shared__ uint32_t s_touch[kStripBlocks / 32];     // local roots that touch a neighbouring strip
   __shared__ int s_l;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
-  if (tid == 0) s_l = find_line<true>(L, n_lines, blk0);
-  reinterpret_cast<uint4*>(s_touch)[tid] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 4) s_bits[0][tid] = 0u;
+  if (wp == 0) {
+    const int l = find_line_warp(L, n_lines, blk0, lane);
+    if (lane == 0) s_l = l;
+  }
+  if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
+  if (tid < 8) s_bits[tid >> 2][tid & 3] = 0u;
   __syncthreads();
   const sd_line ln = L[s_l];
   const int ns = ln.bw >> 6;                          // strips of this line
@@ -336,93 +364,98 @@ __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)row * ln.pitch) + (lane & 7));
     const uint32_t nz = nz16(v);
     const uint32_t other = __shfl_xor_sync(0xffffffffu, nz, 1);
-    if (!(lane & 1)) s_bits[row + 1][(lane & 7) >> 1] = nz | (other << 16);
+    if (!(lane & 1)) s_bits[row + 2][(lane & 7) >> 1] = nz | (other << 16);
   }
   __syncthreads();
 
-  // thread = 16 horizontally adjacent blocks of one block row: one 32-bit word of three pixel rows
+  // thread = 16 horizontally adjacent blocks of one block row = one 32-bit word of each pixel row.
+  // Windows: bit (1 + c) = pixel column c of the word, bit 0 = the pixel left of it, bit 33 = right of it.
   const int br = tid >> 2, q = tid & 3;
-  // bit (1 + c) = pixel column c of this word, bit 0 = the pixel left of it, bit 33 = the pixel right of it
-  uint64_t U = (uint64_t)s_bits[2 * br][q] << 1, T = (uint64_t)s_bits[2 * br + 1][q] << 1, B = (uint64_t)s_bits[2 * br + 2][q] << 1;
-  if (q > 0) {
-    U |= s_bits[2 * br][q - 1] >> 31; T |= s_bits[2 * br + 1][q - 1] >> 31; B |= s_bits[2 * br + 2][q - 1] >> 31;
-  }
-  if (q < 3) U |= (uint64_t)(s_bits[2 * br][q + 1] & 1u) << 33;
   const int base = br * 64 + q * 16;
-
-  // phase 1: horizontal runs inside the thread resolve in registers (parent = first block of the run)
-  uint32_t occ_mask = 0, link0 = 0;
-  {
-    int start = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const uint32_t t2 = (uint32_t)(T >> (1 + 2 * k)) & 3u, b2 = (uint32_t)(B >> (1 + 2 * k)) & 3u;
-      int pv = -1;
-      if (t2 | b2) {
-        const bool linked = ((t2 | b2) & 1u) && (((uint32_t)(T >> (2 * k)) | (uint32_t)(B >> (2 * k))) & 1u);
-        if (k == 0) link0 = linked ? 1u : 0u;
-        if (!linked || k == 0) start = k;
-        pv = base + start;
-        occ_mask |= 1u << k;
-      }
-      s_parent[SD_PH(base + k)] = pv;
-    }
+  auto window = [&](int i) -> uint64_t {
+    uint64_t v = (uint64_t)s_bits[i][q] << 1;
+    if (q > 0) v |= s_bits[i][q - 1] >> 31;
+    if (q < 3) v |= (uint64_t)(s_bits[i][q + 1] & 1u) << 33;
+    return v;
+  };
+  const uint64_t UUw = window(2 * br), Uw = window(2 * br + 1), Tw = window(2 * br + 2), Bw = window(2 * br + 3);
+  const uint64_t Pw = Tw | Bw, PUw = UUw | Uw;
+  // even-bit domain: bit 2k <-> block k of this thread
+  const uint32_t P1 = (uint32_t)(Pw >> 1);
+  const uint32_t occ2 = (P1 | (P1 >> 1)) & kEven;                      // block k has a pixel
+  const uint32_t hl2 = (uint32_t)(Pw & (Pw >> 1)) & kEven;             // block k touches block k-1 (8-conn)
+  const uint32_t hlU2 = (uint32_t)(PUw & (PUw >> 1)) & kEven;          // same for the block row above
+  const uint32_t rs2 = occ2 & ~(hl2 & ~1u);                            // run starts inside the thread
+  s_rs[br][q] = rs2;
+  for (uint32_t t = rs2; t; t &= t - 1) {
+    const int k = (__ffs(t) - 1) >> 1;
+    s_parent[base + k] = base + k;
   }
   __syncthreads();
 
-  // phase 2: unions with the previous thread's run and with the block row above
-  if (occ_mask) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (!((occ_mask >> k) & 1u)) continue;
-      const int idx = base + k;
-      const uint32_t p00 = (uint32_t)(T >> (1 + 2 * k)) & 1u, p01 = (uint32_t)(T >> (2 + 2 * k)) & 1u;
-      const uint32_t ul = (uint32_t)(U >> (2 * k)) & 1u, u10 = (uint32_t)(U >> (1 + 2 * k)) & 1u;
-      const uint32_t u11 = (uint32_t)(U >> (2 + 2 * k)) & 1u, ur = (uint32_t)(U >> (3 + 2 * k)) & 1u;
-      if (k == 0 && link0) suf_union(s_parent, idx, idx - 1);
-      const bool cu = (p00 | p01) & (u10 | u11);
-      if (cu) suf_union(s_parent, idx, idx - 64);
-      // up-left / up-right diagonals; redundant when the block above already links us and itself
-      // touches that diagonal pixel's block.
-      if ((p00 & ul) && !(cu && u10)) suf_union(s_parent, idx, idx - 65);
-      if ((p01 & ur) && !(cu && u11)) suf_union(s_parent, idx, idx - 63);
-    }
+  if (occ2) {
+    if (hl2 & 1u)                                     // run continues from the thread on the left
+      suf_union(s_parent, base, base - 16 + ((31 - __clz(s_rs[br][q - 1])) >> 1));
+    // contacts with the block row above (Uw == 0 for br == 0)
+    const uint32_t T0 = (uint32_t)(Tw >> 1) & kEven, T1 = (uint32_t)(Tw >> 2) & kEven;
+    const uint32_t U0 = (uint32_t)(Uw >> 1) & kEven, U1 = (uint32_t)(Uw >> 2) & kEven;
+    const uint32_t UL = (uint32_t)Uw & kEven, UR = (uint32_t)(Uw >> 3) & kEven;
+    const uint32_t vu0 = (T0 | T1) & (U0 | U1);       // block k - upper block k
+    uint32_t vl = T0 & UL;                            // block k - upper block k-1
+    uint32_t vr = T1 & UR;                            // block k - upper block k+1
+    // drop contacts that join the same (run, upper run) pair as a neighbouring contact
+    vl &= ~(vu0 & hlU2) & ~((vu0 << 2) & hl2);
+    vr &= ~(vu0 & (hlU2 >> 2)) & ~((vu0 >> 2) & (hl2 >> 2));
+    const uint32_t vu = vu0 & ~((vu0 << 2) & hl2 & hlU2);
+    auto link = [&](int k, int kp) {
+      int qq = q, kk = kp;
+      if (kp < 0) { qq = q - 1; kk = 15; } else if (kp > 15) { qq = q + 1; kk = 0; }
+      const int up = run_start(s_rs[br - 1][qq], kk);
+      suf_union(s_parent, base + run_start(rs2, k), base - 64 + (qq - q) * 16 + up);
+    };
+    for (uint32_t t = vu; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k); }
+    for (uint32_t t = vl; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k - 1); }
+    for (uint32_t t = vr; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k + 1); }
   }
   __syncthreads();
 
-  // phase 3: records, boundary columns
+  // records: every block of a run carries the run's root
   uint32_t recw[8];
   int r_first = 0, r_last = 0;
+  {
+    int root = 0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    uint32_t rc = 0;
-    if ((occ_mask >> k) & 1u) {
-      const int r = suf_find(s_parent, base + k);
-      const uint32_t occ4 = ((uint32_t)(T >> (1 + 2 * k)) & 3u) | (((uint32_t)(B >> (1 + 2 * k)) & 3u) << 2);
-      rc = ((uint32_t)r << 4) | occ4;
-      if (k == 0) r_first = r;
-      if (k == 15) r_last = r;
+    for (int k = 0; k < 16; ++k) {
+      uint32_t rc = 0;
+      if ((occ2 >> (2 * k)) & 1u) {
+        if ((rs2 >> (2 * k)) & 1u) root = suf_find(s_parent, base + k);
+        const uint32_t occ4 = ((uint32_t)(Tw >> (1 + 2 * k)) & 3u) | (((uint32_t)(Bw >> (1 + 2 * k)) & 3u) << 2);
+        rc = ((uint32_t)root << 4) | occ4;
+        if (k == 0) r_first = root;
+        if (k == 15) r_last = root;
+      }
+      if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
     }
-    if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
   }
   {
     uint4* rp = reinterpret_cast<uint4*>(w.rec + ln.blk_off + (int64_t)br * ln.bw + s * 64 + q * 16);
     rp[0] = make_uint4(recw[0], recw[1], recw[2], recw[3]);
     rp[1] = make_uint4(recw[4], recw[5], recw[6], recw[7]);
   }
+  const int gbase = (int)ln.blk_off + s * 64;         // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
   if (q == 0) {
-    const bool on = s > 0 && (occ_mask & 1u);
-    if (on) s_touch[r_first] = 1;
-    w.bnd_root[((int64_t)blockIdx.x * 2 + 0) * 64 + br] = on ? (r_first >> 6) * ln.bw + s * 64 + (r_first & 63) : -1;
+    const bool on = s > 0 && (occ2 & 1u);
+    if (on) atomicOr(&s_touch[r_first >> 5], 1u << (r_first & 31));
+    w.bnd_root[((int64_t)blockIdx.x * 2 + 0) * 64 + br] = on ? gbase + (r_first >> 6) * ln.bw + (r_first & 63) : -1;
   }
   if (q == 3) {
-    const bool on = s < ns - 1 && ((occ_mask >> 15) & 1u);
-    if (on) s_touch[r_last] = 1;
-    w.bnd_root[((int64_t)blockIdx.x * 2 + 1) * 64 + br] = on ? (r_last >> 6) * ln.bw + s * 64 + (r_last & 63) : -1;
+    const bool on = s < ns - 1 && ((occ2 >> 30) & 1u);
+    if (on) atomicOr(&s_touch[r_last >> 5], 1u << (r_last & 31));
+    w.bnd_root[((int64_t)blockIdx.x * 2 + 1) * 64 + br] = on ? gbase + (r_last >> 6) * ln.bw + (r_last & 63) : -1;
   }
   if (tid < 128) {
-    const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 1][0] & 1u);
-    const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 1][3] >> 31);
+    const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 2][0] & 1u);
+    const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 2][3] >> 31);
     if (lane == 0) {
       w.bnd_bits[((int64_t)blockIdx.x * 2 + 0) * 4 + wp] = m0;
       w.bnd_bits[((int64_t)blockIdx.x * 2 + 1) * 4 + wp] = m1;
@@ -432,15 +465,15 @@ __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
 
   // roots: interior ones are final -> bitmap; boundary-touching ones register in the global parents
   uint32_t rootbits = 0;
-  if (occ_mask) {
+  {
     volatile int* vp = s_parent;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (uint32_t t = rs2; t; t &= t - 1) {
+      const int k = (__ffs(t) - 1) >> 1;
       const int idx = base + k;
-      if (((occ_mask >> k) & 1u) && vp[SD_PH(idx)] == idx) {
-        if (s_touch[idx]) {
-          const int key = br * ln.bw + s * 64 + q * 16 + k;
-          w.parent[ln.blk_off + key] = key;
+      if (vp[idx] == idx) {
+        if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) {
+          const int g = gbase + br * ln.bw + q * 16 + k;
+          w.parent[g] = g;
         } else {
           rootbits |= 1u << k;
         }
@@ -453,41 +486,40 @@ __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
 
 __device__ __forceinline__ uint32_t col_bit(const uint32_t* __restrict__ p, int r) { return (p[r >> 5] >> (r & 31)) & 1u; }
 
-__global__ void __launch_bounds__(512) ccl_line_merge_kernel(
+// thread = one block row of one strip boundary: pixel column 127 of strip sg-1 against pixel column 0 of strip sg
+__global__ void __launch_bounds__(256) ccl_boundary_merge_kernel(CclWork w, int n_strips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_strips * 64) return;
+  const int sg = i >> 6, br = i & 63;
+  if (sg == 0) return;
+  const int a = w.bnd_root[((int64_t)(sg - 1) * 2 + 1) * 64 + br];
+  if (a < 0) return;                                  // empty, or strip sg-1 is the last strip of its line
+  const int* Rr = w.bnd_root + ((int64_t)sg * 2 + 0) * 64;
+  const uint32_t* Lb = w.bnd_bits + ((int64_t)(sg - 1) * 2 + 1) * 4;
+  const uint32_t* Rb = w.bnd_bits + ((int64_t)sg * 2 + 0) * 4;
+  const uint32_t a0 = col_bit(Lb, 2 * br), a1 = col_bit(Lb, 2 * br + 1);
+  const uint32_t c0 = col_bit(Rb, 2 * br), c1 = col_bit(Rb, 2 * br + 1);
+  if ((a0 | a1) & (c0 | c1)) uf_union(w.parent, a, Rr[br]);
+  if (br > 0 && a0 && col_bit(Rb, 2 * br - 1)) uf_union(w.parent, a, Rr[br - 1]);
+  if (br < 63 && a1 && col_bit(Rb, 2 * br + 2)) uf_union(w.parent, a, Rr[br + 1]);
+}
+
+// boundary-touching local roots that are still roots after the merge are component roots
+__global__ void __launch_bounds__(256) ccl_boundary_mark_kernel(CclWork w, int n_strips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_strips * 128) return;
+  const int k = w.bnd_root[i];
+  if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
+}
+
+// exclusive scan of the root counts per bitmap word of one line (64 * bw / 32 words, a multiple of 128)
+__global__ void __launch_bounds__(1024) ccl_line_scan_kernel(
     const sd_line* __restrict__ L, CclWork w, int* __restrict__ num_out) {
   const int l = blockIdx.x, tid = threadIdx.x;
   const sd_line ln = L[l];
-  const int ns = ln.bw >> 6;
-  const int64_t strip0 = ln.blk_off >> 12;
-  int* parent = w.parent + ln.blk_off;
-  uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
+  const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
   int* prefix = w.prefix + (ln.blk_off >> 5);
-
-  // 1. 8-connectivity across every strip boundary: pixel column 127 of strip b-1 against pixel column 0 of strip b
-  for (int i = tid; i < (ns - 1) * 64; i += blockDim.x) {
-    const int b = 1 + (i >> 6), br = i & 63;
-    const int a = w.bnd_root[((strip0 + b - 1) * 2 + 1) * 64 + br];
-    if (a < 0) continue;
-    const int* Rr = w.bnd_root + ((strip0 + b) * 2 + 0) * 64;
-    const uint32_t* Lb = w.bnd_bits + ((strip0 + b - 1) * 2 + 1) * 4;
-    const uint32_t* Rb = w.bnd_bits + ((strip0 + b) * 2 + 0) * 4;
-    const uint32_t a0 = col_bit(Lb, 2 * br), a1 = col_bit(Lb, 2 * br + 1);
-    const uint32_t c0 = col_bit(Rb, 2 * br), c1 = col_bit(Rb, 2 * br + 1);
-    if ((a0 | a1) & (c0 | c1)) uf_union(parent, a, Rr[br]);
-    if (br > 0 && a0 && col_bit(Rb, 2 * br - 1)) uf_union(parent, a, Rr[br - 1]);
-    if (br < 63 && a1 && col_bit(Rb, 2 * br + 2)) uf_union(parent, a, Rr[br + 1]);
-  }
-  __threadfence();
-  __syncthreads();
-  // 2. boundary-touching local roots that are still roots are component roots
-  for (int i = tid; i < ns * 128; i += blockDim.x) {
-    const int k = w.bnd_root[strip0 * 128 + i];
-    if (k >= 0 && uf_find(parent, k) == k) atomicOr(&bitmap[k >> 5], 1u << (k & 31));
-  }
-  __threadfence();
-  __syncthreads();
-  // 3. exclusive scan of the root counts per bitmap word (64 * bw / 32 words, a multiple of 128)
-  __shared__ int s_warp[16];
+  __shared__ int s_warp[32];
   __shared__ int s_carry;
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -506,12 +538,21 @@ __global__ void __launch_bounds__(512) ccl_line_merge_kernel(
     }
     if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
     __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < (tid >> 5); ++k) woff += s_warp[k];
+    int wv = (tid < 32) ? s_warp[tid] : 0;            // warp 0 scans the 32 warp totals
+    if (tid < 32) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wv, o);
+        if (tid >= o) wv += t;
+      }
+    }
     const int carry = s_carry;
+    __syncthreads();
+    if (tid < 32) s_warp[tid] = wv;                   // inclusive warp totals
+    __syncthreads();
+    const int woff = (tid >> 5) ? s_warp[(tid >> 5) - 1] : 0;
     const int ex = carry + woff + inc - tot;
     if (i < words) *reinterpret_cast<int4*>(prefix + i) = make_int4(ex, ex + n0, ex + n0 + n1, ex + n0 + n1 + n2);
-    __syncthreads();
     if (tid == blockDim.x - 1) s_carry = carry + woff + inc;
     __syncthreads();
   }
@@ -522,12 +563,15 @@ __global__ void __launch_bounds__(256) ccl_strip_write_kernel(
     const sd_line* __restrict__ L, int n_lines, CclWork w, int* __restrict__ labels) {
   __shared__ __align__(16) uint16_t s_rec[kStripBlocks];
   __shared__ int s_lab[kStripBlocks];
-  __shared__ __align__(16) uint8_t s_touch[kStripBlocks];
+  __shared__ uint32_t s_touch[kStripBlocks / 32];
   __shared__ int s_l;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
-  if (tid == 0) s_l = find_line<true>(L, n_lines, blk0);
-  reinterpret_cast<uint4*>(s_touch)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (wp == 0) {
+    const int l = find_line_warp(L, n_lines, blk0, lane);
+    if (lane == 0) s_l = l;
+  }
+  if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
   __syncthreads();
   const sd_line ln = L[s_l];
   const int ns = ln.bw >> 6;
@@ -544,25 +588,23 @@ __global__ void __launch_bounds__(256) ccl_strip_write_kernel(
   __syncthreads();
   if (tid < 64) {
     const uint32_t rc = s_rec[tid * 64];
-    if (s > 0 && (rc & 15u)) s_touch[rc >> 4] = 1;
+    if (s > 0 && (rc & 15u)) atomicOr(&s_touch[rc >> 9], 1u << ((rc >> 4) & 31));
   } else if (tid < 128) {
     const uint32_t rc = s_rec[(tid - 64) * 64 + 63];
-    if (s < ns - 1 && (rc & 15u)) s_touch[rc >> 4] = 1;
+    if (s < ns - 1 && (rc & 15u)) atomicOr(&s_touch[rc >> 9], 1u << ((rc >> 4) & 31));
   }
   __syncthreads();
   {
     const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    const int* parent = w.parent + ln.blk_off;
-    const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
-    const int* prefix = w.prefix + (ln.blk_off >> 5);
+    const int gbase = (int)ln.blk_off + s * 64;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint32_t rc = (rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
       const int idx = base + k;
       if ((rc & 15u) && (int)(rc >> 4) == idx) {
-        int g = br * ln.bw + s * 64 + q * 16 + k;
-        if (s_touch[idx]) g = uf_find(parent, g);
-        s_lab[idx] = 1 + __ldg(prefix + (g >> 5)) + __popc(__ldg(bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
+        int g = gbase + br * ln.bw + q * 16 + k;
+        if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) g = uf_find(w.parent, g);
+        s_lab[idx] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
       }
     }
   }
@@ -895,7 +937,8 @@ extern "C" size_t sd_ccl_workspace_bytes(int64_t blk_total, int n_lines) {
 extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
                             int64_t blk_total, int32_t* d_labels, int32_t* d_num, void* d_work, void* stream) {
   SD_REQUIRE(d_mask && d_lines && d_labels && d_num && d_work && n_lines > 0, "sd_ccl_label: null argument");
-  SD_REQUIRE(blk_total > 0 && blk_total % SD_CCL_CHUNK == 0 && px_total == blk_total * 4, "sd_ccl_label: bad totals");
+  SD_REQUIRE(blk_total > 0 && blk_total % SD_CCL_CHUNK == 0 && px_total == blk_total * 4 && blk_total < INT_MAX,
+             "sd_ccl_label: bad totals");
   SD_REQUIRE(((uintptr_t)d_mask & 15) == 0 && ((uintptr_t)d_labels & 15) == 0, "sd_ccl_label: planes must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   CclWork w;
@@ -903,8 +946,12 @@ extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n
   const int strips = (int)(blk_total / kStripBlocks);
   ccl_strip_label_kernel<<<strips, 256, 0, s>>>(d_mask, d_lines, n_lines, w);
   SD_LAUNCH_CHECK("ccl_strip_label_kernel");
-  ccl_line_merge_kernel<<<n_lines, 512, 0, s>>>(d_lines, w, d_num);
-  SD_LAUNCH_CHECK("ccl_line_merge_kernel");
+  ccl_boundary_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
+  SD_LAUNCH_CHECK("ccl_boundary_merge_kernel");
+  ccl_boundary_mark_kernel<<<ceil_div((int64_t)strips * 128, 256), 256, 0, s>>>(w, strips);
+  SD_LAUNCH_CHECK("ccl_boundary_mark_kernel");
+  ccl_line_scan_kernel<<<n_lines, 1024, 0, s>>>(d_lines, w, d_num);
+  SD_LAUNCH_CHECK("ccl_line_scan_kernel");
   ccl_strip_write_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels);
   SD_LAUNCH_CHECK("ccl_strip_write_kernel");
   return SD_OK;

@@ -20,5 +20,6 @@ out = [f"# ncu launch list summary ({len(rows)} launches, {tot/1000:.2f} ms of k
        "| kernel | launches | total ms | mean us | share |", "|---|---:|---:|---:|---:|"]
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{n}` | {c} | {t/1000:.3f} | {t/c:.1f} | {100*t/tot:.1f}% |")
-open(sys.argv[2], "w").write("\n".join(out) + "\n")
+if len(sys.argv) > 2:
+    open(sys.argv[2], "w").write("\n".join(out) + "\n")
 print("\n".join(out))
