@@ -264,18 +264,16 @@ struct CclWork {
   int* prefix;          // [blk_total/32] exclusive count of root bits before this word, per line
   int* bnd_root;        // [strips][2][64] global index of the local root of each boundary block, -1 if none
   uint32_t* bnd_bits;   // [strips][2][4]  pixel column 0 / 127 of the strip, 128 rows
+  void* strip_tab;      // [strips] StripInfo
 };
 
+__device__ __forceinline__ uint32_t nzflags(uint32_t w) {   // 0x80 in every non-zero byte
+  return (w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+}
 __device__ __forceinline__ uint32_t nz16(uint4 v) {   // bit k = byte k non-zero
-  uint32_t w[4] = {v.x, v.y, v.z, v.w}, r = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t t = w[k];
-    t = (t | ((t & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // msb of each non-zero byte
-    t = (t >> 7) * 0x00204081u;                                  // gather to bits 21..24
-    r |= ((t >> 21) & 0xFu) << (4 * k);
-  }
-  return r;
+  const uint32_t lo = __dp4a(nzflags(v.x), 0x08040201u, __dp4a(nzflags(v.y), 0x80402010u, 0u));   // 128 * bits 0..7
+  const uint32_t hi = __dp4a(nzflags(v.z), 0x08040201u, __dp4a(nzflags(v.w), 0x80402010u, 0u));
+  return (lo | (hi << 8)) >> 7;
 }
 
 // warp-cooperative line lookup: #lines whose block offset is <= off, minus one (lines are sorted)
@@ -338,150 +336,217 @@ __device__ __forceinline__ int run_start(uint32_t rs2, int k) {
   return (31 - __clz(rs2 & ((2u << (2 * k)) - 1u))) >> 1;
 }
 
+// one per strip, built on the device from the line table (no per-CTA search, one 32-byte load)
+struct __align__(16) StripInfo {
+  int64_t px0;          // element offset of the strip's top-left pixel in the packed planes
+  int32_t pitch, bw;
+  int32_t blk_base;     // line.blk_off + s * 64: global index of the strip's block (0, 0)
+  int32_t s, ns, line;
+};
+
+__global__ void __launch_bounds__(128) ccl_strip_table_kernel(const sd_line* __restrict__ L, StripInfo* __restrict__ tab) {
+  const sd_line ln = L[blockIdx.x];
+  const int ns = ln.bw >> 6;
+  const int64_t first = ln.blk_off >> 12;
+  for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+    StripInfo t;
+    t.px0 = ln.px_off + s * 128; t.pitch = ln.pitch; t.bw = ln.bw;
+    t.blk_base = (int)ln.blk_off + s * 64; t.s = s; t.ns = ns; t.line = blockIdx.x;
+    tab[first + s] = t;
+  }
+}
+
+__device__ __forceinline__ StripInfo load_strip(const StripInfo* __restrict__ tab, int i) {
+  const uint4* p = reinterpret_cast<const uint4*>(tab + i);
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  StripInfo t;
+  t.px0 = (int64_t)(((uint64_t)a.y << 32) | a.x); t.pitch = (int)a.z; t.bw = (int)a.w;
+  t.blk_base = (int)b.x; t.s = (int)b.y; t.ns = (int)b.z; t.line = (int)b.w;
+  return t;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// pair k (bits 2k, 2k+1) of x -> bits 4k, 4k+1
+__device__ __forceinline__ uint64_t spread_pairs(uint32_t x) {
+  uint64_t v = x;
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  v = (v | (v << 2)) & 0x3333333333333333ull;
+  return v;
+}
+
+// Persistent: a CTA walks strips blockIdx.x, += gridDim.x; the next strip's mask bytes stream into a
+// staging buffer with cp.async while the current strip is labelled.
 __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
-    const uint8_t* __restrict__ mask, const sd_line* __restrict__ L, int n_lines, CclWork w) {
+    const uint8_t* __restrict__ mask, const StripInfo* __restrict__ tab, int n_strips, CclWork w) {
+  __shared__ __align__(16) uint8_t s_stage[128 * 128];   // raw mask bytes of the strip being converted
   __shared__ uint32_t s_bits[131][4];                 // [2 + r] = pixel row r; rows -2, -1 are empty
   __shared__ int s_parent[kStripBlocks];              // only run starts are live
   __shared__ uint32_t s_rs[64][4];                    // run-start masks (bit 2k = block k of the thread starts a run)
   __shared__ uint32_t s_touch[kStripBlocks / 32];     // local roots that touch a neighbouring strip
-  __shared__ int s_l;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
-  if (wp == 0) {
-    const int l = find_line_warp(L, n_lines, blk0, lane);
-    if (lane == 0) s_l = l;
-  }
-  if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
-  if (tid < 8) s_bits[tid >> 2][tid & 3] = 0u;
-  __syncthreads();
-  const sd_line ln = L[s_l];
-  const int ns = ln.bw >> 6;                          // strips of this line
-  const int s = (int)((blk0 - ln.blk_off) >> 12);     // this strip
-  const uint8_t* m = mask + ln.px_off + s * 128;
+  int strip = blockIdx.x;
+  if (strip >= n_strips) return;
+  auto fetch = [&](const StripInfo& si) {             // a warp instruction moves 4 rows x 128 B
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {                    // a warp instruction reads 4 rows x 128 B
-    const int row = it * 32 + wp * 4 + (lane >> 3);
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(m + (int64_t)row * ln.pitch) + (lane & 7));
-    const uint32_t nz = nz16(v);
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, nz, 1);
-    if (!(lane & 1)) s_bits[row + 2][(lane & 7) >> 1] = nz | (other << 16);
-  }
-  __syncthreads();
-
-  // thread = 16 horizontally adjacent blocks of one block row = one 32-bit word of each pixel row.
-  // Windows: bit (1 + c) = pixel column c of the word, bit 0 = the pixel left of it, bit 33 = right of it.
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 32 + wp * 4 + (lane >> 3);
+      cp_async16(s_stage + row * 128 + (lane & 7) * 16, mask + si.px0 + (int64_t)row * si.pitch + (lane & 7) * 16);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  StripInfo cur = load_strip(tab, strip);
+  fetch(cur);
+  int nxt = strip + gridDim.x;
+  StripInfo ninfo = cur;
+  if (nxt < n_strips) ninfo = load_strip(tab, nxt);
+  if (tid < 8) s_bits[tid >> 2][tid & 3] = 0u;
   const int br = tid >> 2, q = tid & 3;
   const int base = br * 64 + q * 16;
-  auto window = [&](int i) -> uint64_t {
-    uint64_t v = (uint64_t)s_bits[i][q] << 1;
-    if (q > 0) v |= s_bits[i][q - 1] >> 31;
-    if (q < 3) v |= (uint64_t)(s_bits[i][q + 1] & 1u) << 33;
-    return v;
-  };
-  const uint64_t UUw = window(2 * br), Uw = window(2 * br + 1), Tw = window(2 * br + 2), Bw = window(2 * br + 3);
-  const uint64_t Pw = Tw | Bw, PUw = UUw | Uw;
-  // even-bit domain: bit 2k <-> block k of this thread
-  const uint32_t P1 = (uint32_t)(Pw >> 1);
-  const uint32_t occ2 = (P1 | (P1 >> 1)) & kEven;                      // block k has a pixel
-  const uint32_t hl2 = (uint32_t)(Pw & (Pw >> 1)) & kEven;             // block k touches block k-1 (8-conn)
-  const uint32_t hlU2 = (uint32_t)(PUw & (PUw >> 1)) & kEven;          // same for the block row above
-  const uint32_t rs2 = occ2 & ~(hl2 & ~1u);                            // run starts inside the thread
-  s_rs[br][q] = rs2;
-  for (uint32_t t = rs2; t; t &= t - 1) {
-    const int k = (__ffs(t) - 1) >> 1;
-    s_parent[base + k] = base + k;
-  }
-  __syncthreads();
 
-  if (occ2) {
+  while (true) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 32 + wp * 4 + (lane >> 3);
+      const uint4 v = *reinterpret_cast<const uint4*>(s_stage + row * 128 + (lane & 7) * 16);
+      const uint32_t nz = nz16(v);
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, nz, 1);
+      if (!(lane & 1)) s_bits[row + 2][(lane & 7) >> 1] = nz | (other << 16);
+    }
+    if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
+    __syncthreads();
+    const bool has_next = nxt < n_strips;
+    if (has_next) fetch(ninfo);                       // staging is free again
+    const int nn = nxt + gridDim.x;
+    StripInfo nninfo = ninfo;
+    if (nn < n_strips) nninfo = load_strip(tab, nn);
+
+    // thread = 16 horizontally adjacent blocks of one block row = one 32-bit word of each pixel row.
+    // Windows: bit (1 + c) = pixel column c of the word, bit 0 = the pixel left of it, bit 33 = right of it.
+    auto window = [&](int i) -> uint64_t {
+      uint64_t v = (uint64_t)s_bits[i][q] << 1;
+      if (q > 0) v |= s_bits[i][q - 1] >> 31;
+      if (q < 3) v |= (uint64_t)(s_bits[i][q + 1] & 1u) << 33;
+      return v;
+    };
+    const uint64_t UUw = window(2 * br), Uw = window(2 * br + 1), Tw = window(2 * br + 2), Bw = window(2 * br + 3);
+    const uint64_t Pw = Tw | Bw, PUw = UUw | Uw;
+    // even-bit domain: bit 2k <-> block k of this thread
+    const uint32_t P1 = (uint32_t)(Pw >> 1);
+    const uint32_t occ2 = (P1 | (P1 >> 1)) & kEven;                      // block k has a pixel
+    const uint32_t hl2 = (uint32_t)(Pw & (Pw >> 1)) & kEven;             // block k touches block k-1 (8-conn)
+    const uint32_t hlU2 = (uint32_t)(PUw & (PUw >> 1)) & kEven;          // same for the block row above
+    const uint32_t rs2 = occ2 & ~(hl2 & ~1u);                            // run starts inside the thread
+    s_rs[br][q] = rs2;
+    for (uint32_t t = rs2; t; t &= t - 1) {
+      const int k = (__ffs(t) - 1) >> 1;
+      s_parent[base + k] = base + k;
+    }
+    // contacts with the block row above (Uw == 0 for br == 0)
+    uint32_t vu, vl, vr;
+    {
+      const uint32_t T0 = (uint32_t)(Tw >> 1) & kEven, T1 = (uint32_t)(Tw >> 2) & kEven;
+      const uint32_t U0 = (uint32_t)(Uw >> 1) & kEven, U1 = (uint32_t)(Uw >> 2) & kEven;
+      const uint32_t UL = (uint32_t)Uw & kEven, UR = (uint32_t)(Uw >> 3) & kEven;
+      const uint32_t vu0 = (T0 | T1) & (U0 | U1);     // block k - upper block k
+      vl = T0 & UL;                                   // block k - upper block k-1
+      vr = T1 & UR;                                   // block k - upper block k+1
+      // drop contacts that join the same (run, upper run) pair as a neighbouring contact
+      vl &= ~(vu0 & hlU2) & ~((vu0 << 2) & hl2);
+      vr &= ~(vu0 & (hlU2 >> 2)) & ~((vu0 >> 2) & (hl2 >> 2));
+      vu = vu0 & ~((vu0 << 2) & hl2 & hlU2);
+    }
+    __syncthreads();
+
+    // One loop over all contacts of the thread (a single copy of the union code, so the lanes of a warp
+    // run it together): bit 2k = up, bit 2k+1 = up-left, bit 32+2k = up-right of block k.
     if (hl2 & 1u)                                     // run continues from the thread on the left
       suf_union(s_parent, base, base - 16 + ((31 - __clz(s_rs[br][q - 1])) >> 1));
-    // contacts with the block row above (Uw == 0 for br == 0)
-    const uint32_t T0 = (uint32_t)(Tw >> 1) & kEven, T1 = (uint32_t)(Tw >> 2) & kEven;
-    const uint32_t U0 = (uint32_t)(Uw >> 1) & kEven, U1 = (uint32_t)(Uw >> 2) & kEven;
-    const uint32_t UL = (uint32_t)Uw & kEven, UR = (uint32_t)(Uw >> 3) & kEven;
-    const uint32_t vu0 = (T0 | T1) & (U0 | U1);       // block k - upper block k
-    uint32_t vl = T0 & UL;                            // block k - upper block k-1
-    uint32_t vr = T1 & UR;                            // block k - upper block k+1
-    // drop contacts that join the same (run, upper run) pair as a neighbouring contact
-    vl &= ~(vu0 & hlU2) & ~((vu0 << 2) & hl2);
-    vr &= ~(vu0 & (hlU2 >> 2)) & ~((vu0 >> 2) & (hl2 >> 2));
-    const uint32_t vu = vu0 & ~((vu0 << 2) & hl2 & hlU2);
-    auto link = [&](int k, int kp) {
+    for (uint64_t t = (uint64_t)(vu | (vl << 1)) | ((uint64_t)vr << 32); t; t &= t - 1) {
+      const int b = __ffsll((long long)t) - 1;
+      const int k = (b & 31) >> 1;
+      const int kp = k + (b >= 32 ? 1 : -(b & 1));
       int qq = q, kk = kp;
       if (kp < 0) { qq = q - 1; kk = 15; } else if (kp > 15) { qq = q + 1; kk = 0; }
       const int up = run_start(s_rs[br - 1][qq], kk);
       suf_union(s_parent, base + run_start(rs2, k), base - 64 + (qq - q) * 16 + up);
-    };
-    for (uint32_t t = vu; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k); }
-    for (uint32_t t = vl; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k - 1); }
-    for (uint32_t t = vr; t; t &= t - 1) { const int k = (__ffs(t) - 1) >> 1; link(k, k + 1); }
-  }
-  __syncthreads();
+    }
+    __syncthreads();
+    // flatten: afterwards s_parent[run start] is the run's root
+    for (uint32_t t = rs2; t; t &= t - 1) suf_find(s_parent, base + ((__ffs(t) - 1) >> 1));
 
-  // records: every block of a run carries the run's root
-  uint32_t recw[8];
-  int r_first = 0, r_last = 0;
-  {
-    int root = 0;
+    // records: every block of a run carries the run's root
+    uint32_t recw[8];
+    int r_first = 0, r_last = 0;
+    {
+      const uint64_t nib = spread_pairs((uint32_t)(Tw >> 1)) | (spread_pairs((uint32_t)(Bw >> 1)) << 2);   // nibble k = 2x2 occupancy
+      volatile int* vp = s_parent;
+      int root = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      uint32_t rc = 0;
-      if ((occ2 >> (2 * k)) & 1u) {
-        if ((rs2 >> (2 * k)) & 1u) root = suf_find(s_parent, base + k);
-        const uint32_t occ4 = ((uint32_t)(Tw >> (1 + 2 * k)) & 3u) | (((uint32_t)(Bw >> (1 + 2 * k)) & 3u) << 2);
-        rc = ((uint32_t)root << 4) | occ4;
+      for (int k = 0; k < 16; ++k) {
+        if ((rs2 >> (2 * k)) & 1u) root = vp[base + k];
+        const uint32_t occ4 = (uint32_t)(nib >> (4 * k)) & 15u;
+        const uint32_t rc = occ4 ? (((uint32_t)root << 4) | occ4) : 0u;
         if (k == 0) r_first = root;
         if (k == 15) r_last = root;
+        if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
       }
-      if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
     }
-  }
-  {
-    uint4* rp = reinterpret_cast<uint4*>(w.rec + ln.blk_off + (int64_t)br * ln.bw + s * 64 + q * 16);
-    rp[0] = make_uint4(recw[0], recw[1], recw[2], recw[3]);
-    rp[1] = make_uint4(recw[4], recw[5], recw[6], recw[7]);
-  }
-  const int gbase = (int)ln.blk_off + s * 64;         // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
-  if (q == 0) {
-    const bool on = s > 0 && (occ2 & 1u);
-    if (on) atomicOr(&s_touch[r_first >> 5], 1u << (r_first & 31));
-    w.bnd_root[((int64_t)blockIdx.x * 2 + 0) * 64 + br] = on ? gbase + (r_first >> 6) * ln.bw + (r_first & 63) : -1;
-  }
-  if (q == 3) {
-    const bool on = s < ns - 1 && ((occ2 >> 30) & 1u);
-    if (on) atomicOr(&s_touch[r_last >> 5], 1u << (r_last & 31));
-    w.bnd_root[((int64_t)blockIdx.x * 2 + 1) * 64 + br] = on ? gbase + (r_last >> 6) * ln.bw + (r_last & 63) : -1;
-  }
-  if (tid < 128) {
-    const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 2][0] & 1u);
-    const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 2][3] >> 31);
-    if (lane == 0) {
-      w.bnd_bits[((int64_t)blockIdx.x * 2 + 0) * 4 + wp] = m0;
-      w.bnd_bits[((int64_t)blockIdx.x * 2 + 1) * 4 + wp] = m1;
+    const int blk_off = cur.blk_base - cur.s * 64;    // the line's block offset
+    {
+      uint4* rp = reinterpret_cast<uint4*>(w.rec + cur.blk_base + (int64_t)br * cur.bw + q * 16);
+      rp[0] = make_uint4(recw[0], recw[1], recw[2], recw[3]);
+      rp[1] = make_uint4(recw[4], recw[5], recw[6], recw[7]);
     }
-  }
-  __syncthreads();
+    const int gbase = cur.blk_base;                   // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
+    if (q == 0) {
+      const bool on = cur.s > 0 && (occ2 & 1u);
+      if (on) atomicOr(&s_touch[r_first >> 5], 1u << (r_first & 31));
+      w.bnd_root[((int64_t)strip * 2 + 0) * 64 + br] = on ? gbase + (r_first >> 6) * cur.bw + (r_first & 63) : -1;
+    }
+    if (q == 3) {
+      const bool on = cur.s < cur.ns - 1 && ((occ2 >> 30) & 1u);
+      if (on) atomicOr(&s_touch[r_last >> 5], 1u << (r_last & 31));
+      w.bnd_root[((int64_t)strip * 2 + 1) * 64 + br] = on ? gbase + (r_last >> 6) * cur.bw + (r_last & 63) : -1;
+    }
+    if (tid < 128) {
+      const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 2][0] & 1u);
+      const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 2][3] >> 31);
+      if (lane == 0) {
+        w.bnd_bits[((int64_t)strip * 2 + 0) * 4 + wp] = m0;
+        w.bnd_bits[((int64_t)strip * 2 + 1) * 4 + wp] = m1;
+      }
+    }
+    __syncthreads();
 
-  // roots: interior ones are final -> bitmap; boundary-touching ones register in the global parents
-  uint32_t rootbits = 0;
-  {
-    volatile int* vp = s_parent;
-    for (uint32_t t = rs2; t; t &= t - 1) {
-      const int k = (__ffs(t) - 1) >> 1;
-      const int idx = base + k;
-      if (vp[idx] == idx) {
-        if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) {
-          const int g = gbase + br * ln.bw + q * 16 + k;
-          w.parent[g] = g;
-        } else {
-          rootbits |= 1u << k;
+    // roots: interior ones are final -> bitmap; boundary-touching ones register in the global parents
+    uint32_t rootbits = 0;
+    {
+      volatile int* vp = s_parent;
+      for (uint32_t t = rs2; t; t &= t - 1) {
+        const int k = (__ffs(t) - 1) >> 1;
+        const int idx = base + k;
+        if (vp[idx] == idx) {
+          if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) {
+            const int g = gbase + br * cur.bw + q * 16 + k;
+            w.parent[g] = g;
+          } else {
+            rootbits |= 1u << k;
+          }
         }
       }
     }
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, rootbits, 1);
+    if (!(q & 1)) w.bitmap[(blk_off >> 5) + (int64_t)br * (cur.bw >> 5) + cur.s * 2 + (q >> 1)] = rootbits | (other << 16);
+    if (!has_next) break;
+    cur = ninfo; ninfo = nninfo; strip = nxt; nxt = nn;
   }
-  const uint32_t other = __shfl_xor_sync(0xffffffffu, rootbits, 1);
-  if (!(q & 1)) w.bitmap[(ln.blk_off >> 5) + (int64_t)br * (ln.bw >> 5) + s * 2 + (q >> 1)] = rootbits | (other << 16);
 }
 
 __device__ __forceinline__ uint32_t col_bit(const uint32_t* __restrict__ p, int r) { return (p[r >> 5] >> (r & 31)) & 1u; }
@@ -924,8 +989,24 @@ static size_t ccl_carve(void* base, int64_t blk_total, CclWork* w) {
   int* prefix = reinterpret_cast<int*>(take((size_t)blk_total / 32 * 4));
   int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
   uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
-  if (w) { w->parent = parent; w->rec = rec; w->bitmap = bitmap; w->prefix = prefix; w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; }
+  void* strip_tab = take(strips * 32);
+  if (w) { w->strip_tab = strip_tab; w->parent = parent; w->rec = rec; w->bitmap = bitmap; w->prefix = prefix; w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; }
   return off;
+}
+}  // namespace sd
+
+namespace sd {
+// persistent label kernel: as many CTAs as fit on the device at once
+static int ccl_label_grid() {
+  static int grid = 0;
+  if (!grid) {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_strip_label_kernel, 256, 0);
+    grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  return grid;
 }
 }  // namespace sd
 
@@ -944,7 +1025,10 @@ extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n
   CclWork w;
   ccl_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
   const int strips = (int)(blk_total / kStripBlocks);
-  ccl_strip_label_kernel<<<strips, 256, 0, s>>>(d_mask, d_lines, n_lines, w);
+  ccl_strip_table_kernel<<<n_lines, 128, 0, s>>>(d_lines, reinterpret_cast<StripInfo*>(w.strip_tab));
+  SD_LAUNCH_CHECK("ccl_strip_table_kernel");
+  ccl_strip_label_kernel<<<std::min(strips, ccl_label_grid()), 256, 0, s>>>(
+      d_mask, reinterpret_cast<const StripInfo*>(w.strip_tab), strips, w);
   SD_LAUNCH_CHECK("ccl_strip_label_kernel");
   ccl_boundary_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
   SD_LAUNCH_CHECK("ccl_boundary_merge_kernel");
