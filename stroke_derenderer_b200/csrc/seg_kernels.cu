@@ -141,9 +141,8 @@ __device__ __forceinline__ void load16_u8(const uint8_t* __restrict__ base, int6
   uint32_t w[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    int64_t wi = w0 + k;
-    wi = wi < 0 ? 0 : (wi > wmax ? wmax : wi);    // clamped words are masked by the caller
-    w[k] = __ldg(wp + wi);
+    const int64_t wi = w0 + k;                    // words outside the buffer are masked by the caller
+    w[k] = (wi >= 0 && wi <= wmax) ? __ldg(wp + wi) : 0u;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
@@ -159,9 +158,8 @@ __device__ __forceinline__ void load16_f16_thr(const __half* __restrict__ base, 
   uint32_t w[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
-    int64_t wi = w0 + k;
-    wi = wi < 0 ? 0 : (wi > wmax ? wmax : wi);
-    w[k] = __ldg(wp + wi);
+    const int64_t wi = w0 + k;
+    w[k] = (wi >= 0 && wi <= wmax) ? __ldg(wp + wi) : 0u;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -189,18 +187,22 @@ __device__ __forceinline__ uint32_t range_mask(int wi, int lo, int hi) {
   return m;
 }
 
-// one CTA per (line, row): no offset search, every thread walks 16-px units of that row.
+// one CTA per (line, group of kGlueRows rows): a thread owns one 16-px unit column, resolves the covering
+// tiles once and then issues the loads of all its rows back to back (the kernel is latency bound otherwise).
+constexpr int kGlueRows = 4;
 template <bool kProb>
-__global__ void __launch_bounds__(256) glue_kernel(
+__global__ void __launch_bounds__(128) glue_kernel(
     const void* __restrict__ tiles, const sd_line* __restrict__ L, int64_t tile_elems_total, float thr,
     uint32_t on_rep, uint4* __restrict__ out) {
-  const int l = blockIdx.x >> 7, row = blockIdx.x & 127;
+  constexpr int kGroups = SD_TILE_H / kGlueRows;
+  const int l = blockIdx.x / kGroups, r0 = (blockIdx.x % kGroups) * kGlueRows;
   const sd_line ln = L[l];
-  uint4* dst = out + ((ln.px_off + (int64_t)row * ln.pitch) >> 4);
   const int units = ln.pitch >> 4;
   for (int u = threadIdx.x; u < units; u += blockDim.x) {
     const int x0 = u * 16;
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    uint32_t acc[kGlueRows][4];
+#pragma unroll
+    for (int r = 0; r < kGlueRows; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0u; }
     if (x0 < ln.width) {
       const int xl = min(x0 + 15, ln.width - 1);
       const int iA = (ln.n_tiles == 1) ? 0 : min(xl / ln.wu, ln.n_tiles - 1);
@@ -213,22 +215,28 @@ __global__ void __launch_bounds__(256) glue_kernel(
         // valid run positions k: 0 <= x0 + k - start < wd  and x0 + k < W
         const int lo = max(0, start - x0), hi = min(min(16, start + wd - x0), ln.width - x0);
         if (lo >= hi) continue;
-        const int64_t e = ((int64_t)(ln.first_tile + i) * SD_TILE_H + row) * ln.tile_w + (x0 - start);
-        uint32_t v[4];
-        if (kProb) load16_f16_thr(reinterpret_cast<const __half*>(tiles), e, tile_elems_total, thr, v);
-        else load16_u8(reinterpret_cast<const uint8_t*>(tiles), e, tile_elems_total, v);
+        const uint32_t m0 = range_mask(0, lo, hi), m1 = range_mask(1, lo, hi), m2 = range_mask(2, lo, hi), m3 = range_mask(3, lo, hi);
+        const int64_t e0 = ((int64_t)(ln.first_tile + i) * SD_TILE_H + r0) * ln.tile_w + (x0 - start);
+        uint32_t v[kGlueRows][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t m = v[k] & range_mask(k, lo, hi);
-          acc[k] = kProb ? (acc[k] | m) : __vmaxu4(acc[k], m);
+        for (int r = 0; r < kGlueRows; ++r) {
+          if (kProb) load16_f16_thr(reinterpret_cast<const __half*>(tiles), e0 + (int64_t)r * ln.tile_w, tile_elems_total, thr, v[r]);
+          else load16_u8(reinterpret_cast<const uint8_t*>(tiles), e0 + (int64_t)r * ln.tile_w, tile_elems_total, v[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kGlueRows; ++r) {
+          acc[r][0] = kProb ? (acc[r][0] | (v[r][0] & m0)) : __vmaxu4(acc[r][0], v[r][0] & m0);
+          acc[r][1] = kProb ? (acc[r][1] | (v[r][1] & m1)) : __vmaxu4(acc[r][1], v[r][1] & m1);
+          acc[r][2] = kProb ? (acc[r][2] | (v[r][2] & m2)) : __vmaxu4(acc[r][2], v[r][2] & m2);
+          acc[r][3] = kProb ? (acc[r][3] | (v[r][3] & m3)) : __vmaxu4(acc[r][3], v[r][3] & m3);
         }
       }
-      if (kProb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] &= on_rep;
-      }
     }
-    dst[u] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int r = 0; r < kGlueRows; ++r) {
+      if (kProb) { acc[r][0] &= on_rep; acc[r][1] &= on_rep; acc[r][2] &= on_rep; acc[r][3] &= on_rep; }
+      out[((ln.px_off + (int64_t)(r0 + r) * ln.pitch) >> 4) + u] = make_uint4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
   }
 }
 
@@ -956,7 +964,7 @@ extern "C" int sd_glue_u8(const uint8_t* d_tiles, int n_tiles, const sd_line* d_
   SD_REQUIRE(d_tiles && d_lines && d_out && n_lines > 0 && n_tiles > 0 && px_total > 0 && px_total % 16 == 0,
              "sd_glue_u8: bad argument");
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;   // clamps edge loads
-  glue_kernel<false><<<n_lines * SD_TILE_H, 256, 0, (cudaStream_t)stream>>>(
+  glue_kernel<false><<<n_lines * (SD_TILE_H / kGlueRows), 128, 0, (cudaStream_t)stream>>>(
       d_tiles, d_lines, elems, 0.f, 0u, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<u8>");
   return SD_OK;
@@ -969,7 +977,7 @@ extern "C" int sd_glue_threshold_f16(const void* d_prob, int n_tiles, const sd_l
   SD_REQUIRE(on_value > 0 && on_value <= 255, "sd_glue_threshold_f16: on_value %d", on_value);
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;
   const uint32_t rep = (uint32_t)on_value * 0x01010101u;
-  glue_kernel<true><<<n_lines * SD_TILE_H, 256, 0, (cudaStream_t)stream>>>(
+  glue_kernel<true><<<n_lines * (SD_TILE_H / kGlueRows), 128, 0, (cudaStream_t)stream>>>(
       d_prob, d_lines, elems, bin_thr, rep, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<f16>");
   return SD_OK;
