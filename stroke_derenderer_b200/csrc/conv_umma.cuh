@@ -152,25 +152,30 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 constexpr int kMiscBytes = 4096;       // barriers | tmem slot | bias | psi/head vector | gate scale | pixel index
 constexpr int kMaxSmem = 232448;       // 227 KB opt-in limit per CTA
 
-template <int BN, int EPI> struct ConvCfg {
-  static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves
+// MT = M tiles (128 pixels each) that share one B k-block in shared memory.  A 128 x 128 tile reads
+// 32 KB of operands per 256 MMA cycles = the full 128 B/clk of shared-memory bandwidth and stalls the
+// tensor pipe; 128 x 256 (BN = 256) or 2 x (128 x 128) (MT = 2) needs 96 B/clk.
+template <int BN, int EPI, int MT = 1> struct ConvCfg {
+  static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves, per M tile
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * BN * 2 : 0;   // swizzled staging for the TMA store
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * 64 * 2 : 0;   // swizzled staging of ONE 64-channel half for the TMA store
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // 64,128,256,512: powers of two
+  static constexpr int kTmemCols = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // 64,128,256,512: powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + kMiscBytes;
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(EPI != EPI_STORE || BN % 64 == 0, "store epilogue writes 64-channel boxes");
+  static_assert(MT == 1 || EPI == EPI_STORE, "multi-M tiles are implemented for the store epilogue");
 };
 
 constexpr int kConvThreads = 192;
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, EPI>;
+  using Cfg = ConvCfg<BN, EPI, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -218,30 +223,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_work = p.m_tiles * p.n_tiles * p.n_phases;
+  const int m_groups = (p.m_tiles + MT - 1) / MT;
+  const int n_work = m_groups * p.n_tiles * p.n_phases;
   const int kb_per_tap = p.c0_blocks + p.c1_blocks;
   const int num_kb = p.n_taps * kb_per_tap;
+  // M tile index -> pixel origin; a phantom tile (odd tail of an MT group) lands beyond the batch, where the
+  // TMA unit zero-fills loads and clips stores
+  auto origin = [&](int mt, int& x0, int& y0, int& n0) {
+    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
+    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
+    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+  };
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int nt = w % p.n_tiles; int rest = w / p.n_tiles;
-        const int mt = rest % p.m_tiles; const int ph = rest / p.m_tiles;
-        const int tx = mt % p.tiles_x; rest = mt / p.tiles_x;
-        const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-        const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
+        const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
+        const int mg = rest % m_groups; const int ph = rest / m_groups;
+        int x0[MT], y0[MT], n0[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) origin(mg * MT + m, x0[m], y0[m], n0[m]);
         const int brow = ph * p.cout + nt * BN;
         for (int tap = 0; tap < p.n_taps; ++tap) {
-          const int xx = x0 + p.dx[ph][tap], yy = y0 + p.dy[ph][tap];
+          const int dx = p.dx[ph][tap], dy = p.dy[ph][tap];
           for (int cb = 0; cb < kb_per_tap; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
             mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-            if (cb < p.c0_blocks) tma_load_4d(a_dst, &p.tmA0, full_bar(stage), cb * 64, xx, yy, n0);
-            else tma_load_4d(a_dst, &p.tmA1, full_bar(stage), (cb - p.c0_blocks) * 64, xx, yy, n0);
-            tma_load_2d(a_dst + Cfg::kABytes, &p.tmB, full_bar(stage), (tap * kb_per_tap + cb) * 64, brow);
+            const CUtensorMap* tm = cb < p.c0_blocks ? &p.tmA0 : &p.tmA1;
+            const int c = (cb < p.c0_blocks ? cb : cb - p.c0_blocks) * 64;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_4d(a_dst + m * Cfg::kABytes, tm, full_bar(stage), c, x0[m] + dx, y0[m] + dy, n0[m]);
+            tma_load_2d(a_dst + MT * Cfg::kABytes, &p.tmB, full_bar(stage), (tap * kb_per_tap + cb) * 64, brow);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -256,20 +272,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + MT * Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, Cfg::kIdesc, (uint32_t)((kb | k) != 0));
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = umma_desc_sw128(a_addr + m * Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // UMMA_K = 16 halves = 32 B -> +2 in the (addr >> 4) field
+              umma_f16(d_tmem + (uint32_t)(m * BN), adesc + 2u * k, bdesc + 2u * k, Cfg::kIdesc, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
+        umma_commit(tfull_bar(as));               // accumulators complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -284,58 +303,67 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     int as = 0; uint32_t aphase = 0;
     int cur_nt = -1;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int nt = w % p.n_tiles; int rest = w / p.n_tiles;
-      const int mt = rest % p.m_tiles; const int ph = rest / p.m_tiles;
-      const int tx = mt % p.tiles_x; rest = mt / p.tiles_x;
-      const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
+      const int mg = rest % m_groups; const int ph = rest / m_groups;
 
       if constexpr (EPI == EPI_STORE) {
         if (nt != cur_nt) {                       // bias slice of this N tile -> smem (uniform branch)
           epi_bar();                              // everybody is done reading the previous slice
-          if (et < BN) s_bias[et] = __ldg(p.bias + nt * BN + et);
+          for (int i = et; i < BN; i += 128) s_bias[i] = __ldg(p.bias + nt * BN + i);
           cur_nt = nt;
           epi_bar();
         }
         mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
         tc_fence_after();
-        // the previous tile's TMA store must have finished READING the staging buffer
-        if (et == 0) tma_store_wait_read();
-        epi_bar();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          // 128 rows x 128 B per 64-channel half, 16-B chunk j of row r lives at chunk (j ^ (r & 7))
-          const uint32_t half_base = out_base + (uint32_t)(c >> 1) * 16384u + (uint32_t)row * 128u;
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * MT + m) * BN);
+          int x0, y0, n0;
+          origin(mg * MT + m, x0, y0, n0);
+#pragma unroll 1
+          for (int hb = 0; hb < BN / 64; ++hb) {
+            // the previous TMA store must have finished READING the staging buffer
+            if (et == 0) tma_store_wait_read();
+            epi_bar();
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t pk[4];
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = hb * 2 + cc;
+              float v[32];
+              tmem_ld32(taddr + c * 32, v);
+              // 128 rows x 128 B, 16-B chunk j of row r lives at chunk (j ^ (r & 7))
+              const uint32_t row_base = out_base + (uint32_t)row * 128u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = j4 * 8 + j * 2;
-              float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
-              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              __half2 h = __floats2half2_rn(a, b);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int col = j4 * 8 + j * 2;
+                  float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
+                  if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                  __half2 h = __floats2half2_rn(a, b);
+                  pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                const uint32_t chunk = (uint32_t)(cc * 4 + j4);
+                const uint32_t addr = row_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              }
             }
-            const uint32_t chunk = (uint32_t)((c & 1) * 4 + j4);
-            const uint32_t addr = half_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            if (m == MT - 1 && hb == BN / 64 - 1) {
+              tc_fence_before();
+              mbar_arrive(tempty_bar(as));        // TMEM stage free: the next work item's MMAs may start
+            }
+            fence_async_smem();                   // generic-proxy smem writes -> visible to the TMA unit
+            epi_bar();
+            if (et == 0) {
+              tma_store_4d(&p.tmOut[ph], out_base, nt * BN + hb * 64, x0, y0, n0);
+              tma_store_commit();
+            }
           }
         }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(as));              // TMEM stage free: the next tile's MMAs may start
-        fence_async_smem();                       // generic-proxy smem writes -> visible to the TMA unit
-        epi_bar();
-        if (et == 0) {
-          const int x0 = tx * p.box_w, y0 = ty * p.box_h, n0 = tn * p.box_n;
-#pragma unroll
-          for (int hb = 0; hb < BN / 64; ++hb)
-            tma_store_4d(&p.tmOut[ph], out_base + hb * 16384u, nt * BN + hb * 64, x0, y0, n0);
-          tma_store_commit();
-        }
       } else {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+        const int tx = mg % p.tiles_x; const int r2 = mg / p.tiles_x;
+        const int ty = r2 % p.tiles_y; const int tn = r2 / p.tiles_y;
         const int n = tn * p.box_n + ln;
         int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
         const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;     // gate / head never upsample

@@ -242,6 +242,8 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
+  int bn_max = 256;                    // widest N tile of the generic conv kernel (SD_BNMAX=256 to try 128x256 tiles)
   int row_mode = 1;                    // 1: conv_row_kernel on the level-1 64-channel layers; 0 (SD_ROWCONV=0): generic kernel everywhere
 };
 
@@ -302,15 +304,15 @@ static int make_tmap_out(sd_engine* e, CUtensorMap* tm, const Act& o, const Leve
   return SD_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
-  using Cfg = ConvCfg<BN, EPI>;
+  using Cfg = ConvCfg<BN, EPI, MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  conv_umma_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  conv_umma_kernel<BN, EPI, MT><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_umma_kernel");
   return SD_OK;
 }
@@ -336,8 +338,10 @@ static int dispatch_row(const ConvParams& p, int cb, int epi, int grid, cudaStre
   return SD_EINVAL;
 }
 
-static int dispatch_conv(const ConvParams& p, int bn, int epi, int grid, cudaStream_t s) {
+static int dispatch_conv(const ConvParams& p, int bn, int mt, int epi, int grid, cudaStream_t s) {
   if (epi == EPI_STORE) {
+    if (bn == 64 && mt == 2) return launch_conv<64, EPI_STORE, 2>(p, grid, s);
+    if (bn == 128 && mt == 2) return launch_conv<128, EPI_STORE, 2>(p, grid, s);
     if (bn == 64) return launch_conv<64, EPI_STORE>(p, grid, s);
     if (bn == 128) return launch_conv<128, EPI_STORE>(p, grid, s);
     if (bn == 256) return launch_conv<256, EPI_STORE>(p, grid, s);
@@ -456,6 +460,8 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   const int taps = cs.up ? 4 : e->ks[slot] * e->ks[slot];
   const int K = taps * cin_total;
   int bn = co >= 128 ? 128 : co;
+  if (e->bn_max >= 256 && co % 256 == 0 && cs.epi == EPI_STORE) bn = 256;
+  const int mt = (cs.epi == EPI_STORE && bn <= e->mt2_max_bn) ? 2 : 1;   // two M tiles share each B k-block
   if (cs.epi == EPI_GATE) bn = co;
   if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], (cs.up ? 4 : 1) * co, K, bn))) return r;
   p.H = L.H; p.W = L.W;
@@ -497,16 +503,16 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   const int box_n = L.box_n, per_img = p.tiles_x * p.tiles_y;
   const int nsm = e->num_sms;
   op.flops_per_tile = 2.0 * (cs.up ? 4.0 : 1.0) * L.H * L.W * co * K;
-  op.run = [e, p, bn, epi, box_n, per_img, nsm](int B, cudaStream_t s) mutable -> int {
+  op.run = [e, p, bn, mt, epi, box_n, per_img, nsm](int B, cudaStream_t s) mutable -> int {
     p.B = B;
     p.m_tiles = per_img * ((B + box_n - 1) / box_n);
     if (epi == EPI_HEAD) {
       p.head_b = e->head_b; p.thr = e->thr;
       p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
     }
-    const int n_work = p.m_tiles * p.n_tiles * p.n_phases;
+    const int n_work = ((p.m_tiles + mt - 1) / mt) * p.n_tiles * p.n_phases;
     const int grid = n_work < nsm ? n_work : nsm;
-    return dispatch_conv(p, bn, epi, grid, s);
+    return dispatch_conv(p, bn, mt, epi, grid, s);
   };
   e->ops.push_back(op);
   return SD_OK;
@@ -623,6 +629,8 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   }
   e->impl = impl;
   if (const char* rm = getenv("SD_ROWCONV")) e->row_mode = atoi(rm);
+  if (const char* bm = getenv("SD_BNMAX")) e->bn_max = atoi(bm);
+  if (const char* m2 = getenv("SD_MT2")) e->mt2_max_bn = atoi(m2);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
