@@ -653,4 +653,176 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_row_kernel(const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// conv_first_umma_kernel: Conv1.0, 3(+5 zero) -> 64 channels, 3x3, pad 1, bias + ReLU on the tensor pipe.
+// The NHWC8 input makes one (pixel, tap) = 8 halves = 16 B = exactly one row of a UMMA core matrix, so the
+// im2col A tile [128 px x K = 9 taps x 8 ch (+8 zero) = 80] is written by 128 producer threads straight into
+// the canonical no-swizzle K-major layout: core matrix (row group g, tap t) at g * 1280 + t * 128, row r % 8
+// at + 16 B.  Image borders are zero-filled by predication.  Weights [64 x 80] sit in shared memory in the
+// same layout for the whole kernel.  M tile = one 128-pixel row segment; 5 MMAs (K = 16 each) per tile, so
+// the kernel is bound by the 16 KB output store per tile, not by the tensor pipe.
+//   warp 0: MMA issuer | warps 1-4: im2col producers | warps 5-8: epilogue (TMEM -> bias/ReLU -> TMA store)
+// ---------------------------------------------------------------------------------------------
+constexpr int kC1Stages = 4;
+constexpr int kC1K = 80;
+constexpr int kC1GroupBytes = (kC1K / 8) * 128;        // 1280: one 8-row group across K
+constexpr int kC1ABytes = 16 * kC1GroupBytes;          // 20480
+constexpr int kC1BBytes = 8 * kC1GroupBytes;           // 10240 (64 output channels)
+constexpr int kC1Threads = 288;
+constexpr int kC1SmemBytes = kC1Stages * kC1ABytes + kC1BBytes + 16384 + 1024 + 1024;
+
+struct ConvFirstParams {
+  CUtensorMap tmOut;
+  const uint4* in;             // NHWC8 fp16, 16 B per pixel
+  const uint4* w;              // 10240 B, canonical layout (host-packed)
+  const float* bias;           // [64]
+  int B, H, W;
+  int* err_flag;
+};
+
+// K-major operand without swizzle: LBO = distance between core matrices adjacent in K, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(kC1Threads, 2) conv_first_umma_kernel(const __grid_constant__ ConvFirstParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_base = smem_base + kC1Stages * kC1ABytes;
+  const uint32_t out_base = w_base + kC1BBytes;                    // 1024-aligned (20480 * 4 + 10240 = 92160 = 90 KB)
+  uint8_t* misc = smem_al + kC1Stages * kC1ABytes + kC1BBytes + 16384;
+  const uint32_t bar_base = out_base + 16384;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kC1Stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kC1Stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC1Stages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
+  float* s_bias = reinterpret_cast<float*>(misc + 256);
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmOut);
+    for (int s = 0; s < kC1Stages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights -> smem, zero the K-padding core matrix (tap slot 9) of every stage, bias
+  for (int i = threadIdx.x; i < kC1BBytes / 16; i += kC1Threads)
+    reinterpret_cast<uint4*>(smem_al + kC1Stages * kC1ABytes)[i] = __ldg(p.w + i);
+  for (int i = threadIdx.x; i < kC1Stages * 128; i += kC1Threads) {
+    const int st = i >> 7, r = i & 127;
+    *reinterpret_cast<uint4*>(smem_al + st * kC1ABytes + (r >> 3) * kC1GroupBytes + 9 * 128 + (r & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int segs = p.W / 128;
+  const int n_work = p.B * p.H * segs;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      const uint64_t bdesc = umma_desc_none(w_base, 128, kC1GroupBytes);
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2);
+        mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_none(smem_base + stage * kC1ABytes, 128, kC1GroupBytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 64);
+#pragma unroll
+        for (int k = 0; k < kC1K / 16; ++k)     // K = 16 halves = 2 core matrices = 256 B -> +16 in the (addr >> 4) field
+          umma_f16(d_tmem, adesc + 16u * k, bdesc + 16u * k, kIdesc, (uint32_t)(k != 0));
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 4) {
+    // ======================= im2col producers: thread = pixel =======================
+    const int r = threadIdx.x - 32;
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sx = w % segs; const int rest = w / segs;
+      const int y = rest % p.H, n = rest / p.H;
+      const int x = sx * 128 + r;
+      uint4 v[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        v[t] = make_uint4(0u, 0u, 0u, 0u);
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v[t] = __ldg(p.in + ((int64_t)n * p.H + yy) * p.W + xx);
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+      uint8_t* dst = smem_al + stage * kC1ABytes + (r >> 3) * kC1GroupBytes + (r & 7) * 16;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) *reinterpret_cast<uint4*>(dst + t * 128) = v[t];
+      fence_async_smem();                         // generic-proxy writes -> visible to the tensor pipe
+      mbar_arrive(full_bar(stage));
+      if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ======================= epilogue (warps 5..8) =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 160;
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sx = w % segs; const int rest = w / segs;
+      const int y = rest % p.H, n = rest / p.H;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
+      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
+      tc_fence_after();
+      if (et == 0) tma_store_wait_read();
+      epi_bar();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        const uint32_t rbase = out_base + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = j4 * 8 + j * 2;
+            float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
+            __half2 h = __floats2half2_rn(a, b);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const uint32_t chunk = (uint32_t)(c * 4 + j4);
+          const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      fence_async_smem();
+      epi_bar();
+      if (et == 0) { tma_store_4d(&p.tmOut, out_base, 0, sx * 128, y, n); tma_store_commit(); }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
 }  // namespace sd

@@ -242,6 +242,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
   int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
   int bn_max = 256;                    // widest N tile of the generic conv kernel (SD_BNMAX=256 to try 128x256 tiles)
   int row_mode = 1;                    // 1: conv_row_kernel on the level-1 64-channel layers; 0 (SD_ROWCONV=0): generic kernel everywhere
@@ -631,6 +632,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* rm = getenv("SD_ROWCONV")) e->row_mode = atoi(rm);
   if (const char* bm = getenv("SD_BNMAX")) e->bn_max = atoi(bm);
   if (const char* m2 = getenv("SD_MT2")) e->mt2_max_bn = atoi(m2);
+  if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -665,6 +667,13 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
         for (int ci = 0; ci < 3; ++ci)
           for (int k = 0; k < 9; ++k) t[(k * 3 + ci) * 64 + co] = e->hw[s][((size_t)co * 3 + ci) * 9 + k];
       if ((r = upload(e, (void**)&e->w_f32[s], t.data(), t.size() * 4))) return r;
+      // tensor-core form: [64 x K=80] fp16 in the canonical no-swizzle K-major layout, k = tap * 8 + ci
+      std::vector<__half> c1((size_t)kC1BBytes / 2, __float2half(0.f));
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int k = 0; k < 9; ++k)
+            c1[(size_t)(co >> 3) * (kC1GroupBytes / 2) + k * 64 + (co & 7) * 8 + ci] = __float2half_rn(e->hw[s][((size_t)co * 3 + ci) * 9 + k]);
+      if ((r = upload(e, (void**)&e->w_umma[s], c1.data(), c1.size() * 2))) return r;
     }
     const int co = e->cout[s], ci = e->cin[s], taps = e->ks[s] * e->ks[s];
     if (impl == 1) {
@@ -725,7 +734,23 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   Op first;
   first.name = "Conv1.0(simt)";
   first.flops_per_tile = 2.0 * H * W * 64 * 27;
-  if (impl == 0) {
+  if (impl == 0 && e->conv1_tc && W % 128 == 0) {
+    first.name = "Conv1.0";
+    ConvFirstParams cp;
+    memset(&cp, 0, sizeof(cp));
+    if ((r = make_tmap_out(e, &cp.tmOut, e->c1a, e->lv[0], false, 0))) return r;
+    cp.w = reinterpret_cast<const uint4*>(e->w_umma[SD_CONV1_0]); cp.bias = e->bias[SD_CONV1_0];
+    cp.H = H; cp.W = W; cp.err_flag = e->err_flag;
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_first_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemBytes));
+    first.run = [e, cp](int B, cudaStream_t s) mutable -> int {
+      cp.B = B; cp.in = reinterpret_cast<const uint4*>(e->in_tiles);
+      const int n_work = B * e->H * (e->W / 128);
+      const int grid = n_work < 2 * e->num_sms ? n_work : 2 * e->num_sms;
+      conv_first_umma_kernel<<<grid, kC1Threads, kC1SmemBytes, s>>>(cp);
+      SD_LAUNCH_CHECK("conv_first_umma_kernel");
+      return SD_OK;
+    };
+  } else if (impl == 0) {
     first.run = [e](int B, cudaStream_t s) -> int {
       const int64_t total = (int64_t)B * e->H * e->W;
       conv_first_kernel<<<ceil_div(total, 128), 128, 0, s>>>(reinterpret_cast<const uint2*>(e->in_tiles), e->w_f32[SD_CONV1_0],
