@@ -194,6 +194,10 @@ int64_t sd_launch_count(void);
 int sd_engine_enable_timing(sd_engine* e, int on);
 int sd_engine_layer_times(sd_engine* e, float* h_ms, int cap, int* n_out);
 const char* sd_engine_layer_name(sd_engine* e, int i);
+/* Debug builds only (-DSD_CONV_STATS): cycles spent in mbarrier waits of the tcgen05 conv kernels, per wait
+ * code (1 producer<-empty slot, 2 MMA<-TMEM stage, 3 MMA<-full slot, 4 epilogue<-accumulator, 5 weights),
+ * summed over the calling threads since the last reset; zeros in a normal build. */
+int sd_debug_wait_cycles(unsigned long long* h_out8, int reset);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ SOURCES = ["sd_api.cu", "seg_kernels.cu", "unet.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing",
-]
+] + os.environ.get("SD_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -76,11 +76,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+#ifdef SD_CONV_STATS
+// debug build only (SD_EXTRA_NVCC_FLAGS=-DSD_CONV_STATS): cycles spent in mbar_wait per wait code, summed over all
+// calling threads; [0] counts kernel cycles of thread 0 of every CTA.  Read with sd_debug_wait_cycles().
+__device__ unsigned long long g_wait_cycles[8];
+#endif
 // Bounded wait: a descriptor / protocol bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+#ifdef SD_CONV_STATS
+  const long long t0 = clock64();
+#endif
 #pragma unroll 1
   for (uint32_t it = 0; it < 40000000u; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) {
+#ifdef SD_CONV_STATS
+      atomicAdd(&g_wait_cycles[code & 7], (unsigned long long)(clock64() - t0));
+#endif
+      return;
+    }
   }
   if (err_flag) atomicExch(err_flag, code);
   __threadfence_system();
@@ -650,6 +663,263 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_row_kernel(const __grid_
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_band_kernel<CB, EPI>: the same level-1 layers (3x3, Cin = CB*64 -> Cout = 64, W % 128 == 0), dy-stacked.
+// An N = 64 MMA reads 4 KB of A + 2 KB of B from shared memory for 32 tensor cycles (192 B/clk against the
+// 128 B/clk the shared memory delivers) and each input row is fetched three times.  Here ONE input halo row
+// (130 px x 64 ch, fetched once) feeds the three output rows it contributes to in a single N = 192 MMA per
+// (dx, k-step): the weights of ky = 2, 1, 0 are stacked along N and the accumulators of consecutive output rows
+// sit in consecutive 64-column TMEM slots, a ring of 8 slots = all 512 columns.  10 KB per 96 cycles = 107 B/clk.
+//   * every slot only ever receives the three valid contributions of its output row, so all MMAs accumulate;
+//     the epilogue zeroes a slot (tcgen05.st) after draining it;
+//   * a window that wraps around the ring (2 of 8 positions) is issued as two MMAs;
+//   * work item = (image, 128-px segment, band of kBandRows output rows); band edges use N = 64 / 128 windows,
+//     so no MAC is wasted, only the two halo input rows are fetched twice.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBandRows = 32;
+
+template <int CB, int EPI> struct BandCfg {
+  static constexpr int kWBytes = 9 * CB * 8192;        // [dx][cb][ky = 2, 1, 0][64 cout] rows of 128 B
+  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 16384 : 0;
+  static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kWBytes - kOutBytes) / kRowStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
+  static constexpr int kSmemBytes = kStages * kRowStageBytes + kWBytes + kOutBytes + 1024 + kMiscBytes;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int CB, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = BandCfg<CB, EPI>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_base = smem_base + Cfg::kStages * kRowStageBytes;                 // resident weights
+  const uint32_t out_base = w_base + Cfg::kWBytes;
+  uint8_t* misc = smem_al + Cfg::kStages * kRowStageBytes + Cfg::kWBytes + Cfg::kOutBytes;
+  const uint32_t bar_base = out_base + Cfg::kOutBytes;
+  // misc: [0,384) barriers: full[S], empty[S], tfull[8], tempty[8], weights; [384] TMEM slot; [512] bias; [768] head vector
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (24 + s); };
+  const uint32_t w_bar = bar_base + 8u * 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 384);
+  float* s_bias = reinterpret_cast<float*>(misc + 512);
+  float* s_vec = reinterpret_cast<float*>(misc + 768);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    if (CB > 1) tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmB);
+    if (EPI == EPI_STORE) tma_prefetch_desc(&p.tmOut[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) { s_bias[t] = p.bias[t]; if (EPI == EPI_HEAD) s_vec[t] = p.head_w[t]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {                                     // all accumulator slots start at zero
+    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) tmem_st32_zero(t0 + c * 32);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int segs = p.W / 128;
+  const int bands = (p.H + kBandRows - 1) / kBandRows;
+  const int n_work = p.B * bands * segs;
+  // per CTA, the output rows of its work items are numbered consecutively: g -> slot g & 7, use (g >> 3)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // one-time: weights -> smem, block (dx, cb, kyr) <- tap (ky = 2 - kyr, kx = dx), 64 rows x 128 B each
+      mbar_expect_tx(w_bar, Cfg::kWBytes);
+      for (int dx = 0; dx < 3; ++dx)
+        for (int cb = 0; cb < CB; ++cb)
+          for (int kyr = 0; kyr < 3; ++kyr)
+            tma_load_2d(w_base + ((dx * CB + cb) * 3 + kyr) * 8192, &p.tmB, w_bar, (((2 - kyr) * 3 + dx) * CB + cb) * 64, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int sx = w % segs; int rest = w / segs;
+        const int b = rest % bands; const int n = rest / bands;
+        const int y0 = b * kBandRows, y1 = min(y0 + kBandRows, p.H);
+        for (int i = max(y0 - 1, 0); i <= min(y1, p.H - 1); ++i) {
+          for (int cb = 0; cb < CB; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+            mbar_expect_tx(full_bar(stage), kRowBoxBytes);
+            tma_load_4d(smem_base + stage * kRowStageBytes, cb == 0 ? &p.tmA0 : &p.tmA1, full_bar(stage), 0, sx * 128 - 1, i, n);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_bar, 0, p.err_flag, 5);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      int gbase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int b = (w / segs) % bands;
+        const int y0 = b * kBandRows, y1 = min(y0 + kBandRows, p.H);
+        for (int i = max(y0 - 1, 0); i <= min(y1, p.H - 1); ++i) {
+          const int r_lo = max(i - 1, y0), r_hi = min(i + 1, y1 - 1);
+          const int nr = r_hi - r_lo + 1;               // output rows fed by this input row (1..3)
+          const int kyr_lo = r_lo - i + 1;              // first weight block of the window
+          const int g_lo = gbase + (r_lo - y0);
+          const int s_lo = g_lo & 7;
+          // rows that get their first contribution from this input row (row i+1; at the image top also row 0):
+          // their slots must have been drained and zeroed by the epilogue
+          if (i == 0 && y0 == 0) {
+            mbar_wait(tempty_bar(gbase & 7), (uint32_t)(((gbase >> 3) & 1) ^ 1), p.err_flag, 2);
+            tc_fence_after();
+          }
+          if (r_hi == i + 1) {
+            const int g_hi = gbase + (r_hi - y0);
+            mbar_wait(tempty_bar(g_hi & 7), (uint32_t)(((g_hi >> 3) & 1) ^ 1), p.err_flag, 2);
+            tc_fence_after();
+          }
+          const int n1 = min(nr, 8 - s_lo), n2 = nr - n1;   // window split at the end of the ring
+          const uint32_t idesc1 = (1u << 4) | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t d1 = tmem_base + (uint32_t)(s_lo * 64);
+          for (int cb = 0; cb < CB; ++cb) {
+            mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * kRowStageBytes;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint64_t adesc = umma_desc_sw128(a_addr + dx * 128);
+              const uint32_t wb = w_base + ((dx * CB + cb) * 3 + kyr_lo) * 8192;
+              const uint64_t bdesc1 = umma_desc_sw128(wb);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d1, adesc + 2u * k, bdesc1 + 2u * k, idesc1, 1u);
+              if (n2) {
+                const uint64_t bdesc2 = umma_desc_sw128(wb + n1 * 8192);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + 2u * k, bdesc2 + 2u * k, idesc2, 1u);
+              }
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+          // rows whose last contribution this was
+          if (i - 1 >= y0) umma_commit(tfull_bar((gbase + (i - 1 - y0)) & 7));
+          if (i == p.H - 1 && i < y1) umma_commit(tfull_bar((gbase + (i - y0)) & 7));
+        }
+        gbase += y1 - y0;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int g = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sx = w % segs; int rest = w / segs;
+      const int b = rest % bands; const int n = rest / bands;
+      const int y0 = b * kBandRows, y1 = min(y0 + kBandRows, p.H);
+      for (int y = y0; y < y1; ++y, ++g) {
+        const int slot = g & 7;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64);
+        mbar_wait(tfull_bar(slot), (uint32_t)((g >> 3) & 1), p.err_flag, 4);
+        tc_fence_after();
+        if constexpr (EPI == EPI_STORE) {
+          if (et == 0) tma_store_wait_read();
+          epi_bar();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_st32_zero(taddr + c * 32);
+            const uint32_t rbase = out_base + (uint32_t)row * 128u;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int col = j4 * 8 + j * 2;
+                float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b2 = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
+                __half2 h = __floats2half2_rn(a, b2);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              const uint32_t chunk = (uint32_t)(c * 4 + j4);
+              const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(tempty_bar(slot));
+          fence_async_smem();
+          epi_bar();
+          if (et == 0) { tma_store_4d(&p.tmOut[0], out_base, 0, sx * 128, y, n); tma_store_commit(); }
+        } else {
+          float dot = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_st32_zero(taddr + c * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = fmaxf(v[j] + s_bias[c * 32 + j], 0.f);
+              a = __half2float(__float2half_rn(a));
+              dot = fmaf(a, s_vec[c * 32 + j], dot);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(tempty_bar(slot));
+          const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));
+          const int64_t pix = ((int64_t)n * p.H + y) * p.W + sx * 128 + row;
+          if (p.prob_f32) p.prob_f32[pix] = pr;
+          if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
+          if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
+        }
+      }
+    }
+    if (EPI == EPI_STORE && et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

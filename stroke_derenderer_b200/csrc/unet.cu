@@ -245,7 +245,7 @@ struct sd_engine {
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
   int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
   int bn_max = 256;                    // widest N tile of the generic conv kernel (SD_BNMAX=256 to try 128x256 tiles)
-  int row_mode = 1;                    // 1: conv_row_kernel on the level-1 64-channel layers; 0 (SD_ROWCONV=0): generic kernel everywhere
+  int row_mode = 2;                    // level-1 64-channel 3x3 layers: 2 conv_band_kernel, 1 conv_row_kernel, 0 generic kernel (SD_ROWCONV)
 };
 
 namespace sd {
@@ -329,6 +329,27 @@ static int launch_row(const ConvParams& p, int grid, cudaStream_t s) {
   conv_row_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_row_kernel");
   return SD_OK;
+}
+
+template <int CB, int EPI>
+static int launch_band(const ConvParams& p, int grid, cudaStream_t s) {
+  using Cfg = BandCfg<CB, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  conv_band_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  SD_LAUNCH_CHECK("conv_band_kernel");
+  return SD_OK;
+}
+
+static int dispatch_band(const ConvParams& p, int cb, int epi, int grid, cudaStream_t s) {
+  if (cb == 1 && epi == EPI_STORE) return launch_band<1, EPI_STORE>(p, grid, s);
+  if (cb == 2 && epi == EPI_STORE) return launch_band<2, EPI_STORE>(p, grid, s);
+  if (cb == 1 && epi == EPI_HEAD) return launch_band<1, EPI_HEAD>(p, grid, s);
+  set_error("dispatch_band: no kernel for CB=%d epilogue=%d", cb, epi);
+  return SD_EINVAL;
 }
 
 static int dispatch_row(const ConvParams& p, int cb, int epi, int grid, cudaStream_t s) {
@@ -441,14 +462,19 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.head_w = e->w_f32[SD_HEAD];
     }
     Op op;
-    op.name = std::string(cs.name) + "[row]";
+    const int band = e->row_mode >= 2;
+    op.name = std::string(cs.name) + (band ? "[band]" : "[row]");
     const int epi = cs.epi, nsm = e->num_sms, segs = L.W / 128, H = L.H;
     op.flops_per_tile = 2.0 * L.H * L.W * co * 9 * cin_total;
-    op.run = [e, p, cb, epi, nsm, segs, H](int B, cudaStream_t s) mutable -> int {
+    op.run = [e, p, cb, epi, nsm, segs, H, band](int B, cudaStream_t s) mutable -> int {
       p.B = B;
       if (epi == EPI_HEAD) {
         p.head_b = e->head_b; p.thr = e->thr;
         p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
+      }
+      if (band) {
+        const int n_work = B * ((H + kBandRows - 1) / kBandRows) * segs;
+        return dispatch_band(p, cb, epi, n_work < nsm ? n_work : nsm, s);
       }
       const int n_work = B * H * segs;
       return dispatch_row(p, cb, epi, n_work < nsm ? n_work : nsm, s);
@@ -882,6 +908,17 @@ extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, f
     if (e->timing) SD_CUDA_CHECK(cudaEventRecord(e->ev[i], s));
     int r = e->ops[i].run(n_tiles, s);
     if (r) return r;
+#ifdef SD_CONV_STATS
+    if (e->timing) {   // debug build: per-op mbarrier wait cycles, printed as JSON lines on stderr
+      unsigned long long wc[8];
+      SD_CUDA_CHECK(cudaStreamSynchronize(s));
+      SD_CUDA_CHECK(cudaMemcpyFromSymbol(wc, sd::g_wait_cycles, sizeof(wc)));
+      unsigned long long z[8] = {};
+      SD_CUDA_CHECK(cudaMemcpyToSymbol(sd::g_wait_cycles, z, sizeof(z)));
+      fprintf(stderr, "{\"op\": \"%s\", \"wait\": [%llu, %llu, %llu, %llu, %llu, %llu]}\n", e->ops[i].name.c_str(), wc[0], wc[1],
+              wc[2], wc[3], wc[4], wc[5]);
+    }
+#endif
   }
   if (e->timing) {
     SD_CUDA_CHECK(cudaEventRecord(e->ev[e->ops.size()], s));
@@ -926,4 +963,17 @@ extern "C" int sd_engine_layer_times(sd_engine* e, float* h_ms, int cap, int* n_
 extern "C" const char* sd_engine_layer_name(sd_engine* e, int i) {
   if (!e || i < 0 || i >= (int)e->ops.size()) return "";
   return e->ops[i].name.c_str();
+}
+
+// debug: cycles spent in mbarrier waits per wait code since the last reset (zeros unless built with -DSD_CONV_STATS)
+extern "C" int sd_debug_wait_cycles(unsigned long long* h_out8, int reset) {
+#ifdef SD_CONV_STATS
+  SD_CUDA_CHECK(cudaDeviceSynchronize());
+  if (h_out8) SD_CUDA_CHECK(cudaMemcpyFromSymbol(h_out8, sd::g_wait_cycles, 8 * sizeof(unsigned long long)));
+  if (reset) { unsigned long long z[8] = {}; SD_CUDA_CHECK(cudaMemcpyToSymbol(sd::g_wait_cycles, z, sizeof(z))); }
+#else
+  if (h_out8) for (int i = 0; i < 8; ++i) h_out8[i] = 0;
+  (void)reset;
+#endif
+  return SD_OK;
 }

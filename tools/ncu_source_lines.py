@@ -5,6 +5,8 @@ import csv, re, subprocess, sys, tempfile, os, glob
 from collections import defaultdict
 
 sass_csv, lib, kern = sys.argv[1:4]
+# "mangled|demangled": substring of the cubin symbol | substring of the kernel name in the csv
+kern, kern_csv = (kern.split("|") + [kern])[:2]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -32,9 +34,17 @@ for cub in glob.glob(tmp + "/*.cubin"):
             lines_of = s
             break
 rows = list(csv.reader(open(sass_csv)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# a report with several launches holds one section per launch: pick section SECTION (default 0) whose name matches
+secs = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern_csv in r[1]]
+sel = secs[int(os.environ.get("SECTION", "0"))] if secs else 0
+hi = next(i for i in range(sel, len(rows)) if rows[i] and rows[i][0] == "Address")
 hdr = rows[hi]
-body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+body = []
+for r in rows[hi + 1:]:
+    if r and r[0] == "Kernel Name":
+        break
+    if len(r) == len(hdr):
+        body.append(r)
 ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [j for j, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 assert lines_of and len(lines_of) == len(body), (len(lines_of or []), len(body))
