@@ -73,6 +73,7 @@ class LineSegmentationJob:
         self.chunks = []
         with torch.cuda.device(self.device):
             self.s_copy, self.s_unet, self.s_part = (torch.cuda.Stream(self.device) for _ in range(3))
+            t0 = 0
             for c0 in range(0, len(images), lines_per_chunk):
                 imgs = images[c0:c0 + lines_per_chunk]
                 ch = _Chunk()
@@ -81,29 +82,31 @@ class LineSegmentationJob:
                 ch.h_rgb = S.pack_lines_rgb(imgs, ch.batch, pinned=True)
                 ch.d_rgb = ch.h_rgb.to(self.device)
                 ch.d_rgb_in = torch.empty_like(ch.d_rgb)
-                nt = ch.batch.n_tiles
-                ch.tiles = torch.empty((nt, TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
-                ch.masks = torch.empty((nt, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+                ch.t0, ch.t1 = t0, t0 + ch.batch.n_tiles        # the chunk's range in the job-wide tile stack
+                t0 = ch.t1
                 ch.planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, device=self.device)
                 ch.h_planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, pin_memory=True)
                 self.chunks.append(ch)
+            # one tile stack for the whole job: UNet batches run across chunk boundaries, so only the
+            # last batch of the job is partial
+            self.tiles = torch.empty((max(t0, 1), TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
+            self.masks = torch.empty((max(t0, 1), TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+            for ch in self.chunks:
+                ch.tiles = self.tiles[ch.t0:ch.t1]
+                ch.masks = self.masks[ch.t0:ch.t1]
         self.n_tiles = sum(c.batch.n_tiles for c in self.chunks)
         self.n_lines = sum(c.batch.n_lines for c in self.chunks)
-
-    def _binarize(self, ch, d_rgb):
-        S.tile_extract_f16(ch.batch, d_rgb, out=ch.tiles)
-        mt = self.engine.max_tiles
-        for s in range(0, ch.batch.n_tiles, mt):
-            self.engine.forward_into(ch.tiles[s:s + mt], ch.masks[s:s + mt], self.seg.bin_thr)
-        S.glue_u8(ch.batch, ch.masks, out=ch.planes)
 
     def _run(self, from_host: bool, canvases: str):
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             for st in (self.s_copy, self.s_unet, self.s_part):
                 st.wait_stream(cur)
-            ready = []
-            for ch in self.chunks:
+            ready = [None] * len(self.chunks)
+            mt = self.engine.max_tiles
+            done = 0                      # tiles binarized so far
+            glued = 0                     # chunks glued so far
+            for k, ch in enumerate(self.chunks):
                 src = ch.d_rgb
                 if from_host:
                     with torch.cuda.stream(self.s_copy):
@@ -112,9 +115,18 @@ class LineSegmentationJob:
                     self.s_unet.wait_event(ev)
                     src = ch.d_rgb_in
                 with torch.cuda.stream(self.s_unet):
-                    self._binarize(ch, src)
-                    ev = torch.cuda.Event(); ev.record(self.s_unet)
-                ready.append(ev)
+                    S.tile_extract_f16(ch.batch, src, out=ch.tiles)
+                    last = k == len(self.chunks) - 1
+                    while done + mt <= ch.t1 or (last and done < ch.t1):
+                        n = min(mt, self.n_tiles - done)
+                        self.engine.forward_into(self.tiles[done:done + n], self.masks[done:done + n], self.seg.bin_thr)
+                        done += n
+                    while glued < len(self.chunks) and self.chunks[glued].t1 <= done:
+                        g = self.chunks[glued]
+                        S.glue_u8(g.batch, g.masks, out=g.planes)
+                        ev = torch.cuda.Event(); ev.record(self.s_unet)
+                        ready[glued] = ev
+                        glued += 1
             results = []
             with torch.cuda.stream(self.s_part):
                 for ch, ev in zip(self.chunks, ready):

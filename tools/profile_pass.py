@@ -57,6 +57,10 @@ def main():
         eng = UNetEngine(state, device=0, max_tiles=nt)
         masks = torch.empty((nt, 128, 384), dtype=torch.uint8, device=dev)
         out["unet_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5))
+        out["unet_sustained_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5), reps=60)   # power-capped steady state
+        for small in (37, 64):
+            if small < nt:
+                out[f"unet_ms_{small}tiles"] = ev(lambda: eng.forward_into(tiles[:small], masks, 0.5), reps=5)
         torch.cuda.profiler.start()
         eng.forward_into(tiles[:nt], masks, 0.5)
         torch.cuda.synchronize()
