@@ -50,33 +50,50 @@ def parity_state():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons / power during the timed region through NVML (in-process: forking
+    nvidia-smi from a process with GBs of pinned memory stalls the launching thread for 100s of ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[index])
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = [n for n, b in bits.items() if any(r[2] & b for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows), "source": "nvml"}
 
 
 def make_lines(indices, widths):
@@ -154,6 +171,9 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     _lib.require_cuda()
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
@@ -176,8 +196,13 @@ def run_gpu(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         res = None
+        dbg = []
         for _ in range(steps):
+            t_dbg = time.perf_counter()
             res = fn()
+            dbg.append(1e3 * (time.perf_counter() - t_dbg))
+        if os.environ.get("SD_BENCH_DEBUG"):
+            print(f"[rank {rank}] {fn.__name__} host ms per step: {[round(v, 1) for v in dbg]}", file=sys.stderr, flush=True)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -188,14 +213,16 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         job.resident_step()
     sampler = ClockSampler(local)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     l0 = _lib.lib().sd_launch_count()
     ms_res, _ = timed(job.resident_step, args.steps)
     launches = _lib.lib().sd_launch_count() - l0
     job.host_step()
     ms_e2e, res = timed(job.host_step, args.steps)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if not args.no_clock_sampler:
+        sampler.join(timeout=2)
 
     counts = torch.tensor([job.n_tiles, job.n_lines, job.h2d_bytes(), job.d2h_bytes(res), launches], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -304,7 +331,7 @@ def run_gpu(args):
             "gpu_launches": launches_all, "clocks": sampler.summary(),
         }
         out.update(extra)
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     engine.close()
     if world > 1:
         dist.destroy_process_group()
@@ -320,6 +347,7 @@ def main():
     ap.add_argument("--max-tiles", type=int, default=128)
     ap.add_argument("--lines-per-chunk", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_gpu(args))
 
