@@ -166,6 +166,14 @@ int sd_island_stats(const int32_t* d_labels, const sd_line* d_lines, int n_lines
 int sd_group_canvas(const int32_t* d_labels, const sd_line* d_lines,
                     const int64_t* d_groups, int n_groups, const int32_t* d_group_of,
                     const int64_t* d_stat_off, uint8_t* d_canvas, void* stream);
+/* evaluate_strokes.py:202-222 + helper/partition.py:101-140 (resize_and_pad_image) + evaluate_strokes.py:58-69
+ * (_normalize_image): per group, canvas -> cv2.normalize MINMAX -> cv2.resize INTER_LINEAR (8-bit fixed point,
+ * bit-exact) to d_rs_dims[g] = (rs_w, rs_h) -> zero pad to size x size.  d_image_u8: (n_groups, size, size) =
+ * the reference's `image`; d_input_f32 (optional): (n_groups, 3, size, size) = `image_input`, through d_lut =
+ * 3 x 256 floats, lut[c][v] = (v / 255. - mean[c]) / std[c] computed by the caller in float64.  d_groups /
+ * d_canvas as in sd_group_canvas. */
+int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, const int32_t* d_rs_dims, int n_groups,
+                   int size, uint8_t* d_image_u8, float* d_input_f32, const float* d_lut, void* stream);
 
 /* ---- Attention-UNet engine ------------------------------------------------ */
 /* Replaces onnxruntime.InferenceSession (evaluate_binarize.py:48-53) and its

@@ -289,6 +289,65 @@ def normalize_image(image):
     return cv2.normalize(image, None, 0, 255, norm_type=cv2.NORM_MINMAX)
 
 
+def resize_linear_u8(src, dw, dh):
+    """Restatement of cv2.resize(src, (dw, dh)) for one-channel uint8 with the default INTER_LINEAR, the call at
+    helper/partition.py:120.  OpenCV (opencv-python, unpinned in the reference's setup.py:19; 4.13.0 in this
+    image) is third-party; this follows its published 8-bit algorithm (imgproc/resize.cpp: fixed-point
+    coefficients of INTER_RESIZE_COEF_BITS = 11 bits, HResizeLinear then VResizeLinear<uchar,int,short>) and is
+    pinned by tests/test_oracle.py against cv2.resize itself on this image (bit-exact).
+      * source position f = float((d + 0.5) * scale - 0.5), scale = 1 / (dst / src) in double; s = floor(f);
+      * x: a source index outside [0, sw-1) is clamped AND its fraction zeroed; y: only the rows are clamped;
+      * coefficients = round-half-even(float32 fraction * 2048) as int16;
+      * vertical pass: (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
+      * an exact 2x decimation in both directions takes the INTER_AREA fast path (2x2 mean, +2 >> 2)."""
+    src = np.asarray(src, np.uint8)
+    sh, sw = src.shape
+    if sw == 2 * dw and sh == 2 * dh:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    def coeffs(dn, sn, clamp):
+        scale = 1.0 / (dn / sn)
+        ofs = np.zeros(dn, np.int64)
+        a = np.zeros((dn, 2), np.int64)
+        for d in range(dn):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = np.float32(f - np.float32(s))
+            if clamp:
+                if s < 0:
+                    f, s = np.float32(0), 0
+                if s >= sn - 1:
+                    f, s = np.float32(0), sn - 1
+            ofs[d] = s
+            a[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+            a[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+        return ofs, a
+
+    xo, xa = coeffs(dw, sw, True)
+    yo, ya = coeffs(dh, sh, False)
+    S = src.astype(np.int64)
+    H = S[:, xo] * xa[:, 0][None, :] + S[:, np.minimum(xo + 1, sw - 1)] * xa[:, 1][None, :]
+    R0, R1 = H[np.clip(yo, 0, sh - 1), :], H[np.clip(yo + 1, 0, sh - 1), :]
+    b0, b1 = ya[:, 0][:, None], ya[:, 1][:, None]
+    out = (((b0 * (R0 >> 4)) >> 16) + ((b1 * (R1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def normalize_minmax_u8(img):
+    """Restatement of cv2.normalize(img, None, 0, 255, NORM_MINMAX) for uint8 (common.py:100): scale and shift are
+    computed in double, cast to float32, applied with ONE rounding (fused multiply-add) and rounded half-even;
+    an all-equal image gives zeros.  Pinned against cv2 in tests/test_oracle.py."""
+    img = np.asarray(img, np.uint8)
+    mn, mx = int(img.min()), int(img.max())
+    if mx == mn:
+        return np.zeros_like(img)
+    scale = 255.0 / (mx - mn)
+    a, b = np.float32(scale), np.float32(0.0 - mn * scale)
+    v = (img.astype(np.float64) * np.float64(a) + np.float64(b)).astype(np.float32)   # exact product + one rounding
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
 def get_pad_edges(n):
     """helper/partition.py:241-245."""
     return (n // 2, n // 2) if n % 2 == 0 else (n // 2, n // 2 + 1)

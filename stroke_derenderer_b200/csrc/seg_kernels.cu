@@ -773,6 +773,110 @@ __global__ void __launch_bounds__(256) group_canvas_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------
+// K10: 224x224 stroke-estimator crops (evaluate_strokes.py:202-222): per group
+//   canvas {0,1} -> cv2.normalize MINMAX (0/255; a constant canvas becomes 0) -> cv2.resize INTER_LINEAR to
+//   (rs_w, rs_h) -> zero pad to size x size (odd remainder goes right / bottom) = `image`;
+//   `image_input` = per channel ((MINMAX(image) / 255 - mean) / std) as f32, through a 3 x 256 table the host
+//   fills in float64 exactly like the reference expression.
+// cv2's 8-bit bilinear is fixed point and is reproduced bit for bit (oracle/segmentation_ref.py
+// resize_linear_u8, checked against cv2 itself): 11-bit coefficients rounded from float, horizontal pass in
+// int32, vertical pass ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2; x offsets clamp with the
+// coefficient zeroed, y offsets clamp the row only; an exact 2x decimation takes cv2's area path.
+// One CTA per group; the padded crop is built in shared memory so its min / max are known before it is written.
+// ---------------------------------------------------------------------------
+constexpr int kCropMax = 256;   // largest supported crop edge
+
+__device__ __forceinline__ void crop_coeff(int d, int dn, int sn, bool clamp, int& ofs, int& a0, int& a1) {
+  const double scale = 1.0 / ((double)dn / (double)sn);
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (clamp) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  }
+  ofs = s;
+  a0 = __float2int_rn((1.f - f) * 2048.f);
+  a1 = __float2int_rn(f * 2048.f);
+}
+
+__global__ void __launch_bounds__(256) group_crop_kernel(
+    const uint8_t* __restrict__ canvas, const int64_t* __restrict__ groups, const int32_t* __restrict__ rs_dims,
+    int size, uint8_t* __restrict__ out_u8, float* __restrict__ out_f32, const float* __restrict__ lut) {
+  extern __shared__ uint8_t s_img[];                 // size * size
+  __shared__ int s_xo[kCropMax], s_yo[kCropMax];
+  __shared__ short s_xa[kCropMax][2], s_yb[kCropMax][2];
+  __shared__ int s_red[2][8];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int64_t* G = groups + (int64_t)g * 6;
+  const int w = (int)(G[3] - G[1]), h = (int)(G[4] - G[2]);
+  const uint8_t* cv = canvas + G[5];
+  const int rs_w = rs_dims[2 * g], rs_h = rs_dims[2 * g + 1];
+  const int pad_l = (size - rs_w) / 2, pad_t = (size - rs_h) / 2;
+  // cv2.normalize(canvas, 0, 255, MINMAX): all-equal input -> zeros
+  int has_zero = 0;
+  for (int i = tid; i < w * h; i += blockDim.x) has_zero |= (cv[i] == 0);
+  has_zero = __syncthreads_or(has_zero);
+  const int on = has_zero ? 255 : 0;
+  const bool area2 = (w == 2 * rs_w) && (h == 2 * rs_h);
+  for (int d = tid; d < rs_w; d += blockDim.x) { int o, a0, a1; crop_coeff(d, rs_w, w, true, o, a0, a1); s_xo[d] = o; s_xa[d][0] = (short)a0; s_xa[d][1] = (short)a1; }
+  for (int d = tid; d < rs_h; d += blockDim.x) { int o, a0, a1; crop_coeff(d, rs_h, h, false, o, a0, a1); s_yo[d] = o; s_yb[d][0] = (short)a0; s_yb[d][1] = (short)a1; }
+  __syncthreads();
+  int vmax = 0, vmin = 255;
+  for (int p = tid; p < size * size; p += blockDim.x) {
+    const int oy = p / size, ox = p - oy * size;
+    const int dx = ox - pad_l, dy = oy - pad_t;
+    int v = 0;
+    if (dx >= 0 && dx < rs_w && dy >= 0 && dy < rs_h) {
+      if (area2) {
+        const uint8_t* r0 = cv + (int64_t)(2 * dy) * w + 2 * dx;
+        const int sum = (r0[0] != 0) + (r0[1] != 0) + (r0[w] != 0) + (r0[w + 1] != 0);
+        v = (sum * on + 2) >> 2;
+      } else {
+        const int x0 = s_xo[dx], x1 = min(x0 + 1, w - 1);
+        const int y0 = min(max(s_yo[dy], 0), h - 1), y1 = min(max(s_yo[dy] + 1, 0), h - 1);
+        const int a0 = s_xa[dx][0], a1 = s_xa[dx][1], b0 = s_yb[dy][0], b1 = s_yb[dy][1];
+        const uint8_t* r0 = cv + (int64_t)y0 * w;
+        const uint8_t* r1 = cv + (int64_t)y1 * w;
+        const int H0 = ((r0[x0] != 0) * a0 + (r0[x1] != 0) * a1) * on;
+        const int H1 = ((r1[x0] != 0) * a0 + (r1[x1] != 0) * a1) * on;
+        v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+      }
+    }
+    s_img[p] = (uint8_t)v;
+    vmax = max(vmax, v); vmin = min(vmin, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+  }
+  if ((tid & 31) == 0) { s_red[0][tid >> 5] = vmax; s_red[1][tid >> 5] = vmin; }
+  __syncthreads();
+  vmax = s_red[0][0]; vmin = s_red[1][0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) { vmax = max(vmax, s_red[0][k]); vmin = min(vmin, s_red[1][k]); }
+  // image: 4 bytes per thread (size * size % 4 == 0)
+  uint32_t* o8 = reinterpret_cast<uint32_t*>(out_u8 + (int64_t)g * size * size);
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s_img);
+  for (int i = tid; i < size * size / 4; i += blockDim.x) o8[i] = s32[i];
+  if (out_f32) {
+    // second MINMAX (evaluate_strokes.py:58-69): cv2 converts with float scale / shift and one fused rounding
+    const bool flat = vmax == vmin;
+    const double scale_d = flat ? 0.0 : 255.0 / (double)(vmax - vmin);
+    const float scale = (float)scale_d, shift = (float)(0.0 - (double)vmin * scale_d);
+    float* of = out_f32 + (int64_t)g * 3 * size * size;
+    for (int p = tid; p < size * size; p += blockDim.x) {
+      int n = 0;
+      if (!flat) n = min(max(__float2int_rn(fmaf((float)s_img[p], scale, shift)), 0), 255);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) of[(int64_t)c * size * size + p] = __ldg(lut + c * 256 + n);
+    }
+  }
+}
+
 }  // namespace sd
 
 // ===========================================================================
@@ -1074,5 +1178,23 @@ extern "C" int sd_group_canvas(const int32_t* d_labels, const sd_line* d_lines, 
   group_canvas_kernel<<<n_groups, 256, 0, (cudaStream_t)stream>>>(d_labels, d_lines, d_groups, d_group_of,
                                                                  d_stat_off, d_canvas);
   SD_LAUNCH_CHECK("group_canvas_kernel");
+  return SD_OK;
+}
+
+extern "C" int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, const int32_t* d_rs_dims, int n_groups,
+                              int size, uint8_t* d_image_u8, float* d_input_f32, const float* d_lut, void* stream) {
+  if (n_groups == 0) return SD_OK;
+  SD_REQUIRE(d_canvas && d_groups && d_rs_dims && d_image_u8 && n_groups > 0, "sd_group_crops: bad argument");
+  SD_REQUIRE(size > 0 && size <= kCropMax && size % 2 == 0, "sd_group_crops: size %d (even, <= %d)", size, kCropMax);
+  SD_REQUIRE(!d_input_f32 || d_lut, "sd_group_crops: the f32 output needs the 3x256 table");
+  const int smem = size * size;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(group_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropMax * kCropMax));
+    attr_done = true;
+  }
+  group_crop_kernel<<<n_groups, 256, smem, (cudaStream_t)stream>>>(d_canvas, d_groups, d_rs_dims, size, d_image_u8,
+                                                                   d_input_f32, d_lut);
+  SD_LAUNCH_CHECK("group_crop_kernel");
   return SD_OK;
 }

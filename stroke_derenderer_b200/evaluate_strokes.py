@@ -65,9 +65,16 @@ class StrokeEstimationSession:
                 off, pitch = int(ln["px_off"]), int(ln["pitch"])
                 host[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)[:, :m.shape[1]] = np.asarray(m) != 0
             planes = torch.from_numpy(host).to(dev)
-            res = _seg.Segmenter(None, margin=self.margin, device=dev).partition(batch, planes)
-            canv = res.canvases
-        return [self.partitions_from_canvases(c) for c in canv]
+            if self.img_size % 2 or self.img_size > 256:
+                res = _seg.Segmenter(None, margin=self.margin, device=dev).partition(batch, planes)
+                return [self.partitions_from_canvases(c) for c in res.canvases]
+            # crops on the device too (sd_group_crops): cv2.normalize / cv2.resize / pad / mean-std bit for bit
+            seg = _seg.Segmenter(None, margin=self.margin, device=dev)
+            res = seg.partition(batch, planes, canvases="device", crops=True, crop_lut=_seg.input_lut(self.mean, self.std))
+            if self.img_size != _seg.IMG_SIZE and len(res["groups"]):
+                res["crops"] = _seg.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"], size=self.img_size,
+                                                lut=_seg.input_lut(self.mean, self.std))
+            return [res.line_partitions(l) for l in range(batch.n_lines)]
 
     def load_orts(self, filepaths):
         raise NotImplementedError("stroke-estimator graphs are outside the B200 segmentation path (SURVEY.md 2)")

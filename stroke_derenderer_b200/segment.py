@@ -200,6 +200,51 @@ def group_canvases(batch: LineBatch, labels: torch.Tensor, stat_off: np.ndarray,
     return out
 
 
+IMG_SIZE = 224      # evaluate_strokes.py:25
+CROP_MARGIN = 1     # evaluate_strokes.py:207 (resize_and_pad_image(..., margin=1))
+
+
+def crop_geometry(groups: np.ndarray, size: int = IMG_SIZE, margin: int = CROP_MARGIN):
+    """helper/partition.py:112-139 for every row of the group table, vectorised in float64 (the same IEEE
+    operations as the reference's Python floats).  -> (rs_dims int32 (g,2) = rs_w, rs_h; ratio f64 (g,);
+    translate2 f64 (g,2) = x, y)."""
+    w = (groups[:, 3] - groups[:, 1]).astype(np.float64)
+    h = (groups[:, 4] - groups[:, 2]).astype(np.float64)
+    new = float(size - 2 * margin)
+    scale = np.minimum(new / h, new / w)
+    rs_w = np.minimum(np.rint(scale * w), new).astype(np.int64)
+    rs_h = np.minimum(np.rint(scale * h), new).astype(np.int64)
+    ratio = (rs_w / w + rs_h / h) / 2
+    t2 = np.stack([(size - rs_w) / 2, (size - rs_h) / 2], axis=1)
+    return np.stack([rs_w, rs_h], axis=1).astype(np.int32), ratio, t2
+
+
+def input_lut(mean, std) -> np.ndarray:
+    """(3, 256) f32 table of evaluate_strokes.py:66-68: ((v / 255. - mean[c]) / std[c]).astype(float32)."""
+    v = np.arange(256, dtype=np.uint8)
+    return np.stack([(v / 255. - mean[c]) / std[c] for c in range(3)], axis=0).astype(np.float32)
+
+
+def group_crops(device, canvas: torch.Tensor, d_groups: torch.Tensor, groups: np.ndarray, size: int = IMG_SIZE,
+                margin: int = CROP_MARGIN, lut: np.ndarray | None = None):
+    """Device crops of every group: -> dict(image u8 (g,size,size), image_input f32 (g,3,size,size) | None,
+    ratio, translate2, rs_dims)."""
+    n = len(groups)
+    rs, ratio, t2 = crop_geometry(groups, size, margin)
+    image = torch.empty((n, size, size), dtype=torch.uint8, device=device)
+    inp = d_lut = None
+    if lut is not None:
+        inp = torch.empty((n, 3, size, size), dtype=torch.float32, device=device)
+        d_lut = torch.from_numpy(np.ascontiguousarray(lut, np.float32)).to(device)
+    if n:
+        d_rs = torch.from_numpy(rs).to(device)
+        _lib.check(_lib.lib().sd_group_crops(canvas.data_ptr(), d_groups.data_ptr(), d_rs.data_ptr(), n, size, image.data_ptr(),
+                                             inp.data_ptr() if inp is not None else None,
+                                             d_lut.data_ptr() if d_lut is not None else None,
+                                             torch.cuda.current_stream(device).cuda_stream), "sd_group_crops")
+    return {"image": image, "image_input": inp, "ratio": ratio, "translate2": t2, "rs_dims": rs}
+
+
 _PINNED = {}
 
 
@@ -233,6 +278,25 @@ class PartitionResult(dict):
     def canvases(self):
         return [self.line_canvases(l) for l in range(len(self["line_group_start"]) - 1)]
 
+    def line_partitions(self, l: int):
+        """evaluate_strokes.py:202-222 for line l from the device crops (needs partition(..., crops=...)):
+        [dict(image, image_input, translate1=(left, top), ratio, translate2)]."""
+        cr = self["crops"]
+        if cr is None:
+            raise RuntimeError("partition() was called without crops")
+        if "image_host" not in cr:
+            cr["image_host"] = cr["image"].cpu().numpy()
+            cr["input_host"] = cr["image_input"].cpu().numpy() if cr["image_input"] is not None else None
+        a, b = int(self["line_group_start"][l]), int(self["line_group_start"][l + 1])
+        out = []
+        for g in range(a, b):
+            _, left, top, _, _, _ = (int(v) for v in self["groups"][g])
+            out.append({"image": cr["image_host"][g],
+                        "image_input": cr["input_host"][g] if cr["input_host"] is not None else None,
+                        "translate1": (np.int64(left), np.int64(top)), "ratio": float(cr["ratio"][g]),
+                        "translate2": (float(cr["translate2"][g, 0]), float(cr["translate2"][g, 1]))})
+        return out
+
 
 class Segmenter:
     """Batched text segmentation of many line images on ONE GPU:
@@ -264,7 +328,7 @@ class Segmenter:
         return batch, planes
 
     def partition(self, batch: LineBatch, planes: torch.Tensor, canvases: str = "host", key="part",
-                  zero_copy: bool = False) -> PartitionResult:
+                  zero_copy: bool = False, crops: bool = False, crop_lut: np.ndarray | None = None) -> PartitionResult:
         """mask planes -> labels, island stats, groups and group canvases for every line.
         canvases: "host" (copied to pinned host memory), "device" (left in HBM) or "none".
         zero_copy: host arrays alias the reusable pinned staging buffers of `key` (valid until
@@ -285,7 +349,7 @@ class Segmenter:
             groups, group_of, lgs, cbytes = _lib.group_lines(stats_h, stat_off, batch.widths, self.margin, TILE_H, TILE_H)
             res = PartitionResult(labels=labels, num=num_h, stats=stats_h, stat_off=stat_off, groups=groups,
                                   group_of=group_of, line_group_start=lgs, canvas=None, canvas_host=None,
-                                  canvas_bytes=cbytes)
+                                  canvas_bytes=cbytes, crops=None)
             if canvases != "none" and len(groups):
                 d_table = torch.from_numpy(groups).to(self.device, non_blocking=True)
                 d_gof = torch.from_numpy(group_of).to(self.device, non_blocking=True)
@@ -295,6 +359,8 @@ class Segmenter:
                                                       _s(batch)), "sd_group_canvas")
                 res["canvas"] = canvas[:cbytes]
                 res["_keep"] = (d_table, d_gof, d_off)
+                if crops:     # 224x224 stroke-estimator crops straight from the device canvases
+                    res["crops"] = group_crops(self.device, canvas, d_table, groups, lut=crop_lut)
                 if canvases == "host":
                     hb = pinned_buffer((key, "canvas"), cbytes)[:cbytes]
                     hb.copy_(res["canvas"], non_blocking=True)
@@ -303,6 +369,8 @@ class Segmenter:
             elif canvases != "none":
                 res["canvas"] = torch.empty(0, dtype=torch.uint8, device=self.device)
                 res["canvas_host"] = np.zeros(0, np.uint8)
+                if crops:
+                    res["crops"] = group_crops(self.device, res["canvas"], None, groups, lut=crop_lut)
         return res
 
     def segment(self, images):

@@ -222,3 +222,35 @@ def test_split_module_dropin(cuda_device):
     ra = reconstruct_images(out, a[3], a[1], a[2], 64)
     rb = O.reconstruct_images(out, b[3], b[1], b[2], 64)
     assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+
+
+def test_group_crops_bit_exact_vs_reference_calls(cuda_device):
+    """sd_group_crops == normalize -> cv2.resize -> pad -> normalize -> mean/std of evaluate_strokes.py:202-222,
+    on hand-made canvases that hit every branch: up- and down-scaling, exact 2x decimation (area path), constant
+    canvas (normalises to zero), 1-pixel canvases, long islands."""
+    import cv2
+    rng = np.random.default_rng(7)
+    shapes = [(100, 444), (1, 1), (128, 3), (2, 300), (64, 64), (111, 111), (128, 2000), (37, 222), (128, 128), (5, 7)]
+    shapes += [(int(rng.integers(1, 129)), int(rng.integers(1, 600))) for _ in range(40)]
+    canv = []
+    for k, (h, w) in enumerate(shapes):
+        c = (rng.random((h, w)) < (0.2 if k % 2 else 0.6)).astype(np.uint8)
+        if k == 4:
+            c[:] = 1                                   # constant canvas -> cv2.normalize gives zeros
+        c[rng.integers(0, h), rng.integers(0, w)] = 1   # a group always holds at least one ink pixel
+        canv.append(c)
+    dev = torch.device("cuda", 0)
+    table = np.zeros((len(canv), 6), np.int64)
+    off = 0
+    for g, c in enumerate(canv):
+        table[g] = (0, 10, 3, 10 + c.shape[1], 3 + c.shape[0], off)
+        off += c.size
+    flat = torch.from_numpy(np.concatenate([c.reshape(-1) for c in canv])).to(dev)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    out = S.group_crops(dev, flat, torch.from_numpy(table).to(dev), table, lut=S.input_lut(mean, std))
+    img = out["image"].cpu().numpy(); inp = out["image_input"].cpu().numpy()
+    for g, c in enumerate(canv):
+        ref_img, ratio, t2 = O.resize_and_pad_image(O.normalize_image(c), (224, 224), margin=1, pad_value=0)
+        assert np.array_equal(img[g], ref_img), (g, c.shape)
+        assert np.array_equal(inp[g], O.model_input_from_crop(ref_img, mean, std)), (g, c.shape)
+        assert out["ratio"][g] == ratio and tuple(out["translate2"][g]) == t2

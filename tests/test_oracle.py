@@ -165,3 +165,28 @@ def test_live_sessions_vs_reference(reference_modules, parity_state):
     for x, y in zip(pa, pb):
         assert np.array_equal(x["image_input"], y["image_input"]) and x["ratio"] == y["ratio"]
         assert tuple(x["translate1"]) == tuple(y["translate1"]) and tuple(x["translate2"]) == tuple(y["translate2"])
+
+
+def test_resize_restatement_matches_cv2():
+    """The fixed-point bilinear restatement the GPU crop kernel follows == cv2.resize (INTER_LINEAR, uint8)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    cases = [((100, 444), (222, 50)), ((1, 1), (222, 222)), ((128, 3), (5, 222)), ((2, 300), (222, 1)), ((64, 64), (32, 32))]
+    for t in range(250):
+        h, w = int(rng.integers(1, 140)), int(rng.integers(1, 700))
+        scale = min(222 / h, 222 / w)
+        cases.append(((h, w), (int(min(np.rint(scale * w), 222)), int(min(np.rint(scale * h), 222)))))
+    for k, ((h, w), (dw, dh)) in enumerate(cases):
+        if dw < 1 or dh < 1:
+            continue
+        img = (rng.random((h, w)) < (0.3 if k % 2 else 0.7)).astype(np.uint8) * 255 if k % 3 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(O.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), ((h, w), (dw, dh))
+
+
+def test_normalize_restatement_matches_cv2():
+    import cv2
+    rng = np.random.default_rng(1)
+    for t in range(500):
+        lo = int(rng.integers(0, 200)); hi = int(rng.integers(lo, 256))
+        img = rng.integers(lo, hi + 1, (int(rng.integers(1, 40)), int(rng.integers(1, 60))), dtype=np.uint8)
+        assert np.array_equal(O.normalize_minmax_u8(img), cv2.normalize(img, None, 0, 255, norm_type=cv2.NORM_MINMAX))
