@@ -6,7 +6,7 @@ binarized 128x384 tiles/s and line-images/s).
   python bench.py --impl reference --steps K --warmup W  # reference algorithm on the host CPU cores
 
 A step = one pass of the hot path over one batch of synthetic line images:
-tile -> Attention-UNet -> glue/threshold -> CCL -> island boxes -> group canvases.
+tile -> Attention-UNet -> glue/threshold -> CCL -> island boxes -> group canvases -> 224x224 crops.
 Workload at N=1 = BASELINE config 3 (512 lines, widths U[1536, 6144], 6438 tiles); for N>1
 each rank gets 512 lines of the N*512-line generator (N=8 is config 4), weak scaling, no
 data-path collective.  One JSON line is printed by rank 0.
@@ -183,7 +183,7 @@ def run_gpu(args):
     mine = shard_lines(widths, world)[rank]
     images = make_lines(mine, widths)
     engine = UNetEngine(parity_state(), device=local, max_tiles=args.max_tiles)
-    job = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk)
+    job = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops)
 
     def barrier():
         torch.cuda.synchronize()
@@ -348,6 +348,7 @@ def main():
     ap.add_argument("--lines-per-chunk", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true")
+    ap.add_argument("--no-crops", action="store_true", help="stop the step at the group canvases (no 224x224 crops)")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_gpu(args))
 

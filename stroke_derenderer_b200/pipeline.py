@@ -4,7 +4,7 @@ runs the batched segmentation step on each.
 
 The hot-path step of one rank:
    [H2D lines] -> tile_extract -> Attention-UNet (tcgen05) -> glue -> CCL -> stats
-   -> [D2H counts+stats] -> host interval grouping -> group canvases -> [D2H results]
+   -> [D2H counts+stats] -> host interval grouping -> group canvases -> 224x224 crops -> [D2H results]
 """
 
 from __future__ import annotations
@@ -66,8 +66,9 @@ class LineSegmentationJob:
     user makes with (pinned) host buffers: H2D of the lines and D2H of masks, stats and group
     canvases are inside it."""
 
-    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 64):
+    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 64, crops: bool = True):
         self.engine = engine
+        self.crops = crops                  # also build the 224x224 stroke-estimator crops of every group
         self.device = engine.device
         self.seg = S.Segmenter(engine, bin_thr=bin_thr)
         self.chunks = []
@@ -133,8 +134,15 @@ class LineSegmentationJob:
                     self.s_part.wait_event(ev)
                     if from_host:
                         ch.h_planes.copy_(ch.planes, non_blocking=True)
-                    results.append(self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=("chunk", ch.index),
-                                                      zero_copy=True))
+                    res = self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=("chunk", ch.index),
+                                             zero_copy=True, crops=self.crops)
+                    if from_host and self.crops and res["crops"] is not None:
+                        img = res["crops"]["image"]
+                        hb = S.pinned_buffer((("chunk", ch.index), "crops"), img.numel())[:img.numel()]
+                        hb.copy_(img.view(-1), non_blocking=True)
+                        res["crops"]["image_host"] = hb.numpy().reshape(tuple(img.shape))
+                        res["crops"]["input_host"] = None
+                    results.append(res)
             cur.wait_stream(self.s_unet)
             cur.wait_stream(self.s_part)
             if from_host:
@@ -153,4 +161,5 @@ class LineSegmentationJob:
     def d2h_bytes(self, results):
         n = sum(c.batch.px_total for c in self.chunks)
         n += sum(r["num"].nbytes + r["stats"].nbytes + r["canvas_bytes"] for r in results)
+        n += sum(r["crops"]["image"].numel() for r in results if r.get("crops") is not None)
         return int(n)

@@ -97,9 +97,13 @@ def main():
         if args.what != "dense":
             S.tile_extract_f16(batch, d_rgb, out=tiles)
             S.glue_u8(batch, mask_tiles, out=planes)
-        res = seg.partition(batch, planes, canvases="device")
+        res = seg.partition(batch, planes, canvases="device", crops=True)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        if len(res["groups"]):
+            out["group_crops_ms"] = ev(lambda: S.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"]))
+            out["group_crops_f32_ms"] = ev(lambda: S.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"],
+                                                                 lut=S.input_lut([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])))
         px = 128 * int(sum(batch.widths))
         out["seg"] = {"lines": batch.n_lines, "px": px, "islands": int(res["num"].sum() - batch.n_lines),
                       "groups": int(len(res["groups"])), "ccl_GBps_algorithmic": 5 * px / out["ccl_ms"] / 1e6}
