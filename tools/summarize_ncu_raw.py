@@ -8,7 +8,9 @@ import sys
 
 COLS = [
     ("gpu__time_duration.sum", "us", 1e-3),
-    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor %", 1),
+    # tcgen05 kernels: sm__mem_tensor_cycles_active is the counter that tracks the UMMA datapath (it equals executed
+    # MACs / 4096 per SM-cycle on every conv launch); the *_realtime tensor counters return stale values under replay
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe %", 1),
     ("dram__bytes_read.sum", "DRAM rd MB", 1e-6),
     ("dram__bytes_write.sum", "DRAM wr MB", 1e-6),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %", 1),
@@ -59,6 +61,20 @@ def main():
                   f"compare shares and ratios, not absolutes)\n")
     open(sys.argv[2], "w").write("\n".join(out) + "\n")
     print("\n".join(out))
+    if len(sys.argv) > 4:   # traffic json: DRAM bytes per launch of the kernels whose name matches argv[5] (regex)
+        rx = re.compile(sys.argv[5] if len(sys.argv) > 5 else ".")
+        tot = n = 0
+        for r in data:
+            if len(r) < len(hdr) or not rx.search(r[idx["Kernel Name"]]):
+                continue
+            b = 0.0
+            for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[idx[c]], 1.0)
+                b += num(r[idx[c]]) * mul
+            tot += b; n += 1
+        json.dump({"kernels": rx.pattern, "launches": n, "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(n, 1),
+                   "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum"},
+                  open(sys.argv[4], "w"), indent=1)
 
 
 if __name__ == "__main__":
