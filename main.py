@@ -4,7 +4,7 @@ framework's hot path: `strokes=True` writes the segmentation resul
 group boxes) as `<stem>_PARTITIONS.json` instead of `<stem>_STROKES.json`.
 
   python main.py -models DIR [-input DIR] [--output DIR]      (reference flags, main.py:20-30)
-DIR holds `binarizer.npz` (state dict; offline stand-in for the Drive `binarizer.onnx`)
+DIR holds `binarizer.onnx` (read without onnx/onnxruntime) or `binarizer.npz` (state dict with the upstream names)
 and optionally `configs_binarizer.json` / `configs_strokes.json`.
 """
 
@@ -32,9 +32,11 @@ def initialize_sessions(folderpath):
     folder = Path(folderpath)
     cfg_b = folder / "configs_binarizer.json"
     bs = BinarizationSession(configs_path=str(cfg_b) if cfg_b.exists() else None)
-    weights = folder / "binarizer.npz"
+    weights = folder / "binarizer.onnx"               # main.py:43
     if not weights.exists():
-        raise FileNotFoundError(f"{weights} not found (convert the binarizer checkpoint to an .npz state dict)")
+        weights = folder / "binarizer.npz"
+    if not weights.exists():
+        raise FileNotFoundError(f"neither binarizer.onnx nor binarizer.npz found in {folder}")
     ort_bs = bs.init_onnx_inference(str(weights))
     cfg_s = folder / "configs_strokes.json"
     se = StrokeEstimationSession(configs_path=str(cfg_s) if cfg_s.exists() else None)

@@ -36,8 +36,8 @@ class BinarizationSession:
         self.max_tiles = params.get("max_tiles", 64)
 
     def init_onnx_inference(self, onnxpath):
-        """:48-53.  `onnxpath` may be a `.npz` state dict (offline stand-in for the
-        Drive `binarizer.onnx`) or a dict of arrays."""
+        """:48-53.  `onnxpath`: an exported `binarizer.onnx` (initializers read by `onnx_reader`, no
+        onnx/onnxruntime needed), a `.npz` state dict with the upstream parameter names, or a dict of arrays."""
         return UNetEngine(onnxpath, device=self.device, max_tiles=self.max_tiles)
 
     def ort_predict(self, input_numpy, ort):

@@ -92,7 +92,7 @@ def fold_conv_bn(sd: dict, conv: str, bn: str | None):
     s = gamma / sqrt(var + eps); w' = w * s; b' = (b - mean) * s + beta."""
     w = sd[f"{conv}.weight"].astype(np.float64)
     b = sd[f"{conv}.bias"].astype(np.float64)
-    if bn is not None:
+    if bn is not None and f"{bn}.weight" in sd:       # a dict without BN entries is already folded (onnx_reader)
         s = sd[f"{bn}.weight"].astype(np.float64) / np.sqrt(
             sd[f"{bn}.running_var"].astype(np.float64) + BN_EPS)
         w = w * s[:, None, None, None]
@@ -105,6 +105,10 @@ def save_weights(path: str, sd: dict) -> None:
 
 
 def load_weights(path: str) -> dict[str, np.ndarray]:
-    """Loads a `.npz` state dict (the offline stand-in for `binarizer.onnx`)."""
+    """Loads a checkpoint: a `.npz` state dict with the upstream parameter names, or an exported
+    `binarizer.onnx` (/root/reference/main.py:43) through the dependency-free reader."""
+    if str(path).lower().endswith(".onnx"):
+        from .onnx_reader import load_onnx_state
+        return load_onnx_state(str(path))
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
