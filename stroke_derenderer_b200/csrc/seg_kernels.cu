@@ -67,11 +67,14 @@ __device__ __forceinline__ int find_tile_line(const sd_line* __restrict__ L, int
   return lo;
 }
 
-// one CTA per (tile, row); thread x handles output columns x, x+blockDim, ...
+// one CTA per (tile, group of kExtRows rows); a thread converts 3 pixels of every row of the group, all source
+// bytes of the group are requested before the first conversion (the kernel is a pure stream: 3 B in, 16 B out).
+constexpr int kExtRows = 8;
 __global__ void __launch_bounds__(128) tile_extract_f16_kernel(
     const uint8_t* __restrict__ rgb, const sd_line* __restrict__ L, int n_lines, int tile_w,
     uint4* __restrict__ out) {
-  const int tile = blockIdx.x >> 7, row = blockIdx.x & 127;
+  constexpr int kGroups = SD_TILE_H / kExtRows;
+  const int tile = blockIdx.x / kGroups, row0 = (blockIdx.x % kGroups) * kExtRows;
   __shared__ int s_l;
   if (threadIdx.x == 0) s_l = find_tile_line(L, n_lines, tile);
   __syncthreads();
@@ -79,24 +82,25 @@ __global__ void __launch_bounds__(128) tile_extract_f16_kernel(
   const int ti = tile - ln.first_tile;
   const int wd = tile_width(ln, ti);
   const int x0 = (ln.n_tiles == 1) ? 0 : ti * ln.wu;
-  const uint8_t* src = rgb + ln.img_off + ((int64_t)row * ln.width + x0) * 3;
-  uint4* dst = out + ((int64_t)tile * SD_TILE_H + row) * tile_w;
   for (int x = threadIdx.x; x < tile_w; x += blockDim.x) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (x < wd) {
+    uint8_t px[kExtRows][3];
+    const bool in = x < wd;
+#pragma unroll
+    for (int r = 0; r < kExtRows; ++r) {
+      const uint8_t* src = rgb + ln.img_off + ((int64_t)(row0 + r) * ln.width + x0 + x) * 3;
+      px[r][0] = in ? __ldg(src + 0) : 0; px[r][1] = in ? __ldg(src + 1) : 0; px[r][2] = in ? __ldg(src + 2) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kExtRows; ++r) {
       // (x / 255.).astype(float32) then to fp16 (evaluate_binarize.py:99)
       // x/255 is never within an f32 ulp of an fp16 rounding boundary, so the
       // f32 division rounds to the same half as numpy's float64 path (tested
       // for all 256 values).
-      float r = (float)src[3 * x + 0] / 255.f;
-      float g = (float)src[3 * x + 1] / 255.f;
-      float b = (float)src[3 * x + 2] / 255.f;
-      __half2 rg = __floats2half2_rn(r, g);
-      __half2 b0 = __floats2half2_rn(b, 0.f);
-      v.x = *reinterpret_cast<uint32_t*>(&rg);
-      v.y = *reinterpret_cast<uint32_t*>(&b0);
+      __half2 rg = __floats2half2_rn((float)px[r][0] / 255.f, (float)px[r][1] / 255.f);
+      __half2 b0 = __floats2half2_rn((float)px[r][2] / 255.f, 0.f);
+      uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&rg), *reinterpret_cast<uint32_t*>(&b0), 0u, 0u);
+      out[((int64_t)tile * SD_TILE_H + row0 + r) * tile_w + x] = v;
     }
-    dst[x] = v;
   }
 }
 
@@ -189,9 +193,9 @@ __device__ __forceinline__ uint32_t range_mask(int wi, int lo, int hi) {
 
 // one CTA per (line, group of kGlueRows rows): a thread owns one 16-px unit column, resolves the covering
 // tiles once and then issues the loads of all its rows back to back (the kernel is latency bound otherwise).
-constexpr int kGlueRows = 4;
+constexpr int kGlueRows = 8;
 template <bool kProb>
-__global__ void __launch_bounds__(128) glue_kernel(
+__global__ void __launch_bounds__(64) glue_kernel(
     const void* __restrict__ tiles, const sd_line* __restrict__ L, int64_t tile_elems_total, float thr,
     uint32_t on_rep, uint4* __restrict__ out) {
   constexpr int kGroups = SD_TILE_H / kGlueRows;
@@ -1048,7 +1052,7 @@ extern "C" int64_t sd_group_lines(const int32_t* stats, const int64_t* stat_off,
 extern "C" int sd_tile_extract_f16(const uint8_t* d_rgb, const sd_line* d_lines, int n_lines, int n_tiles,
                                    void* d_out, void* stream) {
   SD_REQUIRE(d_rgb && d_lines && d_out && n_lines > 0 && n_tiles > 0, "sd_tile_extract_f16: bad argument");
-  tile_extract_f16_kernel<<<n_tiles * SD_TILE_H, 128, 0, (cudaStream_t)stream>>>(
+  tile_extract_f16_kernel<<<n_tiles * (SD_TILE_H / kExtRows), 128, 0, (cudaStream_t)stream>>>(
       d_rgb, d_lines, n_lines, SD_TILE_W, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("tile_extract_f16_kernel");
   return SD_OK;
@@ -1068,7 +1072,7 @@ extern "C" int sd_glue_u8(const uint8_t* d_tiles, int n_tiles, const sd_line* d_
   SD_REQUIRE(d_tiles && d_lines && d_out && n_lines > 0 && n_tiles > 0 && px_total > 0 && px_total % 16 == 0,
              "sd_glue_u8: bad argument");
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;   // clamps edge loads
-  glue_kernel<false><<<n_lines * (SD_TILE_H / kGlueRows), 128, 0, (cudaStream_t)stream>>>(
+  glue_kernel<false><<<n_lines * (SD_TILE_H / kGlueRows), 64, 0, (cudaStream_t)stream>>>(
       d_tiles, d_lines, elems, 0.f, 0u, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<u8>");
   return SD_OK;
@@ -1081,7 +1085,7 @@ extern "C" int sd_glue_threshold_f16(const void* d_prob, int n_tiles, const sd_l
   SD_REQUIRE(on_value > 0 && on_value <= 255, "sd_glue_threshold_f16: on_value %d", on_value);
   const int64_t elems = (int64_t)n_tiles * SD_TILE_H * SD_TILE_W;
   const uint32_t rep = (uint32_t)on_value * 0x01010101u;
-  glue_kernel<true><<<n_lines * (SD_TILE_H / kGlueRows), 128, 0, (cudaStream_t)stream>>>(
+  glue_kernel<true><<<n_lines * (SD_TILE_H / kGlueRows), 64, 0, (cudaStream_t)stream>>>(
       d_prob, d_lines, elems, bin_thr, rep, reinterpret_cast<uint4*>(d_out));
   SD_LAUNCH_CHECK("glue_kernel<f16>");
   return SD_OK;
