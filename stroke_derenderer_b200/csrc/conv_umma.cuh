@@ -29,6 +29,8 @@ enum { EPI_STORE = 0, EPI_GATE = 1, EPI_HEAD = 2 };
 struct ConvParams {
   CUtensorMap tmA0, tmA1, tmB;
   CUtensorMap tmOut[4];        // store epilogue: one output map per sub-pixel phase
+  CUtensorMap tmPool;          // store epilogue with pool != 0: the 2x2 max-pooled copy of the output
+  int pool;
   // geometry of the (low-res for up-convs) input grid the M tiles walk over
   int H, W, B;                 // image dims of the A source, live batch
   int box_w, box_h, box_n;     // pixels per M tile = box_w*box_h*box_n = 128
@@ -162,6 +164,26 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // named barrier for the 4 epilogue warps only (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 hmax2_v4(uint4 a, uint4 b) {
+  return make_uint4(hmax2_u32(a.x, b.x), hmax2_u32(a.y, b.y), hmax2_u32(a.z, b.z), hmax2_u32(a.w, b.w));
+}
+// 16-B chunk `ch` of row `r` of a [rows x 128 B] tile stored with the 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128(uint32_t base, int r, int ch) {
+  return base + (uint32_t)r * 128u + ((uint32_t)(ch ^ (r & 7)) << 4);
+}
+
 constexpr int kMiscBytes = 4096;       // barriers | tmem slot | bias | psi/head vector | gate scale | pixel index
 constexpr int kMaxSmem = 232448;       // 227 KB opt-in limit per CTA
 
@@ -172,7 +194,7 @@ template <int BN, int EPI, int MT = 1> struct ConvCfg {
   static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves, per M tile
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * 64 * 2 : 0;   // swizzled staging of ONE 64-channel half for the TMA store
+  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * 64 * 2 + 4096 : 0;   // swizzled staging of ONE 64-channel half for the TMA store + its 2x2-pooled copy
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTmemCols = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // 64,128,256,512: powers of two
@@ -211,6 +233,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     if (p.c1_blocks) tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmB);
     if (EPI == EPI_STORE) for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.tmOut[i]);
+    if (EPI == EPI_STORE && p.pool) tma_prefetch_desc(&p.tmPool);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -370,6 +393,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             if (et == 0) {
               tma_store_4d(&p.tmOut[ph], out_base, nt * BN + hb * 64, x0, y0, n0);
               tma_store_commit();
+            }
+            if (p.pool) {
+              // fused MaxPool2x2: the staged tile holds whole 2x2 windows (box dims are even); 32 pooled pixels x 8 chunks
+              const int pw = p.box_w >> 1, phh = p.box_h >> 1;
+              const uint32_t pool_base = out_base + 16384u;
+#pragma unroll
+              for (int task = et; task < 256; task += 128) {
+                const int pp = task >> 3, ch = task & 7;
+                const int px = pp % pw; const int r2 = pp / pw;
+                const int py = r2 % phh, pn = r2 / phh;
+                const int m00 = (pn * p.box_h + 2 * py) * p.box_w + 2 * px, m10 = m00 + p.box_w;
+                const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, m00, ch)), ld_shared_v4(sw128(out_base, m00 + 1, ch))),
+                                         hmax2_v4(ld_shared_v4(sw128(out_base, m10, ch)), ld_shared_v4(sw128(out_base, m10 + 1, ch))));
+                st_shared_v4(sw128(pool_base, pp, ch), v);
+              }
+              fence_async_smem();
+              epi_bar();
+              if (et == 0) {
+                tma_store_4d(&p.tmPool, pool_base, nt * BN + hb * 64, x0 >> 1, y0 >> 1, n0);
+                tma_store_commit();
+              }
             }
           }
         }
@@ -683,7 +727,8 @@ constexpr int kBandRows = 32;
 
 template <int CB, int EPI> struct BandCfg {
   static constexpr int kWBytes = 9 * CB * 8192;        // [dx][cb][ky = 2, 1, 0][64 cout] rows of 128 B
-  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 16384 : 0;
+  static constexpr bool kCanPool = (EPI == EPI_STORE) && CB == 1;      // fused MaxPool2x2 (Conv1.3): two row buffers + pooled row
+  static constexpr int kOutBytes = (EPI == EPI_STORE ? 16384 : 0) + (kCanPool ? 16384 + 8192 : 0);
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kWBytes - kOutBytes) / kRowStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kSmemBytes = kStages * kRowStageBytes + kWBytes + kOutBytes + 1024 + kMiscBytes;
@@ -726,6 +771,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
     if (CB > 1) tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&p.tmOut[0]);
+    if (Cfg::kCanPool && p.pool) tma_prefetch_desc(&p.tmPool);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -859,6 +905,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
         mbar_wait(tfull_bar(slot), (uint32_t)((g >> 3) & 1), p.err_flag, 4);
         tc_fence_after();
         if constexpr (EPI == EPI_STORE) {
+          const bool pooling = Cfg::kCanPool && p.pool;
+          const uint32_t row_buf = out_base + ((pooling && (y & 1)) ? 16384u : 0u);     // rows alternate buffers when pooling
           if (et == 0) tma_store_wait_read();
           epi_bar();
 #pragma unroll 1
@@ -866,7 +914,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
             float v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_st32_zero(taddr + c * 32);
-            const uint32_t rbase = out_base + (uint32_t)row * 128u;
+            const uint32_t rbase = row_buf + (uint32_t)row * 128u;
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               uint32_t pk[4];
@@ -887,7 +935,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
           mbar_arrive(tempty_bar(slot));
           fence_async_smem();
           epi_bar();
-          if (et == 0) { tma_store_4d(&p.tmOut[0], out_base, 0, sx * 128, y, n); tma_store_commit(); }
+          if (et == 0) { tma_store_4d(&p.tmOut[0], row_buf, 0, sx * 128, y, n); tma_store_commit(); }
+          if (pooling && (y & 1)) {
+            // fused MaxPool2x2 over rows y-1 (buffer 0) and y (buffer 1): 64 pooled pixels x 8 chunks
+            const uint32_t pool_base = out_base + 32768u;
+#pragma unroll
+            for (int task = et; task < 512; task += 128) {
+              const int pp = task >> 3, ch = task & 7;
+              const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, 2 * pp, ch)), ld_shared_v4(sw128(out_base, 2 * pp + 1, ch))),
+                                       hmax2_v4(ld_shared_v4(sw128(out_base + 16384u, 2 * pp, ch)),
+                                                ld_shared_v4(sw128(out_base + 16384u, 2 * pp + 1, ch))));
+              st_shared_v4(sw128(pool_base, pp, ch), v);
+            }
+            fence_async_smem();
+            epi_bar();
+            if (et == 0) { tma_store_4d(&p.tmPool, pool_base, 0, sx * 64, y >> 1, n); tma_store_commit(); }
+          }
         } else {
           float dot = 0.f;
 #pragma unroll 1

@@ -242,6 +242,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
   int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
   int bn_max = 256;                    // widest N tile of the generic conv kernel (SD_BNMAX=256 to try 128x256 tiles)
@@ -302,6 +303,18 @@ static int make_tmap_out(sd_engine* e, CUtensorMap* tm, const Act& o, const Leve
   CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out C=%d W=%d H=%d up=%d) failed: %d", o.C, o.W, o.H, (int)up, (int)r); return SD_ECUDA; }
+  return SD_OK;
+}
+
+// pooled copy of a store-epilogue output: (C, W/2, H/2, N) with half-size boxes
+static int make_tmap_pool(sd_engine* e, CUtensorMap* tm, const Act& o, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)e->cap_tiles};
+  cuuint64_t strides[3] = {(cuuint64_t)o.C * 2, (cuuint64_t)o.W * o.C * 2, (cuuint64_t)o.H * o.W * o.C * 2};
+  cuuint32_t boxd[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, o.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pool C=%d W=%d H=%d) failed: %d", o.C, o.W, o.H, (int)r); return SD_ECUDA; }
   return SD_OK;
 }
 
@@ -430,6 +443,7 @@ struct ConvSpec {
   bool up;
   int epi;                          // EPI_*
   int att = -1;                     // gate: index 0..3 (psi slot / bias), x source = in1
+  const Act* pool_out = nullptr;    // store epilogue: also write MaxPool2x2(out) here (fused pool)
 };
 
 static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
@@ -446,7 +460,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   int r;
   const bool row_ok = e->row_mode > 0 && lvl == 0 && L.W % 128 == 0 && co == 64 && !cs.up && e->ks[slot] == 3 &&
                       cs.in0->C == 64 && (!cs.in1 || cs.in1->C == 64) && (cs.epi == EPI_STORE || cs.epi == EPI_HEAD) &&
-                      !(cs.in1 && cs.epi == EPI_HEAD);
+                      !(cs.in1 && cs.epi == EPI_HEAD) && !(cs.pool_out && e->row_mode < 2);
   if (row_ok) {
     const int cb = cs.in1 ? 2 : 1;
     Level halo = L; halo.box_w = 130; halo.box_h = 1; halo.box_n = 1;
@@ -458,12 +472,17 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     if (cs.epi == EPI_STORE) {
       p.out = cs.out->p; p.out_c = cs.out->C;
       if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
+      if (cs.pool_out) {
+        SD_REQUIRE(e->row_mode >= 2 && !cs.in1, "add_umma_conv(%s): fused pool needs the band kernel with one source", cs.name);
+        if ((r = make_tmap_pool(e, &p.tmPool, *cs.pool_out, 64, 1, 1))) return r;
+        p.pool = 1;
+      }
     } else {
       p.head_w = e->w_f32[SD_HEAD];
     }
     Op op;
     const int band = e->row_mode >= 2;
-    op.name = std::string(cs.name) + (band ? "[band]" : "[row]");
+    op.name = std::string(cs.name) + (band ? "[band]" : "[row]") + (p.pool ? "+pool" : "");
     const int epi = cs.epi, nsm = e->num_sms, segs = L.W / 128, H = L.H;
     op.flops_per_tile = 2.0 * L.H * L.W * co * 9 * cin_total;
     op.run = [e, p, cb, epi, nsm, segs, H, band](int B, cudaStream_t s) mutable -> int {
@@ -517,6 +536,11 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     p.out = cs.out->p; p.out_c = cs.out->C;
     for (int ph = 0; ph < p.n_phases; ++ph)
       if ((r = make_tmap_out(e, &p.tmOut[ph], *cs.out, L, cs.up, ph))) return r;
+    if (cs.pool_out) {
+      SD_REQUIRE(!cs.up && L.box_w % 2 == 0 && L.box_h % 2 == 0, "add_umma_conv(%s): fused pool needs even box dims", cs.name);
+      if ((r = make_tmap_pool(e, &p.tmPool, *cs.pool_out, L.box_w / 2, L.box_h / 2, L.box_n))) return r;
+      p.pool = 1;
+    }
   }
   if (cs.epi == EPI_GATE) {
     p.out = cs.out->p; p.out_c = cs.out->C;
@@ -525,7 +549,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   }
   if (cs.epi == EPI_HEAD) { p.head_w = e->w_f32[SD_HEAD]; }
   Op op;
-  op.name = cs.name;
+  op.name = std::string(cs.name) + (p.pool ? "+pool" : "");
   const int epi = cs.epi;
   const int box_n = L.box_n, per_img = p.tiles_x * p.tiles_y;
   const int nsm = e->num_sms;
@@ -659,6 +683,8 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* bm = getenv("SD_BNMAX")) e->bn_max = atoi(bm);
   if (const char* m2 = getenv("SD_MT2")) e->mt2_max_bn = atoi(m2);
   if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
+  if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
+  if (e->row_mode < 2) e->fuse_pool = 0;            // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -803,6 +829,18 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
     add_simt_conv(e, name, slot, i0, i1, o, up, nullptr);
     return SD_OK;
   };
+  // conv followed by MaxPool2x2: fused into the conv's store epilogue on the tcgen05 path
+  auto conv_pool = [&](const char* name, const char* pool_name, int slot, const Act* i0, const Act* o, const Act* po) -> int {
+    if (impl == 0 && e->fuse_pool) {
+      ConvSpec cs{name, slot, i0, nullptr, o, false, EPI_STORE, -1};
+      cs.pool_out = po;
+      return add_umma_conv(e, cs);
+    }
+    int rr = conv(name, slot, i0, nullptr, o, false);
+    if (rr) return rr;
+    add_pool(e, pool_name, o, po);
+    return SD_OK;
+  };
   auto gate = [&](const char* name, int att, const Act* g, const Act* x, const Act* o) -> int {
     const int sg = SD_ATT5_G + 6 * att;
     if (impl == 0) { ConvSpec cs{name, sg, g, x, o, false, EPI_GATE, att}; return add_umma_conv(e, cs); }
@@ -840,17 +878,13 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
     }
   }
 
-  if ((r = conv("Conv1.3", SD_CONV1_1, &e->c1a, nullptr, &A[SD_TAP_X1], false))) return r;
-  add_pool(e, "pool1", &A[SD_TAP_X1], &e->p1);
+  if ((r = conv_pool("Conv1.3", "pool1", SD_CONV1_1, &e->c1a, &A[SD_TAP_X1], &e->p1))) return r;
   if ((r = conv("Conv2.0", SD_CONV2_0, &e->p1, nullptr, &e->c2a, false))) return r;
-  if ((r = conv("Conv2.3", SD_CONV2_1, &e->c2a, nullptr, &A[SD_TAP_X2], false))) return r;
-  add_pool(e, "pool2", &A[SD_TAP_X2], &e->p2);
+  if ((r = conv_pool("Conv2.3", "pool2", SD_CONV2_1, &e->c2a, &A[SD_TAP_X2], &e->p2))) return r;
   if ((r = conv("Conv3.0", SD_CONV3_0, &e->p2, nullptr, &e->c3a, false))) return r;
-  if ((r = conv("Conv3.3", SD_CONV3_1, &e->c3a, nullptr, &A[SD_TAP_X3], false))) return r;
-  add_pool(e, "pool3", &A[SD_TAP_X3], &e->p3);
+  if ((r = conv_pool("Conv3.3", "pool3", SD_CONV3_1, &e->c3a, &A[SD_TAP_X3], &e->p3))) return r;
   if ((r = conv("Conv4.0", SD_CONV4_0, &e->p3, nullptr, &e->c4a, false))) return r;
-  if ((r = conv("Conv4.3", SD_CONV4_1, &e->c4a, nullptr, &A[SD_TAP_X4], false))) return r;
-  add_pool(e, "pool4", &A[SD_TAP_X4], &e->p4);
+  if ((r = conv_pool("Conv4.3", "pool4", SD_CONV4_1, &e->c4a, &A[SD_TAP_X4], &e->p4))) return r;
   if ((r = conv("Conv5.0", SD_CONV5_0, &e->p4, nullptr, &e->c5a, false))) return r;
   if ((r = conv("Conv5.3", SD_CONV5_1, &e->c5a, nullptr, &A[SD_TAP_X5], false))) return r;
 
