@@ -31,6 +31,7 @@ struct ConvParams {
   CUtensorMap tmOut[4];        // store epilogue: one output map per sub-pixel phase
   CUtensorMap tmPool;          // store epilogue with pool != 0: the 2x2 max-pooled copy of the output
   int pool;
+  float bias_c[64], vec_c[64]; // band kernel: bias and head vector in the constant bank (no smem reads in the epilogue)
   // geometry of the (low-res for up-convs) input grid the M tiles walk over
   int H, W, B;                 // image dims of the A source, live batch
   int box_w, box_h, box_n;     // pixels per M tile = box_w*box_h*box_n = 128
@@ -762,8 +763,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
   auto tempty_bar = [&](int s) { return bar_base + 8u * (24 + s); };
   const uint32_t w_bar = bar_base + 8u * 32;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 384);
-  float* s_bias = reinterpret_cast<float*>(misc + 512);
-  float* s_vec = reinterpret_cast<float*>(misc + 768);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -784,10 +783,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    if (t < 64) { s_bias[t] = p.bias[t]; if (EPI == EPI_HEAD) s_vec[t] = p.head_w[t]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -909,7 +904,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
           const uint32_t row_buf = out_base + ((pooling && (y & 1)) ? 16384u : 0u);     // rows alternate buffers when pooling
           if (et == 0) tma_store_wait_read();
           epi_bar();
-#pragma unroll 1
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
             float v[32];
             tmem_ld32(taddr + c * 32, v);
@@ -921,7 +916,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int col = j4 * 8 + j * 2;
-                float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b2 = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
+                float a = fmaxf(v[col] + p.bias_c[c * 32 + col], 0.f), b2 = fmaxf(v[col + 1] + p.bias_c[c * 32 + col + 1], 0.f);
                 __half2 h = __floats2half2_rn(a, b2);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
               }
@@ -953,16 +948,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
           }
         } else {
           float dot = 0.f;
-#pragma unroll 1
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
             float v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_st32_zero(taddr + c * 32);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float a = fmaxf(v[j] + s_bias[c * 32 + j], 0.f);
+              float a = fmaxf(v[j] + p.bias_c[c * 32 + j], 0.f);
               a = __half2float(__float2half_rn(a));
-              dot = fmaf(a, s_vec[c * 32 + j], dot);
+              dot = fmaf(a, p.vec_c[c * 32 + j], dot);
             }
           }
           tmem_st_wait();

@@ -469,6 +469,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], co, 9 * cin_total, 64))) return r;
     p.H = L.H; p.W = L.W; p.cout = co; p.relu = 1; p.n_phases = 1;
     p.bias = e->bias[slot]; p.err_flag = e->err_flag;
+    for (int i = 0; i < 64; ++i) { p.bias_c[i] = e->hb[slot][i]; p.vec_c[i] = cs.epi == EPI_HEAD ? e->hw[SD_HEAD][i] : 0.f; }
     if (cs.epi == EPI_STORE) {
       p.out = cs.out->p; p.out_c = cs.out->C;
       if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;

@@ -1,0 +1,73 @@
+// Micro-benchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M = 128, K = 16) as a function of N, with both
+// operands resident in shared memory (128-byte swizzle, K-major), one CTA per SM, one issuing thread.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu && ./umma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+  return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_blocks, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t bar;
+  const uint32_t bar_a = smem_u32(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t b_base = base + 128 * 1024;                     // B: up to 256 rows x 128 B
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t a = base + (uint32_t)(it % a_blocks) * 16384u;   // rotate over a_blocks different A tiles
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma(tm, desc_sw128(a) + 2u * k, desc_sw128(b_base) + 2u * k, idesc, 1u);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a) : "memory");
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar_a) : "memory");
+    out[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 148 * sizeof(long long));
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 4000;
+  for (int ctas : {1, 148}) {
+    for (int N : {16, 32, 64, 96, 128, 192, 256}) {
+      rate_kernel<<<ctas, 128, 200 * 1024>>>(N, iters, 8, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("N=%d failed: %s\n", N, cudaGetErrorString(e)); return 1; }
+      long long h[148]; cudaMemcpy(h, d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0; for (int i = 0; i < ctas; ++i) mx = h[i] > mx ? h[i] : mx;
+      const double cyc = (double)mx / (iters * 4.0);
+      printf("ctas=%3d N=%3d  %.1f cycles per MMA (K=16)  -> %.0f MAC/clk/SM, smem operand read %.0f B/clk\n", ctas, N, cyc,
+             128.0 * N * 16 / cyc, (128 * 16 * 2 + N * 16 * 2) / cyc);
+    }
+  }
+  return 0;
+}
