@@ -982,6 +982,203 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
+// conv_up4_kernel: nearest-x2 upsample + conv3x3 with Cout = 64 (Up2), all four sub-pixel phases in one work item.
+// Run phase by phase (generic kernel) every MMA has N = 64 and costs the 71-cycle operand-read floor: 45 % of the
+// tensor peak at best.  Here a work item is one M tile of 128 LOW-res pixels; its four phase accumulators sit side
+// by side in TMEM (4 x 64 columns, order (py,px) = (0,1) (0,0) (1,0) (1,1)) and each of the 9 low-res taps is
+// multiplied ONCE against the pre-summed weights of every phase that uses it: N = 256 for the centre tap, 128 for
+// the edge taps (one of them wraps the slot ring and is issued as 2 x 64), 64 for the corners -> 80 instead of
+// 128 MMAs per tile and 18 instead of 32 A boxes.  Store epilogue as in conv_umma_kernel (one strided output map
+// per phase).
+// ---------------------------------------------------------------------------------------------
+struct Up4Cfg {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = 4 * 8192;              // up to four 64-row weight blocks
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = 16384;
+  static constexpr int kStages = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;   // 4
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kMiscBytes;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+// tap order: the centre tap first (its N = 256 MMA initialises all four accumulators).  Per tap: low-res offset,
+// first TMEM slot and number of phases that use it (slots in ring order: 0 = (py,px) (0,1), 1 = (0,0), 2 = (1,0),
+// 3 = (1,1); the (0,+1) tap covers slots 3 and 0 and wraps).  The weights are packed on the host in exactly this
+// order ([tap][cb][phase in slot order][co] rows of 64 halves), so one TMA fetches a stage's whole B operand.
+struct Up4Tap { int dy, dx, first, count, prefix; };
+__host__ __device__ constexpr Up4Tap up4_tap(int t) {
+  constexpr Up4Tap tab[9] = {{0, 0, 0, 4, 0},  {-1, -1, 1, 1, 4}, {-1, 0, 0, 2, 5}, {-1, 1, 0, 1, 7}, {0, -1, 1, 2, 8},
+                             {0, 1, 3, 2, 10}, {1, -1, 2, 1, 12}, {1, 0, 2, 2, 13}, {1, 1, 3, 1, 15}};
+  return tab[t];
+}
+__host__ __device__ constexpr int up4_slot_phase(int slot) { return slot == 0 ? 1 : (slot == 1 ? 0 : (slot == 2 ? 2 : 3)); }   // ph = py * 2 + px
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = Up4Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* misc = smem_al + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes;
+  const uint32_t bar_base = out_base + Cfg::kOutBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
+  float* s_bias = reinterpret_cast<float*>(misc + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB); tma_prefetch_desc(&p.tmA1); tma_prefetch_desc(&p.tmPool);   // weight maps with 64 / 128 / 256-row boxes
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmOut[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 64) s_bias[t] = p.bias[t];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_work = p.m_tiles;
+  const int cbs = p.c0_blocks;                           // 64-channel blocks of the (single) source
+  auto origin = [&](int mt, int& x0, int& y0, int& n0) {
+    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
+    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
+    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int x0, y0, n0;
+        origin(w, x0, y0, n0);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const Up4Tap tp = up4_tap(t);
+          // B operand of the stage: count x 64 rows, one TMA through the map whose box has that many rows
+          const CUtensorMap* tmb = tp.count == 4 ? &p.tmPool : (tp.count == 2 ? &p.tmA1 : &p.tmB);
+          for (int cb = 0; cb < cbs; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+            mbar_expect_tx(full_bar(stage), Cfg::kABytes + tp.count * 8192);
+            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+            tma_load_4d(a_dst, &p.tmA0, full_bar(stage), cb * 64, x0 + tp.dx, y0 + tp.dy, n0);
+            tma_load_2d(a_dst + Cfg::kABytes, tmb, full_bar(stage), 0, (tp.prefix * cbs + cb * tp.count) * 64);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const Up4Tap tp = up4_tap(t);
+          const int first = tp.first, count = tp.count;
+          const int n1 = count < 4 - first ? count : 4 - first, n2 = count - n1;       // split where the slot ring wraps
+          const uint32_t idesc1 = (1u << 4) | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
+          for (int cb = 0; cb < cbs; ++cb) {
+            mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc1 = umma_desc_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem + (uint32_t)(first * 64), adesc + 2u * k, bdesc1 + 2u * k, idesc1, (uint32_t)((t | cb | k) != 0));
+            if (n2) {
+              const uint64_t bdesc2 = umma_desc_sw128(a_addr + Cfg::kABytes + n1 * 8192);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2u * k, bdesc2 + 2u * k, idesc2, 1u);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int x0, y0, n0;
+      origin(w, x0, y0, n0);
+      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int slot = 0; slot < 4; ++slot) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + slot * 64);
+        if (et == 0) tma_store_wait_read();
+        epi_bar();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          const uint32_t rbase = out_base + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = j4 * 8 + j * 2;
+              float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
+              __half2 h = __floats2half2_rn(a, b);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t chunk = (uint32_t)(c * 4 + j4);
+            const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        }
+        if (slot == 3) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));
+        }
+        fence_async_smem();
+        epi_bar();
+        if (et == 0) { tma_store_4d(&p.tmOut[up4_slot_phase(slot)], out_base, 0, x0, y0, n0); tma_store_commit(); }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // conv_first_umma_kernel: Conv1.0, 3(+5 zero) -> 64 channels, 3x3, pad 1, bias + ReLU on the tensor pipe.
 // The NHWC8 input makes one (pixel, tap) = 8 halves = 16 B = exactly one row of a UMMA core matrix, so the
 // im2col A tile [128 px x K = 9 taps x 8 ch (+8 zero) = 80] is written by 128 producer threads straight into

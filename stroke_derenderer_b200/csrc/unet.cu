@@ -242,6 +242,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int up4 = 1;                         // Up2: four sub-pixel phases per work item (SD_UP4=0: generic kernel, phase by phase)
   int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
   int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
@@ -549,6 +550,52 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     p.gate_x = cs.in1->p; p.gate_c = cs.in1->C;
   }
   if (cs.epi == EPI_HEAD) { p.head_w = e->w_f32[SD_HEAD]; }
+  if (cs.up && co == 64 && !cs.in1 && cs.epi == EPI_STORE && e->up4) {
+    // all four sub-pixel phases per work item (conv_up4_kernel).  Weights re-packed as [tap][cb][phase in slot
+    // order][co] rows of 64 halves, so a stage's B operand is one box of 64 / 128 / 256 rows (three maps).
+    {
+      const int cbs = cin_total / 64;
+      std::vector<__half> wp((size_t)16 * cbs * 64 * 64);
+      std::vector<__half> src((size_t)4 * co * K);
+      SD_CUDA_CHECK(cudaMemcpy(src.data(), e->w_umma[slot], src.size() * 2, cudaMemcpyDeviceToHost));
+      for (int t = 0; t < 9; ++t) {
+        const Up4Tap tp = up4_tap(t);
+        for (int cb = 0; cb < cbs; ++cb)
+          for (int i = 0; i < tp.count; ++i) {
+            const int ph = up4_slot_phase((tp.first + i) & 3);
+            const int ty = tp.dy + 1 - (ph >> 1), tx = tp.dx + 1 - (ph & 1);
+            const size_t row0 = ((size_t)tp.prefix * cbs + (size_t)cb * tp.count + i) * 64;
+            for (int c2 = 0; c2 < 64; ++c2)
+              for (int k = 0; k < 64; ++k)
+                wp[(row0 + c2) * 64 + k] = src[((size_t)ph * co + c2) * K + (size_t)(ty * 2 + tx) * cin_total + cb * 64 + k];
+          }
+      }
+      __half* d_wp = nullptr;
+      if ((r = upload(e, (void**)&d_wp, wp.data(), wp.size() * 2))) return r;
+      const int rows = 16 * cbs * 64;
+      if ((r = make_tmap_w(e, &p.tmB, d_wp, rows, 64, 64))) return r;
+      if ((r = make_tmap_w(e, &p.tmA1, d_wp, rows, 64, 128))) return r;
+      if ((r = make_tmap_w(e, &p.tmPool, d_wp, rows, 64, 256))) return r;
+    }
+    Op op4;
+    op4.name = std::string(cs.name) + "[4ph]";
+    op4.flops_per_tile = 2.0 * 4.0 * L.H * L.W * co * K;
+    const int box_n4 = L.box_n, per_img4 = p.tiles_x * p.tiles_y, nsm4 = e->num_sms;
+    op4.run = [p, box_n4, per_img4, nsm4](int B, cudaStream_t s) mutable -> int {
+      p.B = B;
+      p.m_tiles = per_img4 * ((B + box_n4 - 1) / box_n4);
+      static bool attr_done = false;
+      if (!attr_done) {
+        SD_CUDA_CHECK(cudaFuncSetAttribute(conv_up4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Up4Cfg::kSmemBytes));
+        attr_done = true;
+      }
+      conv_up4_kernel<<<p.m_tiles < nsm4 ? p.m_tiles : nsm4, kConvThreads, Up4Cfg::kSmemBytes, s>>>(p);
+      SD_LAUNCH_CHECK("conv_up4_kernel");
+      return SD_OK;
+    };
+    e->ops.push_back(op4);
+    return SD_OK;
+  }
   Op op;
   op.name = std::string(cs.name) + (p.pool ? "+pool" : "");
   const int epi = cs.epi;
@@ -685,6 +732,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* m2 = getenv("SD_MT2")) e->mt2_max_bn = atoi(m2);
   if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
   if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
+  if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
   if (e->row_mode < 2) e->fuse_pool = 0;            // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
