@@ -134,37 +134,26 @@ __global__ void __launch_bounds__(96) tile_extract_u8_kernel(
 // overlap, by tile i-1; the output is the max (OR) of the covering tiles.
 // A thread produces 16 aligned output bytes of one row with one 128-bit store.
 // ---------------------------------------------------------------------------
-// 16 consecutive source bytes starting at (possibly unaligned, possibly
-// negative) element offset `e` of a tile buffer with `n_elems` elements.
-__device__ __forceinline__ void load16_u8(const uint8_t* __restrict__ base, int64_t e, int64_t n_elems,
-                                          uint32_t out[4]) {
-  const int64_t w0 = e >> 2;                      // floor (e may be negative)
-  const int sh = (int)(e & 3) * 8;
-  const int64_t wmax = (n_elems >> 2) - 1;
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(base);
+// 16 consecutive source elements of one tile row, starting at element offset `off` of the row (may be negative
+// or run past the row: those positions are masked by the caller, so word indices are simply clamped to the row).
+__device__ __forceinline__ void load16_u8(const uint32_t* __restrict__ row_words, int off, int row_words_n, uint32_t out[4]) {
+  const int w0 = off >> 2;                        // floor
+  const int sh = (off & 3) * 8;
   uint32_t w[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int64_t wi = w0 + k;                    // words outside the buffer are masked by the caller
-    w[k] = (wi >= 0 && wi <= wmax) ? __ldg(wp + wi) : 0u;
-  }
+  for (int k = 0; k < 5; ++k) w[k] = __ldg(row_words + min(max(w0 + k, 0), row_words_n - 1));
 #pragma unroll
   for (int k = 0; k < 4; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
 }
 
 // 16 consecutive fp16 probabilities -> 16 bytes of 0xFF/0x00 by `> thr`.
-__device__ __forceinline__ void load16_f16_thr(const __half* __restrict__ base, int64_t e, int64_t n_elems,
-                                               float thr, uint32_t out[4]) {
-  const int64_t w0 = e >> 1;
-  const int sh = (int)(e & 1) * 16;
-  const int64_t wmax = (n_elems >> 1) - 1;
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(base);
+__device__ __forceinline__ void load16_f16_thr(const uint32_t* __restrict__ row_words, int off, int row_words_n, float thr,
+                                               uint32_t out[4]) {
+  const int w0 = off >> 1;
+  const int sh = (off & 1) * 16;
   uint32_t w[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int64_t wi = w0 + k;
-    w[k] = (wi >= 0 && wi <= wmax) ? __ldg(wp + wi) : 0u;
-  }
+  for (int k = 0; k < 9; ++k) w[k] = __ldg(row_words + min(max(w0 + k, 0), row_words_n - 1));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     uint32_t acc = 0;
@@ -220,19 +209,27 @@ __global__ void __launch_bounds__(64) glue_kernel(
         const int lo = max(0, start - x0), hi = min(min(16, start + wd - x0), ln.width - x0);
         if (lo >= hi) continue;
         const uint32_t m0 = range_mask(0, lo, hi), m1 = range_mask(1, lo, hi), m2 = range_mask(2, lo, hi), m3 = range_mask(3, lo, hi);
-        const int64_t e0 = ((int64_t)(ln.first_tile + i) * SD_TILE_H + r0) * ln.tile_w + (x0 - start);
+        // tile rows are tile_w elements = a whole number of 32-bit words, 4-byte aligned
+        const int wpr = kProb ? ln.tile_w >> 1 : ln.tile_w >> 2;
+        const uint32_t* row0 = reinterpret_cast<const uint32_t*>(tiles) + ((int64_t)(ln.first_tile + i) * SD_TILE_H + r0) * wpr;
+        const int off = x0 - start;
         uint32_t v[kGlueRows][4];
 #pragma unroll
         for (int r = 0; r < kGlueRows; ++r) {
-          if (kProb) load16_f16_thr(reinterpret_cast<const __half*>(tiles), e0 + (int64_t)r * ln.tile_w, tile_elems_total, thr, v[r]);
-          else load16_u8(reinterpret_cast<const uint8_t*>(tiles), e0 + (int64_t)r * ln.tile_w, tile_elems_total, v[r]);
+          if (kProb) load16_f16_thr(row0 + r * wpr, off, wpr, thr, v[r]);
+          else load16_u8(row0 + r * wpr, off, wpr, v[r]);
         }
+        if (t == 0) {                                 // first covering tile: max(0, v) == v
 #pragma unroll
-        for (int r = 0; r < kGlueRows; ++r) {
-          acc[r][0] = kProb ? (acc[r][0] | (v[r][0] & m0)) : __vmaxu4(acc[r][0], v[r][0] & m0);
-          acc[r][1] = kProb ? (acc[r][1] | (v[r][1] & m1)) : __vmaxu4(acc[r][1], v[r][1] & m1);
-          acc[r][2] = kProb ? (acc[r][2] | (v[r][2] & m2)) : __vmaxu4(acc[r][2], v[r][2] & m2);
-          acc[r][3] = kProb ? (acc[r][3] | (v[r][3] & m3)) : __vmaxu4(acc[r][3], v[r][3] & m3);
+          for (int r = 0; r < kGlueRows; ++r) { acc[r][0] = v[r][0] & m0; acc[r][1] = v[r][1] & m1; acc[r][2] = v[r][2] & m2; acc[r][3] = v[r][3] & m3; }
+        } else {
+#pragma unroll
+          for (int r = 0; r < kGlueRows; ++r) {
+            acc[r][0] = kProb ? (acc[r][0] | (v[r][0] & m0)) : __vmaxu4(acc[r][0], v[r][0] & m0);
+            acc[r][1] = kProb ? (acc[r][1] | (v[r][1] & m1)) : __vmaxu4(acc[r][1], v[r][1] & m1);
+            acc[r][2] = kProb ? (acc[r][2] | (v[r][2] & m2)) : __vmaxu4(acc[r][2], v[r][2] & m2);
+            acc[r][3] = kProb ? (acc[r][3] | (v[r][3] & m3)) : __vmaxu4(acc[r][3], v[r][3] & m3);
+          }
         }
       }
     }
