@@ -113,3 +113,21 @@ def test_binarize_images_vs_reference_golden(cuda_device, parity_state, golden_a
         assert np.array_equal(step, out)
     finally:
         ort.close()
+
+
+def test_batch_invariance(cuda_device, parity_state):
+    """Tiles are independent images: a tile's probabilities must not depend on what else is in the batch or on
+    its position in it (catches cross-tile leaks in the persistent kernels: accumulator rings, pooled row pairs,
+    phantom M tiles of odd groups).  Bit-exact, because every tile is reduced in the same order."""
+    e = UNetEngine(parity_state, device=0, max_tiles=7, impl=0)
+    try:
+        x = _tiles(7, seed=11)
+        xt = UNetEngine.pack_input(torch.from_numpy(x).cuda())
+        full = e.forward(xt, want_prob32=True, want_mask=True)
+        p_full, m_full = full["prob32"].cpu().numpy(), full["mask"].cpu().numpy()
+        for idx in ([0], [6], [3, 1], [2, 4, 5], [6, 5, 4, 3, 2]):
+            sub = e.forward(xt[idx].contiguous(), want_prob32=True, want_mask=True)
+            assert np.array_equal(sub["prob32"].cpu().numpy(), p_full[idx]), idx
+            assert np.array_equal(sub["mask"].cpu().numpy(), m_full[idx]), idx
+    finally:
+        e.close()
