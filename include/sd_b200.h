@@ -206,6 +206,9 @@ const char* sd_engine_layer_name(sd_engine* e, int i);
  * code (1 producer<-empty slot, 2 MMA<-TMEM stage, 3 MMA<-full slot, 4 epilogue<-accumulator, 5 weights),
  * summed over the calling threads since the last reset; zeros in a normal build. */
 int sd_debug_wait_cycles(unsigned long long* h_out8, int reset);
+/* Code of the bounded mbarrier wait that timed out in a tcgen05 conv kernel (0 = none); readable even after the
+ * trapped kernel has poisoned the CUDA context. */
+int sd_engine_wait_error(sd_engine* e);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ EXPORTS = {
     "sd_engine_layer_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "sd_engine_layer_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "sd_debug_wait_cycles": (C.c_int, [C.c_void_p, C.c_int]),
+    "sd_engine_wait_error": (C.c_int, [C.c_void_p]),
 }
 
 

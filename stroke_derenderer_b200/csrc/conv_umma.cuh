@@ -89,8 +89,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 #ifdef SD_CONV_STATS
   const long long t0 = clock64();
 #endif
+  // the bound depends on the role so that, when a pipeline deadlocks, the wait closest to the cause reports:
+  // MMA<-full (3) first, then producer<-empty (1), MMA<-epilogue (2), epilogue<-MMA (4)
+  const int role = code % 10;
+  const uint32_t bound = role == 3 ? 20000000u : (role == 1 ? 30000000u : (role == 2 ? 40000000u : 50000000u));
 #pragma unroll 1
-  for (uint32_t it = 0; it < 40000000u; ++it) {
+  for (uint32_t it = 0; it < bound; ++it) {
     if (mbar_try_wait(bar, parity)) {
 #ifdef SD_CONV_STATS
       atomicAdd(&g_wait_cycles[code & 7], (unsigned long long)(clock64() - t0));
@@ -504,6 +508,269 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_umma2_kernel: the store-epilogue conv for Cout % 256 == 0 on a PAIR of SMs (thread-block cluster of 2,
+// tcgen05.mma.cta_group::2): one 256 x 256 tile per pair.  Each CTA stages its own 128-pixel A tile and HALF of
+// the 256-row B k-block (the tensor cores of both SMs read both halves), so a pipeline stage is 32 KB instead of
+// 48 KB and six stages fit instead of four: the same shared memory now covers 50 % more TMA latency, which is
+// what starves the single-CTA kernel (its MMA warp waits on `full` barriers 25-30 % of the time).
+//   * both CTAs' TMA loads signal the LEADER's (even CTA's) full barrier (.cta_group::2 form, peer bit cleared);
+//   * only the leader issues MMAs; tcgen05.commit multicasts the slot-free / accumulator-full signals to both;
+//   * each CTA's epilogue drains its own 128 accumulator lanes and arrives on the leader's TMEM-empty barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even CTA of the pair
+
+struct Conv2Cfg {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = 128 * 128;             // this CTA's half of the 256-row B k-block
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = 128 * 64 * 2 + 4096;
+  static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;   // 6
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kMiscBytes;
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = 256
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the even CTA's barrier from either CTA
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) conv_umma2_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = Conv2Cfg;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t out_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* misc = smem_al + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes;
+  const uint32_t bar_base = out_base + Cfg::kOutBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
+  float* s_bias = reinterpret_cast<float*>(misc + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();              // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    if (p.c1_blocks) tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < p.n_phases; ++i) tma_prefetch_desc(&p.tmOut[i]);
+    if (p.pool) tma_prefetch_desc(&p.tmPool);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+#ifdef SD_CTA2_DEBUG
+  if (threadIdx.x == 0 && pair == 0 && p.err_flag) {
+    p.err_flag[2 + 4 * rank] = (int)smem_u32(smem_raw);
+    p.err_flag[3 + 4 * rank] = (int)full_bar(0);
+    p.err_flag[4 + 4 * rank] = (int)(full_bar(0) & kPeerBitMask);
+    uint32_t mapped;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(mapped) : "r"(full_bar(0)), "r"(0u));
+    p.err_flag[5 + 4 * rank] = (int)mapped;
+  }
+#endif
+  const int m_groups = (p.m_tiles + 1) / 2;             // an M group = the two tiles of a pair
+  const int n_work = m_groups * p.n_tiles * p.n_phases;
+  const int kb_per_tap = p.c0_blocks + p.c1_blocks;
+  const int num_kb = p.n_taps * kb_per_tap;
+  auto origin = [&](int mt, int& x0, int& y0, int& n0) {
+    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
+    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
+    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+  };
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = pair; w < n_work; w += n_pairs) {
+        const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
+        const int mg = rest % m_groups; const int ph = rest / m_groups;
+        int x0, y0, n0;
+        origin(mg * 2 + (int)rank, x0, y0, n0);
+        const int brow = ph * p.cout + nt * BN + (int)rank * 128;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int dx = p.dx[ph][tap], dy = p.dy[ph][tap];
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1 + 10 * (int)rank);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);    // both CTAs' bytes land on the leader's barrier
+            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+            const CUtensorMap* tm = cb < p.c0_blocks ? &p.tmA0 : &p.tmA1;
+            const int c = (cb < p.c0_blocks ? cb : cb - p.c0_blocks) * 64;
+            tma_load_4d_2sm(a_dst, tm, full_bar(stage), c, x0 + dx, y0 + dy, n0);
+            tma_load_2d_2sm(a_dst + Cfg::kABytes, &p.tmB, full_bar(stage), (tap * kb_per_tap + cb) * 64, brow);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = pair; w < n_work; w += n_pairs) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2 + 10 * (int)rank);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 3 + 10 * (int)rank);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, Cfg::kIdesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue (warps 2..5, both CTAs: own 128 accumulator lanes) =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int as = 0; uint32_t aphase = 0;
+    int cur_nt = -1;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
+      const int mg = rest % m_groups; const int ph = rest / m_groups;
+      if (nt != cur_nt) {
+        epi_bar();
+        for (int i = et; i < BN; i += 128) s_bias[i] = __ldg(p.bias + nt * BN + i);
+        cur_nt = nt;
+        epi_bar();
+      }
+      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4 + 10 * (int)rank);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      int x0, y0, n0;
+      origin(mg * 2 + (int)rank, x0, y0, n0);
+#pragma unroll 1
+      for (int hb = 0; hb < BN / 64; ++hb) {
+        if (et == 0) tma_store_wait_read();
+        epi_bar();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = hb * 2 + cc;
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          const uint32_t row_base = out_base + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = j4 * 8 + j * 2;
+              float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __half2 h = __floats2half2_rn(a, b);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t chunk = (uint32_t)(cc * 4 + j4);
+            const uint32_t addr = row_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        }
+        if (hb == BN / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive_leader(tempty_bar(as));       // 128 + 128 arrivals free the accumulator stage of the pair
+        }
+        fence_async_smem();
+        epi_bar();
+        if (et == 0) {
+          tma_store_4d(&p.tmOut[ph], out_base, nt * BN + hb * 64, x0, y0, n0);
+          tma_store_commit();
+        }
+        if (p.pool) {
+          const int pw = p.box_w >> 1, phh = p.box_h >> 1;
+          const uint32_t pool_base = out_base + 16384u;
+#pragma unroll
+          for (int task = et; task < 256; task += 128) {
+            const int pp = task >> 3, ch = task & 7;
+            const int px = pp % pw; const int r2 = pp / pw;
+            const int py = r2 % phh, pn = r2 / phh;
+            const int m00 = (pn * p.box_h + 2 * py) * p.box_w + 2 * px, m10 = m00 + p.box_w;
+            const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, m00, ch)), ld_shared_v4(sw128(out_base, m00 + 1, ch))),
+                                     hmax2_v4(ld_shared_v4(sw128(out_base, m10, ch)), ld_shared_v4(sw128(out_base, m10 + 1, ch))));
+            st_shared_v4(sw128(pool_base, pp, ch), v);
+          }
+          fence_async_smem();
+          epi_bar();
+          if (et == 0) {
+            tma_store_4d(&p.tmPool, pool_base, nt * BN + hb * 64, x0 >> 1, y0 >> 1, n0);
+            tma_store_commit();
+          }
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody exits while the peer may still signal its barriers / read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

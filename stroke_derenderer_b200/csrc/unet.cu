@@ -230,7 +230,8 @@ struct sd_engine {
   Act act[SD_NUM_TAPS];                // named taps
   Act c1a, p1, c2a, p2, c3a, p3, c4a, p4, c5a, u5a, u4a, u3a, u2a;
   float* qbuf = nullptr;               // debug impl: gate pre-activation, fp32
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;             // device alias of err_flag_host
+  int* err_flag_host = nullptr;        // pinned, mapped: still readable after a kernel trapped (barrier wait codes)
   std::vector<void*> allocs;
   std::vector<Op> ops;
   // per-call outputs (captured by the head op)
@@ -242,6 +243,7 @@ struct sd_engine {
   std::vector<float> last_ms;
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
+  int cta2 = 1;                        // Cout % 256 == 0 layers on SM pairs (cluster of 2, tcgen05 cta_group::2); SD_CTA2=0: one CTA per tile
   int up4 = 1;                         // Up2: four sub-pixel phases per work item (SD_UP4=0: generic kernel, phase by phase)
   int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
@@ -372,6 +374,21 @@ static int dispatch_row(const ConvParams& p, int cb, int epi, int grid, cudaStre
   if (cb == 1 && epi == EPI_HEAD) return launch_row<1, EPI_HEAD>(p, grid, s);
   set_error("dispatch_row: no kernel for CB=%d epilogue=%d", cb, epi);
   return SD_EINVAL;
+}
+
+// 2-SM variant (cluster of 2, cta_group::2) of the 256-wide store-epilogue conv
+static int launch_conv2(const ConvParams& p, int n_sms, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int n_work = ((p.m_tiles + 1) / 2) * p.n_tiles * p.n_phases;
+  int pairs = n_sms / 2;
+  if (n_work < pairs) pairs = n_work;
+  conv_umma2_kernel<<<2 * pairs, kConvThreads, Conv2Cfg::kSmemBytes, s>>>(p);
+  SD_LAUNCH_CHECK("conv_umma2_kernel");
+  return SD_OK;
 }
 
 static int dispatch_conv(const ConvParams& p, int bn, int mt, int epi, int grid, cudaStream_t s) {
@@ -602,13 +619,20 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   const int box_n = L.box_n, per_img = p.tiles_x * p.tiles_y;
   const int nsm = e->num_sms;
   op.flops_per_tile = 2.0 * (cs.up ? 4.0 : 1.0) * L.H * L.W * co * K;
-  op.run = [e, p, bn, mt, epi, box_n, per_img, nsm](int B, cudaStream_t s) mutable -> int {
+  const bool cta2 = e->cta2 && bn == 256 && epi == EPI_STORE;
+  if (cta2) {
+    op.name += "[2sm]";
+    // each CTA of a pair fetches its own 128-row half of the 256-row B k-block
+    if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], (cs.up ? 4 : 1) * co, K, 128))) return r;
+  }
+  op.run = [e, p, bn, mt, epi, box_n, per_img, nsm, cta2](int B, cudaStream_t s) mutable -> int {
     p.B = B;
     p.m_tiles = per_img * ((B + box_n - 1) / box_n);
     if (epi == EPI_HEAD) {
       p.head_b = e->head_b; p.thr = e->thr;
       p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
     }
+    if (cta2) return launch_conv2(p, nsm, s);
     const int n_work = ((p.m_tiles + mt - 1) / mt) * p.n_tiles * p.n_phases;
     const int grid = n_work < nsm ? n_work : nsm;
     return dispatch_conv(p, bn, mt, epi, grid, s);
@@ -686,6 +710,7 @@ extern "C" void sd_engine_destroy(sd_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (void* p : e->allocs) cudaFree(p);
+  if (e->err_flag_host) cudaFreeHost(e->err_flag_host);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   delete e;
 }
@@ -733,6 +758,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
   if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
   if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
+  if (const char* c2 = getenv("SD_CTA2")) e->cta2 = atoi(c2);
   if (e->row_mode < 2) e->fuse_pool = 0;            // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -747,9 +773,9 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   e->lv[3] = {H / 8, W / 8, 16, 8, 1};
   e->lv[4] = {H / 16, W / 16, 8, 8, 2};
   int r;
-  SD_CUDA_CHECK(cudaMalloc((void**)&e->err_flag, sizeof(int)));
-  e->allocs.push_back(e->err_flag);
-  SD_CUDA_CHECK(cudaMemset(e->err_flag, 0, sizeof(int)));
+  SD_CUDA_CHECK(cudaHostAlloc((void**)&e->err_flag_host, 16 * sizeof(int), cudaHostAllocMapped));
+  for (int i = 0; i < 16; ++i) e->err_flag_host[i] = 0;
+  SD_CUDA_CHECK(cudaHostGetDevicePointer((void**)&e->err_flag, e->err_flag_host, 0));
 
   // ---- weights ----
   for (int s = 0; s < SD_NUM_SLOTS; ++s) {
@@ -1008,7 +1034,7 @@ extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, f
     SD_CUDA_CHECK(cudaStreamSynchronize(s));
     for (size_t i = 0; i < e->ops.size(); ++i) SD_CUDA_CHECK(cudaEventElapsedTime(&e->last_ms[i], e->ev[i], e->ev[i + 1]));
     int flag = 0;
-    SD_CUDA_CHECK(cudaMemcpy(&flag, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    flag = *e->err_flag_host;
     SD_REQUIRE(flag == 0, "sd_unet_forward: kernel barrier timeout (code %d)", flag);
   }
   return SD_OK;
@@ -1060,3 +1086,8 @@ extern "C" int sd_debug_wait_cycles(unsigned long long* h_out8, int reset) {
 #endif
   return SD_OK;
 }
+
+// debug: code of the mbarrier wait that timed out (0 = none).  The flag lives in pinned host memory, so it can
+// be read after the trapped kernel has poisoned the CUDA context.
+extern "C" int sd_engine_wait_error(sd_engine* e) { return (e && e->err_flag_host) ? *e->err_flag_host : -1; }
+extern "C" int sd_engine_debug_word(sd_engine* e, int i) { return (e && e->err_flag_host && i >= 0 && i < 16) ? e->err_flag_host[i] : -1; }

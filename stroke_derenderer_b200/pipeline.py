@@ -9,6 +9,10 @@ The hot-path step of one rank:
 
 from __future__ import annotations
 
+import os
+import sys
+import time
+
 import numpy as np
 import torch
 
@@ -129,6 +133,8 @@ class LineSegmentationJob:
                         ready[glued] = ev
                         glued += 1
             results = []
+            dbg = os.environ.get("SD_PIPE_DEBUG")
+            t_dbg = [time.perf_counter()]
             with torch.cuda.stream(self.s_part):
                 for ch, ev in zip(self.chunks, ready):
                     self.s_part.wait_event(ev)
@@ -143,10 +149,15 @@ class LineSegmentationJob:
                         res["crops"]["image_host"] = hb.numpy().reshape(tuple(img.shape))
                         res["crops"]["input_host"] = None
                     results.append(res)
+                    t_dbg.append(time.perf_counter())
             cur.wait_stream(self.s_unet)
             cur.wait_stream(self.s_part)
             if from_host:
                 cur.synchronize()
+            if dbg:
+                t_dbg.append(time.perf_counter())
+                print("[pipe] enqueue->partitions done (ms):", [round(1e3 * (b - a), 1) for a, b in zip(t_dbg, t_dbg[1:])],
+                      file=sys.stderr, flush=True)
         return results
 
     def resident_step(self):
