@@ -15,6 +15,7 @@
 #include <vector>
 #include <algorithm>
 #include <limits.h>
+#include <cstdlib>
 
 namespace sd {
 
@@ -314,18 +315,20 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-// shared-memory union-find over run starts.  Parents only ever decrease (min-root), non-roots never
-// become roots again, and a compressing store writes an ancestor that is smaller than the value it
-// replaces, so the racing plain stores keep every tree valid; a union completes only when its
-// atomicMin hit a true root.
+// shared-memory union-find over run starts (min-root: parents are smaller than their children, a union
+// completes only when its atomicMin hit a true root).  NO path compression while unions are in flight: a
+// compressing plain store can race with the atomicMin of a union that targets the same node through a stale
+// root and silently drop that link (seen as a split component in ~25 % of runs on some strips).  Paths are
+// compressed afterwards, once every root is final (suf_find_flatten).
 __device__ __forceinline__ int suf_find(volatile int* p, int a) {
+  int q;
+  while ((q = p[a]) != a) a = q;
+  return a;
+}
+__device__ __forceinline__ int suf_find_flatten(volatile int* p, int a) {   // only after the union phase
   int r = a, q;
   while ((q = p[r]) != r) r = q;
-  while (a > r) {
-    q = p[a];
-    if (q > r) p[a] = r;
-    a = q;
-  }
+  while (a > r) { q = p[a]; p[a] = r; a = q; }
   return r;
 }
 __device__ __forceinline__ void suf_union(int* p, int a, int b) {
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(256) ccl_strip_label_kernel(
     }
     __syncthreads();
     // flatten: afterwards s_parent[run start] is the run's root
-    for (uint32_t t = rs2; t; t &= t - 1) suf_find(s_parent, base + ((__ffs(t) - 1) >> 1));
+    for (uint32_t t = rs2; t; t &= t - 1) suf_find_flatten(s_parent, base + ((__ffs(t) - 1) >> 1));
 
     // records: every block of a run carries the run's root
     uint32_t recw[8];
@@ -1118,6 +1121,7 @@ static int ccl_label_grid() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_strip_label_kernel, 256, 0);
     grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (const char* g = getenv("SD_CCL_GRID")) grid = atoi(g);      // debug: e.g. a huge value = one strip per CTA
   }
   return grid;
 }

@@ -254,3 +254,71 @@ def test_group_crops_bit_exact_vs_reference_calls(cuda_device):
         assert np.array_equal(img[g], ref_img), (g, c.shape)
         assert np.array_equal(inp[g], O.model_input_from_crop(ref_img, mean, std)), (g, c.shape)
         assert out["ratio"][g] == ratio and tuple(out["translate2"][g]) == t2
+
+
+def _properties_of_partition(batch, planes, res):
+    """Size-independent invariants of labelling + grouping, checked on the device for every line of a batch."""
+    labels = res["labels"]
+    mask = planes != 0
+    # 1. labels cover exactly the mask
+    assert bool(((labels > 0) == mask).all())
+    # 2. idempotence: labelling the labelled mask again gives the same labels (numbering is a function of the mask)
+    labels2, num2 = S.ccl_label(batch, (labels > 0).to(torch.uint8))
+    assert bool((labels2 == labels).all()) and np.array_equal(num2.cpu().numpy(), res["num"])
+    # 3. stats: areas sum to the mask, every label 1..n-1 is used, boxes lie inside the image
+    st, off = res["stats"], res["stat_off"]
+    assert int(st[:, 4].sum()) == int(mask.sum().item())
+    assert (st[:, 4] > 0).all() and (st[:, 0] >= 0).all() and (st[:, 1] >= 0).all() and (st[:, 1] + st[:, 3] <= 128).all()
+    for l in range(batch.n_lines):
+        assert (st[off[l]:off[l + 1], 0] + st[off[l]:off[l + 1], 2] <= batch.widths[l]).all()
+    assert np.array_equal(np.diff(off), res["num"].astype(np.int64) - 1)
+    # 4. every island belongs to exactly one group, and the group canvases hold exactly the ink of their members
+    assert (res["group_of"][:int(off[-1])] >= 0).all()
+    assert res["canvas"].max().item() <= 1
+    area_by_group = np.bincount(res["group_of"][:int(off[-1])], weights=st[:, 4], minlength=len(res["groups"])).astype(np.int64)
+    assert int(res["canvas"].sum(dtype=torch.int64).item()) == int(area_by_group.sum())
+    g = res["groups"]
+    canvas_h = None
+    for k in np.linspace(0, len(g) - 1, 64).astype(int):            # a spread of groups, canvas by canvas
+        _, left, top, right, bottom, o = (int(v) for v in g[k])
+        n_px = (right - left) * (bottom - top)
+        assert int(res["canvas"][o:o + n_px].sum(dtype=torch.int64).item()) == int(area_by_group[k]), k
+
+
+def test_full_size_config3_properties(cuda_device):
+    """BASELINE config 3 at full size (512 lines, 6 438 tiles worth of columns): the oracle takes minutes there, so
+    the device result is checked through invariants; two lines are also compared with cv2 bit for bit."""
+    import cv2
+    widths = config_widths(512)
+    masks = [ink_mask(synth_line(int(w), seed=i)) for i, w in enumerate(widths)]
+    batch, planes = _pack_masks(masks)
+    res = S.Segmenter(None, device=torch.device("cuda", 0)).partition(batch, planes, canvases="device")
+    _properties_of_partition(batch, planes, res)
+    for i in (0, 511):
+        n, ref = cv2.connectedComponents(masks[i])
+        assert int(res["num"][i]) == n and np.array_equal(batch.plane(res["labels"], i).cpu().numpy(), ref)
+
+
+def test_full_size_config5_properties(cuda_device):
+    """BASELINE config 5: 64 dense 128x16384 masks in one launch (~800 k islands)."""
+    masks = [synth_dense_mask(16384, 0.003 if i % 2 == 0 else 0.01, seed=i) for i in range(64)]
+    batch, planes = _pack_masks(masks)
+    res = S.Segmenter(None, device=torch.device("cuda", 0)).partition(batch, planes, canvases="device")
+    _properties_of_partition(batch, planes, res)
+
+
+def test_ccl_union_race_regression(cuda_device):
+    """A looped stroke whose two branches merge across a thread-word boundary: with path compression running
+    concurrently with the unions this strip lost a link in ~25 % of launches (one component became two).  2 000
+    copies in one launch make a rare race visible."""
+    import cv2
+    line = ink_mask(synth_line(int(config_widths(512)[127]), seed=127))
+    strip = np.ascontiguousarray(line[:, 2560:2688])
+    n_ref, ref = cv2.connectedComponents(strip)
+    assert n_ref == 6                                  # the synthetic strip this test was written for
+    batch, planes = _pack_masks([strip] * 2000)
+    for _ in range(3):
+        labels, num = S.ccl_label(batch, planes)
+        assert bool((num == n_ref).all()), int((num != n_ref).sum().item())
+        got = labels.view(2000, 128, 128)
+        assert bool((got == torch.from_numpy(ref).to(got.device).to(torch.int32)[None]).all())
