@@ -131,3 +131,51 @@ def test_batch_invariance(cuda_device, parity_state):
             assert np.array_equal(sub["mask"].cpu().numpy(), m_full[idx]), idx
     finally:
         e.close()
+
+
+def test_repeatability_under_load(cuda_device, parity_state):
+    """The same batch through the engine 12 times, back to back (persistent kernels, mbarrier pipelines, TMEM
+    rings, cluster pairs): every run must reproduce the first bit for bit."""
+    e = UNetEngine(parity_state, device=0, max_tiles=48, impl=0)
+    try:
+        rng = np.random.default_rng(3)
+        x = torch.from_numpy(rng.random((48, 128, 384, 8), dtype=np.float32)).cuda().half()
+        x[..., 3:] = 0
+        first = e.forward(x, want_prob32=True, want_mask=True)
+        p0, m0 = first["prob32"].clone(), first["mask"].clone()
+        for _ in range(12):
+            out = e.forward(x, want_prob32=True, want_mask=True)
+            assert bool((out["prob32"] == p0).all()) and bool((out["mask"] == m0).all())
+    finally:
+        e.close()
+
+
+def test_pipeline_job_equals_direct_segmentation(cuda_device, parity_state):
+    """LineSegmentationJob (chunks, three streams, UNet batches that cross chunk boundaries, pinned D2H) returns
+    exactly what one direct Segmenter pass over the same lines returns."""
+    from stroke_derenderer_b200.pipeline import LineSegmentationJob
+    from stroke_derenderer_b200.segment import Segmenter
+    widths = [700, 1536, 333, 2048, 4000, 384, 1000, 3072, 640, 2222, 1234]
+    lines = [synth_line(w, seed=50 + i) for i, w in enumerate(widths)]
+    e = UNetEngine(parity_state, device=0, max_tiles=16, impl=0)
+    try:
+        ref = Segmenter(e).segment(lines)
+        ref_parts = Segmenter(e).partition(ref["batch"], ref["planes"], canvases="device", crops=True)
+        job = LineSegmentationJob(e, lines, lines_per_chunk=4)
+        for results in (job.resident_step(), job.host_step()):
+            torch.cuda.synchronize()
+            li = 0
+            for ch, res in zip(job.chunks, results):
+                for k in range(ch.batch.n_lines):
+                    assert torch.equal(ch.batch.plane(ch.planes, k), ref["batch"].plane(ref["planes"], li)), li
+                    assert torch.equal(ch.batch.plane(res["labels"], k), ref["batch"].plane(ref["labels"], li)), li
+                    a, b = int(res["line_group_start"][k]), int(res["line_group_start"][k + 1])
+                    ra, rb = int(ref_parts["line_group_start"][li]), int(ref_parts["line_group_start"][li + 1])
+                    assert b - a == rb - ra and np.array_equal(res["groups"][a:b, 1:5], ref_parts["groups"][ra:rb, 1:5]), li
+                    assert torch.equal(res["crops"]["image"][a:b], ref_parts["crops"]["image"][ra:rb]), li
+                    if "image_host" in res["crops"]:
+                        assert np.array_equal(res["crops"]["image_host"][a:b], ref_parts["crops"]["image"][ra:rb].cpu().numpy()), li
+                    li += 1
+            assert li == len(lines)
+    finally:
+        e.close()
