@@ -775,211 +775,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv_row_kernel<CB, EPI>: 3x3 conv, Cin = CB*64 -> Cout = 64, on a full-resolution level whose
-// width is a multiple of 128 (level 1: 128 x 384).  These layers are L2->SM bandwidth bound in the
-// generic kernel (N = 64 re-uses each 16 KB A box for only 64 outputs, ~190 B/cycle/SM wanted vs
-// ~40 available).  Here
-//   * ALL weights (9 taps x CB x 8 KB) are loaded once per CTA and stay in shared memory;
-//   * an M tile is one output row segment of 128 pixels; for each dy ONE halo row segment of
-//     130 pixels x 64 channels (16.6 KB) is fetched and serves the three dx taps through UMMA
-//     descriptors whose start address is shifted by dx rows (128 B) inside the swizzled buffer.
-// L2->SM traffic per tile drops from 216*CB KB to 50*CB KB.
+// Level-1 halo rows: one A stage of the band kernel is a row segment of 130 pixels x 64 channels (the 128 output
+// pixels plus one halo pixel on each side), fetched by one 4-D TMA box; the three dx taps read it through UMMA
+// descriptors whose start address is shifted by dx rows (128 B) inside the swizzled buffer.  Measured on B200: the
+// 128-B swizzle is applied on absolute shared-memory address bits, so a start that is not 1024-B aligned needs no
+// correction (setting base_offset = (addr >> 7) & 7 gives wrong results).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowStageBytes = 17 * 1024;     // 130 rows x 128 B = 16640, padded to keep 1024-B alignment
 constexpr int kRowBoxBytes = 130 * 128;
 
-template <int CB, int EPI> struct RowCfg {
-  static constexpr int kWBytes = 9 * CB * 8192;
-  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 16384 : 0;
-  static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kWBytes - kOutBytes) / kRowStageBytes;
-  static constexpr int kStages = kFit > 8 ? 8 : kFit;
-  static constexpr int kSmemBytes = kStages * kRowStageBytes + kWBytes + kOutBytes + 1024 + kMiscBytes;
-  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
-  static_assert(kStages >= 3, "pipeline too shallow");
-};
-
-// Row-shifted operand: start address = buffer + dx * 128 B, base_offset field left 0.  Measured on B200:
-// the 128-B swizzle is applied on absolute shared-memory address bits, so a start that is not 1024-B
-// aligned needs no correction (setting base_offset = (addr >> 7) & 7 gives wrong results).
-
-template <int CB, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = RowCfg<CB, EPI>;
-  constexpr int BN = 64;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t w_base = smem_base + Cfg::kStages * kRowStageBytes;                 // resident weights
-  const uint32_t out_base = w_base + Cfg::kWBytes;
-  uint8_t* misc = smem_al + Cfg::kStages * kRowStageBytes + Cfg::kWBytes + Cfg::kOutBytes;
-  const uint32_t bar_base = out_base + Cfg::kOutBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
-  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::kStages + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
-  float* s_bias = reinterpret_cast<float*>(misc + 256);
-  float* s_vec = reinterpret_cast<float*>(misc + 1280);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA0);
-    if (CB > 1) tma_prefetch_desc(&p.tmA1);
-    tma_prefetch_desc(&p.tmB);
-    if (EPI == EPI_STORE) tma_prefetch_desc(&p.tmOut[0]);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
-    mbar_init(w_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(128u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    if (t < BN) { s_bias[t] = p.bias[t]; if (EPI == EPI_HEAD) s_vec[t] = p.head_w[t]; }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int segs = p.W / 128;
-  const int n_work = p.B * p.H * segs;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // one-time: all weights -> smem (k-block index = tap * CB + cb, 64 rows x 128 B each, swizzled)
-      mbar_expect_tx(w_bar, Cfg::kWBytes);
-      for (int kb = 0; kb < 9 * CB; ++kb) tma_load_2d(w_base + kb * 8192, &p.tmB, w_bar, kb * 64, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sx = w % segs; const int rest = w / segs;
-        const int y = rest % p.H, n = rest / p.H;
-        for (int dy = 0; dy < 3; ++dy) {
-          for (int cb = 0; cb < CB; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
-            mbar_expect_tx(full_bar(stage), kRowBoxBytes);
-            tma_load_4d(smem_base + stage * kRowStageBytes, cb == 0 ? &p.tmA0 : &p.tmA1, full_bar(stage),
-                        0, sx * 128 - 1, y + dy - 1, n);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(w_bar, 0, p.err_flag, 5);
-      tc_fence_after();
-      int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u, p.err_flag, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int dy = 0; dy < 3; ++dy) {
-          for (int cb = 0; cb < CB; ++cb) {
-            mbar_wait(full_bar(stage), phase, p.err_flag, 3);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + stage * kRowStageBytes;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const uint64_t adesc = umma_desc_sw128(a_addr + dx * 128);
-              const uint64_t bdesc = umma_desc_sw128(w_base + ((dy * 3 + dx) * CB + cb) * 8192);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, Cfg::kIdesc, (uint32_t)((dy | cb | dx | k) != 0));
-            }
-            umma_commit(empty_bar(stage));
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-        umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
-      }
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    int as = 0; uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int sx = w % segs; const int rest = w / segs;
-      const int y = rest % p.H, n = rest / p.H;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
-      tc_fence_after();
-      if constexpr (EPI == EPI_STORE) {
-        if (et == 0) tma_store_wait_read();
-        epi_bar();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          const uint32_t rbase = out_base + (uint32_t)row * 128u;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = j4 * 8 + j * 2;
-              float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
-              __half2 h = __floats2half2_rn(a, b);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            const uint32_t chunk = (uint32_t)(c * 4 + j4);
-            const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(as));
-        fence_async_smem();
-        epi_bar();
-        if (et == 0) { tma_store_4d(&p.tmOut[0], out_base, 0, sx * 128, y, n); tma_store_commit(); }
-      } else {
-        float dot = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = fmaxf(v[j] + s_bias[c * 32 + j], 0.f);
-            a = __half2float(__float2half_rn(a));
-            dot = fmaf(a, s_vec[c * 32 + j], dot);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(as));
-        const float pr = 1.f / (1.f + expf(-(dot + p.head_b)));
-        const int64_t pix = ((int64_t)n * p.H + y) * p.W + sx * 128 + row;
-        if (p.prob_f32) p.prob_f32[pix] = pr;
-        if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
-        if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
-      }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
-    }
-    if (EPI == EPI_STORE && et == 0) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// conv_band_kernel<CB, EPI>: the same level-1 layers (3x3, Cin = CB*64 -> Cout = 64, W % 128 == 0), dy-stacked.
+// conv_band_kernel<CB, EPI>: the level-1 layers with 3x3 taps, Cin = CB*64 -> Cout = 64, W % 128 == 0, dy-stacked.
 // An N = 64 MMA reads 4 KB of A + 2 KB of B from shared memory for 32 tensor cycles (192 B/clk against the
 // 128 B/clk the shared memory delivers) and each input row is fetched three times.  Here ONE input halo row
 // (130 px x 64 ch, fetched once) feeds the three output rows it contributes to in a single N = 192 MMA per

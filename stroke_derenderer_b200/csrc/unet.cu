@@ -249,7 +249,7 @@ struct sd_engine {
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
   int mt2_max_bn = 128;                // SD_MT2=128: 2 x (128 x BN) tiles per work item for BN <= 128 (0 = off)
   int bn_max = 256;                    // widest N tile of the generic conv kernel (SD_BNMAX=256 to try 128x256 tiles)
-  int row_mode = 2;                    // level-1 64-channel 3x3 layers: 2 conv_band_kernel, 1 conv_row_kernel, 0 generic kernel (SD_ROWCONV)
+  int band = 1;                        // level-1 64-channel 3x3 layers on conv_band_kernel (SD_BAND=0: generic kernel)
 };
 
 namespace sd {
@@ -335,19 +335,6 @@ static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
 }
 
 template <int CB, int EPI>
-static int launch_row(const ConvParams& p, int grid, cudaStream_t s) {
-  using Cfg = RowCfg<CB, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_row_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
-  conv_row_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
-  SD_LAUNCH_CHECK("conv_row_kernel");
-  return SD_OK;
-}
-
-template <int CB, int EPI>
 static int launch_band(const ConvParams& p, int grid, cudaStream_t s) {
   using Cfg = BandCfg<CB, EPI>;
   static bool attr_done = false;
@@ -365,14 +352,6 @@ static int dispatch_band(const ConvParams& p, int cb, int epi, int grid, cudaStr
   if (cb == 2 && epi == EPI_STORE) return launch_band<2, EPI_STORE>(p, grid, s);
   if (cb == 1 && epi == EPI_HEAD) return launch_band<1, EPI_HEAD>(p, grid, s);
   set_error("dispatch_band: no kernel for CB=%d epilogue=%d", cb, epi);
-  return SD_EINVAL;
-}
-
-static int dispatch_row(const ConvParams& p, int cb, int epi, int grid, cudaStream_t s) {
-  if (cb == 1 && epi == EPI_STORE) return launch_row<1, EPI_STORE>(p, grid, s);
-  if (cb == 2 && epi == EPI_STORE) return launch_row<2, EPI_STORE>(p, grid, s);
-  if (cb == 1 && epi == EPI_HEAD) return launch_row<1, EPI_HEAD>(p, grid, s);
-  set_error("dispatch_row: no kernel for CB=%d epilogue=%d", cb, epi);
   return SD_EINVAL;
 }
 
@@ -476,10 +455,11 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   SD_REQUIRE(lvl >= 0, "add_umma_conv(%s): unknown level", cs.name);
   const Level& L = e->lv[lvl];
   int r;
-  const bool row_ok = e->row_mode > 0 && lvl == 0 && L.W % 128 == 0 && co == 64 && !cs.up && e->ks[slot] == 3 &&
-                      cs.in0->C == 64 && (!cs.in1 || cs.in1->C == 64) && (cs.epi == EPI_STORE || cs.epi == EPI_HEAD) &&
-                      !(cs.in1 && cs.epi == EPI_HEAD) && !(cs.pool_out && e->row_mode < 2);
-  if (row_ok) {
+  // level-1 3x3 layers with 64 output channels: dy-stacked band kernel
+  const bool band_ok = e->band && lvl == 0 && L.W % 128 == 0 && co == 64 && !cs.up && e->ks[slot] == 3 &&
+                       cs.in0->C == 64 && (!cs.in1 || cs.in1->C == 64) && (cs.epi == EPI_STORE || cs.epi == EPI_HEAD) &&
+                       !(cs.in1 && cs.epi == EPI_HEAD);
+  if (band_ok) {
     const int cb = cs.in1 ? 2 : 1;
     Level halo = L; halo.box_w = 130; halo.box_h = 1; halo.box_n = 1;
     if ((r = make_tmap_act(e, &p.tmA0, *cs.in0, halo))) return r;
@@ -492,7 +472,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.out = cs.out->p; p.out_c = cs.out->C;
       if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
       if (cs.pool_out) {
-        SD_REQUIRE(e->row_mode >= 2 && !cs.in1, "add_umma_conv(%s): fused pool needs the band kernel with one source", cs.name);
+        SD_REQUIRE(!cs.in1, "add_umma_conv(%s): fused pool needs a single source", cs.name);
         if ((r = make_tmap_pool(e, &p.tmPool, *cs.pool_out, 64, 1, 1))) return r;
         p.pool = 1;
       }
@@ -500,22 +480,17 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.head_w = e->w_f32[SD_HEAD];
     }
     Op op;
-    const int band = e->row_mode >= 2;
-    op.name = std::string(cs.name) + (band ? "[band]" : "[row]") + (p.pool ? "+pool" : "");
+    op.name = std::string(cs.name) + "[band]" + (p.pool ? "+pool" : "");
     const int epi = cs.epi, nsm = e->num_sms, segs = L.W / 128, H = L.H;
     op.flops_per_tile = 2.0 * L.H * L.W * co * 9 * cin_total;
-    op.run = [e, p, cb, epi, nsm, segs, H, band](int B, cudaStream_t s) mutable -> int {
+    op.run = [e, p, cb, epi, nsm, segs, H](int B, cudaStream_t s) mutable -> int {
       p.B = B;
       if (epi == EPI_HEAD) {
         p.head_b = e->head_b; p.thr = e->thr;
         p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
       }
-      if (band) {
-        const int n_work = B * ((H + kBandRows - 1) / kBandRows) * segs;
-        return dispatch_band(p, cb, epi, n_work < nsm ? n_work : nsm, s);
-      }
-      const int n_work = B * H * segs;
-      return dispatch_row(p, cb, epi, n_work < nsm ? n_work : nsm, s);
+      const int n_work = B * ((H + kBandRows - 1) / kBandRows) * segs;
+      return dispatch_band(p, cb, epi, n_work < nsm ? n_work : nsm, s);
     };
     e->ops.push_back(op);
     return SD_OK;
@@ -752,14 +727,14 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
                exp_shape[s][0], exp_shape[s][1], exp_shape[s][2]);
   }
   e->impl = impl;
-  if (const char* rm = getenv("SD_ROWCONV")) e->row_mode = atoi(rm);
+  if (const char* rm = getenv("SD_BAND")) e->band = atoi(rm);
   if (const char* bm = getenv("SD_BNMAX")) e->bn_max = atoi(bm);
   if (const char* m2 = getenv("SD_MT2")) e->mt2_max_bn = atoi(m2);
   if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
   if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
   if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
   if (const char* c2 = getenv("SD_CTA2")) e->cta2 = atoi(c2);
-  if (e->row_mode < 2) e->fuse_pool = 0;            // the level-1 pool is fused in the band kernel only
+  if (!e->band) e->fuse_pool = 0;                   // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
