@@ -323,6 +323,21 @@ def run_gpu(args):
             "glue_u8": {"ms": t_glue, "GBps": b_glue / t_glue / 1e6, "frac": b_glue / t_glue / 1e6 / hb},
             "ccl_label": {"ms": t_ccl, "GBps": b_ccl / t_ccl / 1e6, "frac": b_ccl / t_ccl / 1e6 / hb},
             "peak_GBps": hb}
+        # BASELINE config 5 (CCL / clustering-bound stress): 64 dense 128x16384 masks (~800 k islands) in one launch
+        from stroke_derenderer_b200.synth import synth_dense_mask
+        n5 = 64
+        b5 = S.plan_batch([16384] * n5, torch.device("cuda", local))
+        h5 = np.zeros(b5.px_total, np.uint8)
+        for i in range(n5):
+            ln = b5.lines[i]
+            h5[int(ln["px_off"]):int(ln["px_off"]) + 128 * int(ln["pitch"])] = (synth_dense_mask(16384, 0.003 if i % 2 == 0 else 0.01, seed=i) * 255).reshape(-1)
+        p5 = torch.from_numpy(h5).to(torch.device("cuda", local))
+        w5 = torch.empty(_lib.lib().sd_ccl_workspace_bytes(b5.blk_total, b5.n_lines), dtype=torch.uint8, device="cuda")
+        t5 = ev_time(lambda: S.ccl_label(b5, p5, w5))
+        px5 = 128 * 16384 * n5
+        extra["hbm_stages"]["ccl_label_config5"] = {"ms": t5, "GBps": 5 * px5 / t5 / 1e6, "frac": 5 * px5 / t5 / 1e6 / hb,
+                                                    "sample": f"{n5} dense lines 128x16384, {px5} px"}
+        del p5, w5
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
