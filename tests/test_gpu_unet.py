@@ -179,3 +179,40 @@ def test_pipeline_job_equals_direct_segmentation(cuda_device, parity_state):
             assert li == len(lines)
     finally:
         e.close()
+
+
+def test_main_cli_dropin(cuda_device, parity_state, tmp_path):
+    """B1 boundary: the root main.py (initialize_sessions / load_images / main) with a `binarizer.onnx` read by the
+    dependency-free reader, PNG input, `_BINARIZED.png` + `_PARTITIONS.json` output."""
+    import json
+    import sys
+    import cv2
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root))
+    import main as cli
+    from onnx_writer import write_onnx as _write_onnx
+    models, inp, out = tmp_path / "models", tmp_path / "in", tmp_path / "out"
+    models.mkdir(); inp.mkdir()
+    _write_onnx(models / "binarizer.onnx", parity_state, folded=True)
+    (models / "configs_binarizer.json").write_text(json.dumps({"bin_thr": 0.5, "minibatch": 8}))
+    lines = {"a": synth_line(900, 21), "b": synth_line(400, 22)}
+    for stem, img in lines.items():
+        cv2.imwrite(str(inp / f"{stem}.png"), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    args = cli.parse_args(["-models", str(models), "-input", str(inp), "--output", str(out)])
+    sessions = cli.initialize_sessions(args.models)
+    try:
+        imgs = cli.load_images(sorted(str(p) for p in Path(args.input).glob("*.png")))
+        cli.main(imgs, *sessions, args.output, strokes=True)
+        for stem, img in lines.items():
+            png = cv2.imread(str(out / f"{stem}_BINARIZED.png"), cv2.IMREAD_GRAYSCALE)
+            assert png is not None and png.shape == (128, img.shape[1]) and set(np.unique(png)) <= {0, 255}
+            direct = sessions[0].binarize_image(img, sessions[1])[:, :, 0]
+            assert np.array_equal(png, direct)
+            parts = json.loads((out / f"{stem}_PARTITIONS.json").read_text())
+            want = sessions[2].get_partitions(direct > 127)
+            assert len(parts) == len(want)
+            for p, w in zip(parts, want):
+                assert p["translate1"] == [int(w["translate1"][0]), int(w["translate1"][1])] and p["ratio"] == float(w["ratio"])
+    finally:
+        sessions[1].close()
