@@ -31,6 +31,7 @@ struct ConvParams {
   CUtensorMap tmOut[4];        // store epilogue: one output map per sub-pixel phase
   CUtensorMap tmPool;          // store epilogue with pool != 0: the 2x2 max-pooled copy of the output
   int pool;
+  int gate_tma;                // gate epilogue: skip tensor through shared memory (TMA load, scale in place, TMA store)
   float bias_c[64], vec_c[64]; // band kernel: bias and head vector in the constant bank (no smem reads in the epilogue)
   // geometry of the (low-res for up-convs) input grid the M tiles walk over
   int H, W, B;                 // image dims of the A source, live batch
@@ -199,7 +200,9 @@ template <int BN, int EPI, int MT = 1> struct ConvCfg {
   static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves, per M tile
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * 64 * 2 + 4096 : 0;   // swizzled staging of ONE 64-channel half for the TMA store + its 2x2-pooled copy
+  // store: swizzled staging of ONE 64-channel half for the TMA store + its 2x2-pooled copy; gate: two 64-channel
+  // blocks of the skip tensor (TMA in, scaled in place, TMA out)
+  static constexpr int kOutBytes = (EPI == EPI_STORE) ? 128 * 64 * 2 + 4096 : (EPI == EPI_GATE ? 2 * 16384 : 0);
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTmemCols = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // 64,128,256,512: powers of two
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  auto xbar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 4 + s); };      // gate: skip-tensor block landed
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
   float* s_bias = reinterpret_cast<float*>(misc + 256);        // up to 256 floats
   float* s_vec = reinterpret_cast<float*>(misc + 1280);        // psi / head weights, up to 256 floats
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); mbar_init(xbar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -343,6 +347,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     const int lh = rr % p.box_h; const int ln = rr / p.box_h;
     int as = 0; uint32_t aphase = 0;
     int cur_nt = -1;
+    uint32_t xphase[2] = {0u, 0u};                // gate: parity of the two skip-tensor buffers
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
       const int mg = rest % m_groups; const int ph = rest / m_groups;
@@ -433,10 +438,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         // gate: the skip-tensor row does not depend on the GEMM -> issue its first loads now so
         // their latency hides behind the wait for the accumulator
         uint4 xpre[8];
+        const bool gate_tma = EPI == EPI_GATE && p.gate_tma;
+        const int gx0 = tx * p.box_w, gy0 = ty * p.box_h, gn0 = tn * p.box_n;
         if constexpr (EPI == EPI_GATE) {
-          const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + (live ? pix : 0) * p.gate_c);
+          if (gate_tma) {
+            // first 64-channel block of the skip tensor -> buffer 0, in flight while the accumulator is awaited
+            if (et == 0) {
+              tma_store_wait_read();                    // the previous tile's stores are done reading the buffers
+              mbar_expect_tx(xbar(0), 16384);
+              tma_load_4d(out_base, &p.tmA1, xbar(0), 0, gx0, gy0, gn0);
+            }
+          } else {
+            const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + (live ? pix : 0) * p.gate_c);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) xpre[c] = __ldg(xi + c);
+            for (int c = 0; c < 8; ++c) xpre[c] = __ldg(xi + c);
+          }
         }
         mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
         tc_fence_after();
@@ -461,7 +477,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
           // (A 128-thread "coalesced" sweep over the tile measured slower: each row is a whole number of
           // 128-B lines, so the per-row walk already moves full lines.)
           const float sc = 1.f / (1.f + expf(-(dot + p.psi_b)));
-          if (live) {
+          if (gate_tma) {
+            const int nhb = p.gate_c >> 6;
+#pragma unroll 1
+            for (int hb = 0; hb < nhb; ++hb) {
+              const int b = hb & 1;
+              const uint32_t buf = out_base + (uint32_t)b * 16384u;
+              if (hb + 1 < nhb && et == 0) {            // next block into the other buffer once its last store has been read
+                tma_store_wait_read();
+                mbar_expect_tx(xbar(b ^ 1), 16384);
+                tma_load_4d(out_base + (uint32_t)(b ^ 1) * 16384u, &p.tmA1, xbar(b ^ 1), (hb + 1) * 64, gx0, gy0, gn0);
+              }
+              mbar_wait(xbar(b), xphase[b], p.err_flag, 6);
+              xphase[b] ^= 1u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t addr = sw128(buf, row, j);
+                uint4 t = ld_shared_v4(addr);
+                __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = __half22float2(h[k]);
+                  h[k] = __floats2half2_rn(f.x * sc, f.y * sc);
+                }
+                st_shared_v4(addr, t);
+              }
+              fence_async_smem();
+              epi_bar();
+              if (et == 0) { tma_store_4d(&p.tmOut[0], buf, hb * 64, gx0, gy0, gn0); tma_store_commit(); }
+            }
+          } else if (live) {
             const uint4* xi = reinterpret_cast<const uint4*>(p.gate_x + pix * p.gate_c);
             uint4* xo = reinterpret_cast<uint4*>(p.out + pix * p.out_c);
             const int nchunk = p.gate_c >> 3;            // 16-B chunks per row: 8, 16, 32 or 64
@@ -500,7 +545,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
-    if (EPI == EPI_STORE && et == 0) tma_store_wait_all();   // all output bytes written before the CTA retires
+    if (EPI != EPI_HEAD && et == 0) tma_store_wait_all();    // all output bytes written before the CTA retires
   }
 
   tc_fence_before();

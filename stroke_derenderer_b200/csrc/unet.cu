@@ -244,6 +244,7 @@ struct sd_engine {
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
   int cta2 = 1;                        // Cout % 256 == 0 layers on SM pairs (cluster of 2, tcgen05 cta_group::2); SD_CTA2=0: one CTA per tile
+  int gate_tma = 1;                    // gate epilogue moves the skip tensor with TMA (load, scale in smem, store); SD_GATETMA=0: per-thread row walk
   int up4 = 1;                         // Up2: four sub-pixel phases per work item (SD_UP4=0: generic kernel, phase by phase)
   int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
   int conv1_tc = 1;                    // Conv1.0 on the tensor pipe (SD_CONV1TC=0: CUDA-core kernel)
@@ -540,6 +541,8 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     p.out = cs.out->p; p.out_c = cs.out->C;
     p.psi_w = e->w_f32[SD_ATT5_PSI + 6 * cs.att]; p.psi_b = e->psi_b[cs.att];
     p.gate_x = cs.in1->p; p.gate_c = cs.in1->C;
+    p.gate_tma = e->gate_tma;
+    if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
   }
   if (cs.epi == EPI_HEAD) { p.head_w = e->w_f32[SD_HEAD]; }
   if (cs.up && co == 64 && !cs.in1 && cs.epi == EPI_STORE && e->up4) {
@@ -733,6 +736,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* c1 = getenv("SD_CONV1TC")) e->conv1_tc = atoi(c1);
   if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
   if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
+  if (const char* gt = getenv("SD_GATETMA")) e->gate_tma = atoi(gt);
   if (const char* c2 = getenv("SD_CTA2")) e->cta2 = atoi(c2);
   if (!e->band) e->fuse_pool = 0;                   // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
