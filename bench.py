@@ -277,7 +277,8 @@ def run_gpu(args):
         tp = ROOT / "profiles" / "r01_conv_traffic.json"      # dram bytes of the same launches from one ncu --set full capture
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]
+                tj = json.loads(tp.read_text())     # captured on a 128-tile pass; DRAM bytes scale with the tiles of a pass
+                traffic = tj["dram_bytes_per_launch"] * nb / tj.get("tiles_per_pass", 128)
             except Exception:
                 traffic = None
         roof = {"bound": "tensor",
@@ -376,7 +377,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--max-tiles", type=int, default=128)
+    ap.add_argument("--max-tiles", type=int, default=256, help="tiles per UNet pass (engine size)")
     ap.add_argument("--lines-per-chunk", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true")

@@ -175,6 +175,18 @@ int sd_group_canvas(const int32_t* d_labels, const sd_line* d_lines,
 int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, const int32_t* d_rs_dims, int n_groups,
                    int size, uint8_t* d_image_u8, float* d_input_f32, const float* d_lut, void* stream);
 
+/* common.py:85-93 / helper/split.py:127-135 (resize_to_height) for lines whose height is not 128:
+ * cv2.resize(img, (dst_w, 128)) with the default INTER_LINEAR, bit-exact (8-bit fixed point, 2x area shortcut),
+ * dst_w = int(w * (128 / h)) computed by the caller like the reference does.  Reads (src_h, src_w, 3) u8 at
+ * d_src + src_off and writes (128, dst_w, 3) u8 at d_rgb + dst_off (= sd_line.img_off of the packed input). */
+typedef struct sd_resize_job {
+  int64_t src_off;
+  int64_t dst_off;
+  int32_t src_h, src_w, dst_w, reserved;
+} sd_resize_job;
+int sd_resize_lines(const uint8_t* d_src, const sd_resize_job* d_jobs, int n_jobs, int max_dst_w,
+                    uint8_t* d_rgb, void* stream);
+
 /* ---- Attention-UNet engine ------------------------------------------------ */
 /* Replaces onnxruntime.InferenceSession (evaluate_binarize.py:48-53) and its
  * .run() (:62, :100).  max_tiles bounds one sd_unet_forward call. */

@@ -24,6 +24,11 @@ LINE_DTYPE = np.dtype([
 ], align=True)
 assert LINE_DTYPE.itemsize == 56
 
+# numpy mirror of `struct sd_resize_job`
+RESIZE_DTYPE = np.dtype([("src_off", "<i8"), ("dst_off", "<i8"), ("src_h", "<i4"), ("src_w", "<i4"), ("dst_w", "<i4"),
+                         ("reserved", "<i4")], align=True)
+assert RESIZE_DTYPE.itemsize == 32
+
 
 class Plan(C.Structure):
     _fields_ = [("img_bytes", C.c_int64), ("px_total", C.c_int64), ("blk_total", C.c_int64),
@@ -64,6 +69,7 @@ EXPORTS = {
                                   C.c_void_p]),
     "sd_group_crops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "sd_resize_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_engine_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sd_engine_destroy": (None, [C.c_void_p]),
     "sd_engine_set_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),

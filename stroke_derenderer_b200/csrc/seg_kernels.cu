@@ -881,6 +881,67 @@ __global__ void __launch_bounds__(256) group_crop_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------
+// K11: general-height line resize (common.py:85-93 / helper/split.py:127-135): cv2.resize(img, (int(w * (128 / h)),
+//   128)) with the default INTER_LINEAR on (h, w, 3) u8, written straight into the packed line buffer that
+//   tile_extract reads.  Same bit-exact restatement of cv2's 8-bit fixed-point bilinear as K10 (oracle:
+//   resize_linear_u8 per channel, pinned against cv2 on 3-channel images in tests/test_oracle.py).
+// One CTA = 128 output columns x all 128 rows of one line; the 128 + 128 coefficient pairs are computed once in
+// shared memory (they need a double division each), then every thread walks one column through 64 rows.
+// ---------------------------------------------------------------------------
+constexpr int kRsCols = 128;
+
+__global__ void __launch_bounds__(256) resize_lines_kernel(const uint8_t* __restrict__ src,
+                                                           const sd_resize_job* __restrict__ jobs,
+                                                           uint8_t* __restrict__ dst) {
+  const sd_resize_job J = jobs[blockIdx.y];
+  const int xc = blockIdx.x * kRsCols;
+  if (xc >= J.dst_w) return;
+  __shared__ int s_xo[kRsCols], s_yo[SD_TILE_H];
+  __shared__ short s_xa[kRsCols][2], s_yb[SD_TILE_H][2];
+  const int tid = threadIdx.x, col = tid & (kRsCols - 1), x = xc + col;
+  {
+    int o = 0, a0 = 0, a1 = 0;
+    if (tid < kRsCols) {
+      if (x < J.dst_w) crop_coeff(x, J.dst_w, J.src_w, true, o, a0, a1);
+      s_xo[col] = o; s_xa[col][0] = (short)a0; s_xa[col][1] = (short)a1;
+    } else {
+      crop_coeff(col, SD_TILE_H, J.src_h, false, o, a0, a1);
+      s_yo[col] = o; s_yb[col][0] = (short)a0; s_yb[col][1] = (short)a1;
+    }
+  }
+  __syncthreads();
+  if (x >= J.dst_w) return;
+  const uint8_t* S = src + J.src_off;
+  uint8_t* D = dst + J.dst_off;
+  const int64_t srow = (int64_t)J.src_w * 3;
+  if (J.src_w == 2 * J.dst_w && J.src_h == 2 * SD_TILE_H) {          // cv2: exact 2x decimation -> INTER_AREA
+    for (int y = tid >> 7; y < SD_TILE_H; y += 2) {
+      const uint8_t* r0 = S + (int64_t)(2 * y) * srow + (int64_t)(2 * x) * 3;
+      uint8_t* o = D + ((int64_t)y * J.dst_w + x) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((r0[c] + r0[3 + c] + r0[srow + c] + r0[srow + 3 + c] + 2) >> 2);
+    }
+    return;
+  }
+  const int x0 = s_xo[col] * 3, x1 = min(s_xo[col] + 1, J.src_w - 1) * 3;
+  const int a0 = s_xa[col][0], a1 = s_xa[col][1];
+  for (int y = tid >> 7; y < SD_TILE_H; y += 2) {
+    const int y0 = min(max(s_yo[y], 0), J.src_h - 1), y1 = min(max(s_yo[y] + 1, 0), J.src_h - 1);
+    const int b0 = s_yb[y][0], b1 = s_yb[y][1];
+    const uint8_t* r0 = S + (int64_t)y0 * srow;
+    const uint8_t* r1 = S + (int64_t)y1 * srow;
+    uint8_t* o = D + ((int64_t)y * J.dst_w + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int H0 = r0[x0 + c] * a0 + r0[x1 + c] * a1;
+      const int H1 = r1[x0 + c] * a0 + r1[x1 + c] * a1;
+      const int v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
+      o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
+}
+
 }  // namespace sd
 
 // ===========================================================================
@@ -1201,5 +1262,16 @@ extern "C" int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, 
   group_crop_kernel<<<n_groups, 256, smem, (cudaStream_t)stream>>>(d_canvas, d_groups, d_rs_dims, size, d_image_u8,
                                                                    d_input_f32, d_lut);
   SD_LAUNCH_CHECK("group_crop_kernel");
+  return SD_OK;
+}
+
+extern "C" int sd_resize_lines(const uint8_t* d_src, const sd_resize_job* d_jobs, int n_jobs, int max_dst_w,
+                               uint8_t* d_rgb, void* stream) {
+  if (n_jobs == 0) return SD_OK;
+  SD_REQUIRE(d_src && d_jobs && d_rgb && n_jobs > 0 && max_dst_w > 0, "sd_resize_lines: bad argument");
+  SD_REQUIRE(n_jobs <= 65535, "sd_resize_lines: %d jobs in one call (max 65535)", n_jobs);
+  const dim3 grid((max_dst_w + kRsCols - 1) / kRsCols, n_jobs);
+  resize_lines_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_jobs, d_rgb);
+  SD_LAUNCH_CHECK("resize_lines_kernel");
   return SD_OK;
 }

@@ -75,9 +75,8 @@ class BinarizationSession:
         but the input lines and the glued masks crosses PCIe."""
         if (self.height, self.width, self.overlap) != (HEIGHT, WIDTH, OVERLAP):
             raise ValueError("B200 path supports the default 128/384/64 geometry")
-        images_rs = [resize_to_height(im, self.height) if im.shape[0] != self.height else im for im in images]
         seg = _seg.Segmenter(ort, bin_thr=self.bin_thr)
-        batch, planes = seg.binarize(images_rs)
+        batch, planes = seg.binarize(images)       # resize_to_height (:76) happens on the device, bit-exact with cv2
         return [batch.plane(planes, i).cpu().numpy()[:, :, None].copy() for i in range(batch.n_lines)]
 
     def binarize_image(self, image, ort):

@@ -83,10 +83,13 @@ class LineSegmentationJob:
                 imgs = images[c0:c0 + lines_per_chunk]
                 ch = _Chunk()
                 ch.index = len(self.chunks)
-                ch.batch = S.plan_batch([im.shape[1] for im in imgs], self.device)
+                ch.batch = S.plan_batch([S.resized_width(im) for im in imgs], self.device)
                 ch.h_rgb = S.pack_lines_rgb(imgs, ch.batch, pinned=True)
                 ch.d_rgb = ch.h_rgb.to(self.device)
                 ch.d_rgb_in = torch.empty_like(ch.d_rgb)
+                ch.resize = S.ResizePlan(imgs, ch.batch)            # lines whose height is not 128 (none in the configs)
+                ch.resize.upload()
+                ch.resize.run(ch.d_rgb)
                 ch.t0, ch.t1 = t0, t0 + ch.batch.n_tiles        # the chunk's range in the job-wide tile stack
                 t0 = ch.t1
                 ch.planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, device=self.device)
@@ -116,10 +119,13 @@ class LineSegmentationJob:
                 if from_host:
                     with torch.cuda.stream(self.s_copy):
                         ch.d_rgb_in.copy_(ch.h_rgb, non_blocking=True)
+                        ch.resize.upload()
                         ev = torch.cuda.Event(); ev.record(self.s_copy)
                     self.s_unet.wait_event(ev)
                     src = ch.d_rgb_in
                 with torch.cuda.stream(self.s_unet):
+                    if from_host:
+                        ch.resize.run(src)
                     S.tile_extract_f16(ch.batch, src, out=ch.tiles)
                     last = k == len(self.chunks) - 1
                     while done + mt <= ch.t1 or (last and done < ch.t1):
@@ -167,7 +173,7 @@ class LineSegmentationJob:
         return self._run(True, "host")
 
     def h2d_bytes(self):
-        return int(sum(c.batch.plan.img_bytes for c in self.chunks))
+        return int(sum(c.batch.plan.img_bytes + (c.resize.h_src.numel() if c.resize.n else 0) for c in self.chunks))
 
     def d2h_bytes(self, results):
         n = sum(c.batch.px_total for c in self.chunks)

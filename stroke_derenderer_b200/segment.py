@@ -65,16 +65,76 @@ def plan_batch(widths, device, tile_w=TILE_W, overlap=64) -> LineBatch:
     return LineBatch(torch.device(device), lines, plan, d_lines, [int(w) for w in widths])
 
 
+def resized_width(img, height: int = TILE_H) -> int:
+    """Line width after resize_to_height (common.py:89-91): int(w * (height / h)); w itself at h == height,
+    where cv2.resize is a copy."""
+    h, w = img.shape[0], img.shape[1]
+    return int(w) if h == height else int(w * (height / h))
+
+
 def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True) -> torch.Tensor:
-    """Host-packs (128, W, 3) u8 images at sd_line.img_off (pinned staging)."""
+    """Host-packs (128, W, 3) u8 images at sd_line.img_off (pinned staging).  Lines of another height are left
+    out: `ResizePlan` fills their slots on the device."""
     buf = torch.empty(int(batch.plan.img_bytes), dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
     nb = buf.numpy()
     for img, ln in zip(images, batch.lines):
+        if img.shape[0] != TILE_H:
+            continue
         a = np.ascontiguousarray(img, dtype=np.uint8)
         assert a.shape == (TILE_H, int(ln["width"]), 3), (a.shape, int(ln["width"]))
         off = int(ln["img_off"])
         nb[off:off + a.size] = a.reshape(-1)
     return buf
+
+
+class ResizePlan:
+    """The lines of a batch whose height is not 128 (resize_to_height, common.py:85-93): their pixels at the
+    original size in one pinned buffer plus the sd_resize_job table; `run` resizes them on the device into
+    their slots of the packed line buffer (sd_resize_lines, bit-exact with cv2.resize)."""
+
+    def __init__(self, images, batch: LineBatch, pinned: bool = True):
+        todo = [(i, im) for i, im in enumerate(images) if im.shape[0] != TILE_H]
+        self.n = len(todo)
+        self.device = batch.device
+        if not self.n:
+            return
+        jobs = np.zeros(self.n, _lib.RESIZE_DTYPE)
+        off = 0
+        for j, (i, im) in enumerate(todo):
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError(f"line {i}: expected an (h, w, 3) image, got {im.shape}")
+            ln = batch.lines[i]
+            jobs[j] = (off, int(ln["img_off"]), im.shape[0], im.shape[1], int(ln["width"]), 0)
+            off += (im.size + 15) // 16 * 16
+        self.h_src = torch.empty(off, dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+        nb = self.h_src.numpy()
+        for (i, im), jb in zip(todo, jobs):
+            nb[int(jb["src_off"]):int(jb["src_off"]) + im.size] = np.ascontiguousarray(im, dtype=np.uint8).reshape(-1)
+        self.max_dst_w = int(jobs["dst_w"].max())
+        self.d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(self.device)
+        self.d_src = None
+
+    def upload(self):
+        if self.n:
+            self.d_src = self.h_src.to(self.device, non_blocking=True) if self.d_src is None else self.d_src.copy_(
+                self.h_src, non_blocking=True)
+
+    def run(self, d_rgb: torch.Tensor):
+        """Enqueues the resize on the current stream (after `upload` on the same stream or an event wait)."""
+        if self.n:
+            _lib.check(_lib.lib().sd_resize_lines(self.d_src.data_ptr(), self.d_jobs.data_ptr(), self.n, self.max_dst_w,
+                                                  d_rgb.data_ptr(), stream_ptr(self.device)), "sd_resize_lines")
+
+
+def upload_lines(images, device):
+    """images of any height -> (batch, packed (128, W', 3) lines on the device): resize_to_height of every line
+    (common.py:85-93; evaluate_binarize.py:76), with the lines that need it resized on the GPU."""
+    batch = plan_batch([resized_width(im) for im in images], device)
+    d_rgb = pack_lines_rgb(images, batch).to(device, non_blocking=True)
+    rp = ResizePlan(images, batch)
+    rp.upload()
+    rp.run(d_rgb)
+    return batch, d_rgb
 
 
 def _s(batch): return stream_ptr(batch.device)
@@ -315,9 +375,11 @@ class Segmenter:
     def binarize(self, images, d_rgb: torch.Tensor | None = None, batch: LineBatch | None = None):
         """-> (batch, mask planes u8 {0,255} packed on device)."""
         with torch.cuda.device(self.device):
-            if batch is None:
+            if batch is None and d_rgb is None:
+                batch, d_rgb = upload_lines(images, self.device)       # any height: resize_to_height on the GPU
+            elif batch is None:
                 batch = plan_batch([im.shape[1] for im in images], self.device)
-            if d_rgb is None:
+            elif d_rgb is None:
                 d_rgb = pack_lines_rgb(images, batch).to(self.device, non_blocking=True)
             tiles = tile_extract_f16(batch, d_rgb)
             masks = torch.empty((batch.n_tiles, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)

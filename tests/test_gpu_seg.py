@@ -224,6 +224,49 @@ def test_split_module_dropin(cuda_device):
     assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
 
 
+def test_resize_lines_bit_exact_vs_cv2(cuda_device):
+    """sd_resize_lines == resize_to_height (common.py:85-93: cv2.resize, INTER_LINEAR) on lines of other heights,
+    mixed in one batch with 128-px lines: up- and down-scaling, the exact-2x area path (even and odd widths),
+    1- and 2-row sources, widths that are not multiples of the 128-column CTA."""
+    rng = np.random.default_rng(11)
+    shapes = [(200, 1000), (128, 700), (64, 300), (256, 1024), (256, 1025), (130, 777), (127, 500), (1, 40), (2, 9),
+              (128, 384), (129, 1290), (37, 400), (255, 1001), (512, 3000), (300, 2000), (90, 12000)]
+    shapes += [(int(rng.integers(3, 400)), int(rng.integers(8, 1500))) for _ in range(20)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes if int(w * (128 / h)) >= 1]
+    batch, d_rgb = S.upload_lines(imgs, torch.device("cuda", 0))
+    got = d_rgb.cpu().numpy()
+    for im, ln in zip(imgs, batch.lines):
+        ref = O.resize_to_height(im, 128) if im.shape[0] != 128 else im
+        assert int(ln["width"]) == ref.shape[1]
+        off = int(ln["img_off"])
+        assert np.array_equal(got[off:off + ref.size].reshape(ref.shape), ref), im.shape
+
+
+def test_binarize_images_other_heights(cuda_device, parity_state):
+    """BinarizationSession.binarize_images on lines taller / shorter than 128 (evaluate_binarize.py:76) == the same
+    call on the lines resized by the reference's cv2 call first; and the chunked pipeline agrees."""
+    from stroke_derenderer_b200.evaluate_binarize import BinarizationSession
+    from stroke_derenderer_b200.pipeline import LineSegmentationJob
+    bs = BinarizationSession(max_tiles=16)
+    ort = bs.init_onnx_inference(parity_state)
+    lines = [synth_line(900, 3), synth_line(1500, 4), synth_line(400, 5)]
+    import cv2
+    raw = [cv2.resize(lines[0], (1400, 200)), lines[1], cv2.resize(lines[2], (300, 96))]
+    a = bs.binarize_images(raw, ort)
+    b = bs.binarize_images([O.resize_to_height(im, 128) if im.shape[0] != 128 else im for im in raw], ort)
+    assert [x.shape for x in a] == [x.shape for x in b]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    job = LineSegmentationJob(ort, raw, lines_per_chunk=2, crops=False)
+    for step in (job.resident_step, job.host_step):
+        res = step()
+        torch.cuda.synchronize()
+        k = 0
+        for ch in job.chunks:
+            for i in range(ch.batch.n_lines):
+                assert np.array_equal(ch.batch.plane(ch.planes, i).cpu().numpy(), a[k][:, :, 0]), (step.__name__, k)
+                k += 1
+
+
 def test_group_crops_bit_exact_vs_reference_calls(cuda_device):
     """sd_group_crops == normalize -> cv2.resize -> pad -> normalize -> mean/std of evaluate_strokes.py:202-222,
     on hand-made canvases that hit every branch: up- and down-scaling, exact 2x decimation (area path), constant

@@ -133,6 +133,27 @@ def test_batch_invariance(cuda_device, parity_state):
         e.close()
 
 
+def test_large_batch_matches_small_batches(cuda_device, parity_state):
+    """The benchmark's engine size (256 tiles per pass: offsets beyond 2^31 bytes in the level-1 tensors, the
+    largest work-item counts) gives the same masks, bit for bit, as the same tiles through a 64-tile engine."""
+    rng = np.random.default_rng(17)
+    x = torch.from_numpy(rng.random((256, 128, 384, 8), dtype=np.float32)).cuda().half()
+    x[..., 3:] = 0
+    big = UNetEngine(parity_state, device=0, max_tiles=256, impl=0)
+    try:
+        m_big = big.forward(x, want_mask=True)["mask"].clone()
+        m_tail = big.forward(x[:130].contiguous(), want_mask=True)["mask"].clone()    # a partial pass
+    finally:
+        big.close()
+    small = UNetEngine(parity_state, device=0, max_tiles=64, impl=0)
+    try:
+        m_small = torch.cat([small.forward(x[s:s + 64].contiguous(), want_mask=True)["mask"].clone() for s in range(0, 256, 64)])
+    finally:
+        small.close()
+    assert bool((m_big != 0).any()) and bool((m_big == 0).any())
+    assert bool((m_big == m_small).all()) and bool((m_tail == m_small[:130]).all())
+
+
 def test_repeatability_under_load(cuda_device, parity_state):
     """The same batch through the engine 12 times, back to back (persistent kernels, mbarrier pipelines, TMEM
     rings, cluster pairs): every run must reproduce the first bit for bit."""

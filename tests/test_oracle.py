@@ -183,6 +183,24 @@ def test_resize_restatement_matches_cv2():
         assert np.array_equal(O.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), ((h, w), (dw, dh))
 
 
+def test_resize_restatement_matches_cv2_on_rgb_lines():
+    """resize_to_height (common.py:85-93) of (h, w, 3) lines: the restatement, applied per channel, == cv2.resize
+    for heights below, above and at twice 128 (cv2 switches to its area path at exactly 2x)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    shapes = [(200, 1000), (64, 300), (256, 1024), (256, 1025), (130, 777), (127, 500), (1, 40), (2, 9), (129, 1290),
+              (37, 400), (255, 1001), (512, 3000), (300, 2000)]
+    shapes += [(int(rng.integers(3, 400)), int(rng.integers(8, 1500))) for _ in range(25)]
+    for h, w in shapes:
+        dw = int(w * (128 / h))
+        if dw < 1:
+            continue
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = O.resize_to_height(img, 128)
+        mine = np.stack([O.resize_linear_u8(img[:, :, c], dw, 128) for c in range(3)], -1)
+        assert ref.shape == mine.shape and np.array_equal(ref, mine), (h, w)
+
+
 def test_normalize_restatement_matches_cv2():
     import cv2
     rng = np.random.default_rng(1)
