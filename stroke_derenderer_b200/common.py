@@ -52,8 +52,9 @@ def save_json(json_dict, save_path):
 
 
 def resize_to_height(img, height):
-    """common.py:85-93. Host cv2 (identity for the 128-px lines the configs use);
-    a GPU general-height resize is SURVEY.md 8(f) item 3."""
+    """common.py:85-93, host form (cv2) for the per-stage legacy API (`preprocess_images`, `cut_and_stack`).
+    The fused path (`binarize_images`, `LineSegmentationJob`) resizes on the GPU instead: `segment.upload_lines`
+    -> sd_resize_lines, bit-exact with this call."""
     h, w = img.shape[0], img.shape[1]
     return cv2.resize(img, (int(w * (height / h)), height))
 
