@@ -178,7 +178,9 @@ int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, const int32
 /* common.py:85-93 / helper/split.py:127-135 (resize_to_height) for lines whose height is not 128:
  * cv2.resize(img, (dst_w, 128)) with the default INTER_LINEAR, bit-exact (8-bit fixed point, 2x area shortcut),
  * dst_w = int(w * (128 / h)) computed by the caller like the reference does.  Reads (src_h, src_w, 3) u8 at
- * d_src + src_off and writes (128, dst_w, 3) u8 at d_rgb + dst_off (= sd_line.img_off of the packed input). */
+ * d_src + src_off and writes (128, dst_w, 3) u8 at d_rgb + dst_off (= sd_line.img_off of the packed input).
+ * Layout contract of d_src: every image is followed by at least 8 readable bytes (the kernel fetches pixel pairs
+ * as aligned 32-bit words); images that do not start on a 4-byte boundary still work, through byte gathers. */
 typedef struct sd_resize_job {
   int64_t src_off;
   int64_t dst_off;

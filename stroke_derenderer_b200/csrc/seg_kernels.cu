@@ -886,10 +886,35 @@ __global__ void __launch_bounds__(256) group_crop_kernel(
 //   128)) with the default INTER_LINEAR on (h, w, 3) u8, written straight into the packed line buffer that
 //   tile_extract reads.  Same bit-exact restatement of cv2's 8-bit fixed-point bilinear as K10 (oracle:
 //   resize_linear_u8 per channel, pinned against cv2 on 3-channel images in tests/test_oracle.py).
-// One CTA = 128 output columns x all 128 rows of one line; the 128 + 128 coefficient pairs are computed once in
-// shared memory (they need a double division each), then every thread walks one column through 64 rows.
+// One CTA = 128 output columns x 32 rows of one line; the 128 + 32 coefficient pairs are computed once in shared
+// memory (they need a double division each), then every thread walks one column through 16 rows, four rows of
+// loads in flight at a time (the first version, 64 dependent rows per thread, was latency-bound).  The two
+// horizontally adjacent source pixels (6 bytes) come in as aligned 32-bit words realigned with funnel shifts
+// (a third of the load instructions of byte gathers).  The kernel is bound by instruction issue (~100 integer
+// instructions per output pixel), not by HBM or latency: staging the source rows in shared memory (+25 %) and
+// packing a warp's 96 output bytes into aligned words through shared memory (+40 %) were both measured slower.
 // ---------------------------------------------------------------------------
-constexpr int kRsCols = 128;
+constexpr int kRsCols = 128;    // output columns per CTA
+constexpr int kRsBand = 32;     // output rows per CTA (two threads per column, 16 rows each)
+constexpr int kRsBatch = 4;     // rows whose loads are in flight together
+static_assert(SD_TILE_H % kRsBand == 0 && kRsBand % (2 * kRsBatch) == 0, "resize band");
+
+// bytes p[0..5] of a 4-byte aligned buffer region as (lo = p[0..3], hi = p[4..7]); reads up to 8 bytes past p + 3
+__device__ __forceinline__ void load6(const uint8_t* p, uint32_t& lo, uint32_t& hi) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const int o = (int)(a & 3);
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = (o == 3) ? __ldg(w + 2) : 0u;
+  lo = __funnelshift_r(w0, w1, 8 * o);
+  hi = __funnelshift_r(w1, w2, 8 * o);
+}
+
+__device__ __forceinline__ int resize_px(int p00, int p01, int p10, int p11, int a0, int a1, int b0, int b1, bool area2) {
+  if (area2) return (p00 + p01 + p10 + p11 + 2) >> 2;             // cv2: exact 2x decimation -> INTER_AREA
+  const int H0 = p00 * a0 + p01 * a1, H1 = p10 * a0 + p11 * a1;
+  const int v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
+  return min(max(v, 0), 255);
+}
 
 __global__ void __launch_bounds__(256) resize_lines_kernel(const uint8_t* __restrict__ src,
                                                            const sd_resize_job* __restrict__ jobs,
@@ -897,16 +922,22 @@ __global__ void __launch_bounds__(256) resize_lines_kernel(const uint8_t* __rest
   const sd_resize_job J = jobs[blockIdx.y];
   const int xc = blockIdx.x * kRsCols;
   if (xc >= J.dst_w) return;
-  __shared__ int s_xo[kRsCols], s_yo[SD_TILE_H];
-  __shared__ short s_xa[kRsCols][2], s_yb[SD_TILE_H][2];
+  __shared__ int s_xo[kRsCols], s_yo[kRsBand];
+  __shared__ short s_xa[kRsCols][2], s_yb[kRsBand][2];
   const int tid = threadIdx.x, col = tid & (kRsCols - 1), x = xc + col;
+  const int yb = blockIdx.z * kRsBand;                  // this CTA's band of output rows
+  const bool area2 = J.src_w == 2 * J.dst_w && J.src_h == 2 * SD_TILE_H;
   {
     int o = 0, a0 = 0, a1 = 0;
     if (tid < kRsCols) {
-      if (x < J.dst_w) crop_coeff(x, J.dst_w, J.src_w, true, o, a0, a1);
+      if (x < J.dst_w) {
+        if (area2) o = 2 * x;
+        else crop_coeff(x, J.dst_w, J.src_w, true, o, a0, a1);
+      }
       s_xo[col] = o; s_xa[col][0] = (short)a0; s_xa[col][1] = (short)a1;
-    } else {
-      crop_coeff(col, SD_TILE_H, J.src_h, false, o, a0, a1);
+    } else if (col < kRsBand) {
+      if (area2) o = 2 * (yb + col);
+      else crop_coeff(yb + col, SD_TILE_H, J.src_h, false, o, a0, a1);
       s_yo[col] = o; s_yb[col][0] = (short)a0; s_yb[col][1] = (short)a1;
     }
   }
@@ -915,33 +946,45 @@ __global__ void __launch_bounds__(256) resize_lines_kernel(const uint8_t* __rest
   const uint8_t* S = src + J.src_off;
   uint8_t* D = dst + J.dst_off;
   const int64_t srow = (int64_t)J.src_w * 3;
-  if (J.src_w == 2 * J.dst_w && J.src_h == 2 * SD_TILE_H) {          // cv2: exact 2x decimation -> INTER_AREA
-    for (int y = tid >> 7; y < SD_TILE_H; y += 2) {
-      const uint8_t* r0 = S + (int64_t)(2 * y) * srow + (int64_t)(2 * x) * 3;
-      uint8_t* o = D + ((int64_t)y * J.dst_w + x) * 3;
+  const int x0 = s_xo[col] * 3;
+  const int a0 = s_xa[col][0], a1 = s_xa[col][1];
+  // x1 = min(x0 + 1, src_w - 1): the clamp only happens where a1 == 0 (crop_coeff), so the pixel after x0 may stand
+  // in for it as long as its bytes are readable: the layout contract pads every image (include/sd_b200.h)
+  const bool words = (reinterpret_cast<uintptr_t>(S) & 3) == 0;
+  if (!words) {                       // misaligned source: byte gathers
+    const int dx = (s_xo[col] + 1 < J.src_w) ? 3 : 0;
+    for (int r = tid >> 7; r < kRsBand; r += 2) {
+      const int y0 = min(max(s_yo[r], 0), J.src_h - 1), y1 = min(max(s_yo[r] + 1, 0), J.src_h - 1);
+      const uint8_t* r0 = S + (int64_t)y0 * srow + x0;
+      const uint8_t* r1 = S + (int64_t)y1 * srow + x0;
+      uint8_t* o = D + ((int64_t)(yb + r) * J.dst_w + x) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((r0[c] + r0[3 + c] + r0[srow + c] + r0[srow + 3 + c] + 2) >> 2);
+      for (int c = 0; c < 3; ++c) o[c] = (uint8_t)resize_px(r0[c], r0[dx + c], r1[c], r1[dx + c], a0, a1, s_yb[r][0], s_yb[r][1], area2);
     }
     return;
   }
-  const int x0 = s_xo[col] * 3, x1 = min(s_xo[col] + 1, J.src_w - 1) * 3;
-  const int a0 = s_xa[col][0], a1 = s_xa[col][1];
-  for (int y = tid >> 7; y < SD_TILE_H; y += 2) {
-    const int y0 = min(max(s_yo[y], 0), J.src_h - 1), y1 = min(max(s_yo[y] + 1, 0), J.src_h - 1);
-    const int b0 = s_yb[y][0], b1 = s_yb[y][1];
-    const uint8_t* r0 = S + (int64_t)y0 * srow;
-    const uint8_t* r1 = S + (int64_t)y1 * srow;
-    uint8_t* o = D + ((int64_t)y * J.dst_w + x) * 3;
+  // 16 rows per thread in batches of kRsBatch: all loads of a batch are issued before any arithmetic
+#pragma unroll 1
+  for (int rb = tid >> 7; rb < kRsBand; rb += 2 * kRsBatch) {
+    uint32_t l0[kRsBatch], h0[kRsBatch], l1[kRsBatch], h1[kRsBatch];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int H0 = r0[x0 + c] * a0 + r0[x1 + c] * a1;
-      const int H1 = r1[x0 + c] * a0 + r1[x1 + c] * a1;
-      const int v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
-      o[c] = (uint8_t)min(max(v, 0), 255);
+    for (int k = 0; k < kRsBatch; ++k) {
+      const int r = rb + 2 * k;
+      const int y0 = min(max(s_yo[r], 0), J.src_h - 1), y1 = min(max(s_yo[r] + 1, 0), J.src_h - 1);
+      load6(S + (int64_t)y0 * srow + x0, l0[k], h0[k]);
+      load6(S + (int64_t)y1 * srow + x0, l1[k], h1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kRsBatch; ++k) {
+      const int r = rb + 2 * k;
+      const int b0 = s_yb[r][0], b1 = s_yb[r][1];
+      uint8_t* o = D + ((int64_t)(yb + r) * J.dst_w + x) * 3;
+      o[0] = (uint8_t)resize_px(l0[k] & 255, l0[k] >> 24, l1[k] & 255, l1[k] >> 24, a0, a1, b0, b1, area2);
+      o[1] = (uint8_t)resize_px((l0[k] >> 8) & 255, h0[k] & 255, (l1[k] >> 8) & 255, h1[k] & 255, a0, a1, b0, b1, area2);
+      o[2] = (uint8_t)resize_px((l0[k] >> 16) & 255, (h0[k] >> 8) & 255, (l1[k] >> 16) & 255, (h1[k] >> 8) & 255, a0, a1, b0, b1, area2);
     }
   }
 }
-
 }  // namespace sd
 
 // ===========================================================================
@@ -1270,7 +1313,7 @@ extern "C" int sd_resize_lines(const uint8_t* d_src, const sd_resize_job* d_jobs
   if (n_jobs == 0) return SD_OK;
   SD_REQUIRE(d_src && d_jobs && d_rgb && n_jobs > 0 && max_dst_w > 0, "sd_resize_lines: bad argument");
   SD_REQUIRE(n_jobs <= 65535, "sd_resize_lines: %d jobs in one call (max 65535)", n_jobs);
-  const dim3 grid((max_dst_w + kRsCols - 1) / kRsCols, n_jobs);
+  const dim3 grid((max_dst_w + kRsCols - 1) / kRsCols, n_jobs, SD_TILE_H / kRsBand);
   resize_lines_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_jobs, d_rgb);
   SD_LAUNCH_CHECK("resize_lines_kernel");
   return SD_OK;

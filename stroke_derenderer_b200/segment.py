@@ -105,7 +105,7 @@ class ResizePlan:
                 raise ValueError(f"line {i}: expected an (h, w, 3) image, got {im.shape}")
             ln = batch.lines[i]
             jobs[j] = (off, int(ln["img_off"]), im.shape[0], im.shape[1], int(ln["width"]), 0)
-            off += (im.size + 15) // 16 * 16
+            off += (im.size + 8 + 15) // 16 * 16        # the kernel's word loads may read 8 bytes past an image
         self.h_src = torch.empty(off, dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
         nb = self.h_src.numpy()
         for (i, im), jb in zip(todo, jobs):

@@ -227,10 +227,11 @@ def test_split_module_dropin(cuda_device):
 def test_resize_lines_bit_exact_vs_cv2(cuda_device):
     """sd_resize_lines == resize_to_height (common.py:85-93: cv2.resize, INTER_LINEAR) on lines of other heights,
     mixed in one batch with 128-px lines: up- and down-scaling, the exact-2x area path (even and odd widths),
-    1- and 2-row sources, widths that are not multiples of the 128-column CTA."""
+    1- and 2-row sources, widths that are not multiples of the 128-column CTA, and reductions beyond the
+    kernel's staging window (direct-gather fallback)."""
     rng = np.random.default_rng(11)
     shapes = [(200, 1000), (128, 700), (64, 300), (256, 1024), (256, 1025), (130, 777), (127, 500), (1, 40), (2, 9),
-              (128, 384), (129, 1290), (37, 400), (255, 1001), (512, 3000), (300, 2000), (90, 12000)]
+              (128, 384), (129, 1290), (37, 400), (255, 1001), (512, 3000), (300, 2000), (90, 12000), (800, 5000), (1500, 4000), (679, 2037), (700, 700)]
     shapes += [(int(rng.integers(3, 400)), int(rng.integers(8, 1500))) for _ in range(20)]
     imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes if int(w * (128 / h)) >= 1]
     batch, d_rgb = S.upload_lines(imgs, torch.device("cuda", 0))
