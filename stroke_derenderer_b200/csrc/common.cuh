@@ -44,4 +44,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute applies to the current device only: one flag per device for each call site
+// (`static PerDeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`), so that a process driving several
+// GPUs raises the shared-memory limit of a kernel on each of them.
+struct PerDeviceOnce {
+  std::atomic<bool> done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    return !done[dev].exchange(true, std::memory_order_relaxed);
+  }
+};
+
 }  // namespace sd

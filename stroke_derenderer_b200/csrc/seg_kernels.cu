@@ -1297,11 +1297,8 @@ extern "C" int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, 
   SD_REQUIRE(size > 0 && size <= kCropMax && size % 2 == 0, "sd_group_crops: size %d (even, <= %d)", size, kCropMax);
   SD_REQUIRE(!d_input_f32 || d_lut, "sd_group_crops: the f32 output needs the 3x256 table");
   const int smem = size * size;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(group_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropMax * kCropMax));
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(group_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropMax * kCropMax));
   group_crop_kernel<<<n_groups, 256, smem, (cudaStream_t)stream>>>(d_canvas, d_groups, d_rs_dims, size, d_image_u8,
                                                                    d_input_f32, d_lut);
   SD_LAUNCH_CHECK("group_crop_kernel");

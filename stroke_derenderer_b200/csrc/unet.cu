@@ -325,11 +325,8 @@ static int make_tmap_pool(sd_engine* e, CUtensorMap* tm, const Act& o, int bw, i
 template <int BN, int EPI, int MT = 1>
 static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
   using Cfg = ConvCfg<BN, EPI, MT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   conv_umma_kernel<BN, EPI, MT><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_umma_kernel");
   return SD_OK;
@@ -338,11 +335,8 @@ static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
 template <int CB, int EPI>
 static int launch_band(const ConvParams& p, int grid, cudaStream_t s) {
   using Cfg = BandCfg<CB, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   conv_band_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_band_kernel");
   return SD_OK;
@@ -358,11 +352,8 @@ static int dispatch_band(const ConvParams& p, int cb, int epi, int grid, cudaStr
 
 // 2-SM variant (cluster of 2, cta_group::2) of the 256-wide store-epilogue conv
 static int launch_conv2(const ConvParams& p, int n_sms, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   const int n_work = ((p.m_tiles + 1) / 2) * p.n_tiles * p.n_phases;
   int pairs = n_sms / 2;
   if (n_work < pairs) pairs = n_work;
@@ -579,11 +570,8 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     op4.run = [p, box_n4, per_img4, nsm4](int B, cudaStream_t s) mutable -> int {
       p.B = B;
       p.m_tiles = per_img4 * ((B + box_n4 - 1) / box_n4);
-      static bool attr_done = false;
-      if (!attr_done) {
-        SD_CUDA_CHECK(cudaFuncSetAttribute(conv_up4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Up4Cfg::kSmemBytes));
-        attr_done = true;
-      }
+      static PerDeviceOnce attr_once;
+      if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_up4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Up4Cfg::kSmemBytes));
       conv_up4_kernel<<<p.m_tiles < nsm4 ? p.m_tiles : nsm4, kConvThreads, Up4Cfg::kSmemBytes, s>>>(p);
       SD_LAUNCH_CHECK("conv_up4_kernel");
       return SD_OK;
