@@ -33,6 +33,44 @@ def test_line_struct_layout_matches_header():
     assert sum(8 if t == "int64_t" else 4 for t, _ in fields) == _lib.LINE_DTYPE.itemsize
 
 
+def test_resize_job_layout_and_plan():
+    """struct sd_resize_job == its numpy mirror, and segment.ResizePlan builds the table the kernel's contract asks
+    for: destination widths and slots of resize_to_height (common.py:89-91), every source image followed by at
+    least 8 readable bytes, 128-px lines left to the host pack."""
+    import torch
+    from stroke_derenderer_b200 import segment as S
+    hdr = (ROOT / "include" / "sd_b200.h").read_text()
+    body = hdr[hdr.index("typedef struct sd_resize_job {"):hdr.index("} sd_resize_job;")]
+    names = []
+    for t, decl in re.findall(r"\b(int64_t|int32_t)\s+([\w\s,]+);", body):
+        names += [(t, n.strip()) for n in decl.split(",")]
+    assert [n for _, n in names] == list(_lib.RESIZE_DTYPE.names)
+    assert sum(8 if t == "int64_t" else 4 for t, _ in names) == _lib.RESIZE_DTYPE.itemsize == 32
+    rng = np.random.default_rng(0)
+    shapes = [(200, 1000), (128, 700), (64, 300), (256, 1024), (37, 401)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    widths = [S.resized_width(im) for im in imgs]
+    assert widths == [O.resize_to_height(im, 128).shape[1] for im in imgs]
+    lines, plan = _lib.plan_lines(widths)
+    batch = S.LineBatch(torch.device("cpu"), lines, plan, torch.zeros(1, dtype=torch.uint8), widths)
+    rp = S.ResizePlan(imgs, batch, pinned=False)
+    jobs = rp.d_jobs.numpy().view(_lib.RESIZE_DTYPE)
+    assert rp.n == 4 and rp.max_dst_w == max(w for w, im in zip(widths, imgs) if im.shape[0] != 128)
+    todo = [i for i, im in enumerate(imgs) if im.shape[0] != 128]
+    end = 0
+    for jb, i in zip(jobs, todo):
+        im = imgs[i]
+        assert (int(jb["src_h"]), int(jb["src_w"]), int(jb["dst_w"])) == (im.shape[0], im.shape[1], widths[i])
+        assert int(jb["dst_off"]) == int(lines[i]["img_off"]) and int(jb["src_off"]) % 16 == 0 and int(jb["src_off"]) >= end
+        a = int(jb["src_off"])
+        assert np.array_equal(rp.h_src.numpy()[a:a + im.size], im.reshape(-1))
+        end = a + im.size + 8
+    assert rp.h_src.numel() >= end
+    packed = S.pack_lines_rgb(imgs, batch, pinned=False).numpy()
+    off = int(lines[1]["img_off"])
+    assert np.array_equal(packed[off:off + imgs[1].size], imgs[1].reshape(-1))
+
+
 def test_plan_lines_matches_oracle_geometry():
     widths = [1, 2, 100, 383, 384, 385, 639, 640, 1000, 1536, 3072, 6144, 16384, 20480, 21000, 32768]
     lines, plan = _lib.plan_lines(widths)
