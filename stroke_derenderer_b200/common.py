@@ -25,30 +25,26 @@ def save_image(img, save_filepath, grayscale=False):
     cv2.imwrite(save_filepath, cv2.cvtColor(img, code))
 
 
-def save_metrics(metrics, filename):
-    with open(filename, "wb") as fid:
-        pickle.dump(metrics, fid)
+def _dump(obj, path, mode, writer):
+    with open(path, mode) as fh:
+        writer(obj, fh)
 
 
-def load_metrics(filename):
-    with open(filename, "rb") as f:
-        return pickle.load(f)
+def _read(path, mode, reader):
+    with open(path, mode) as fh:
+        return reader(fh)
+
+
+# common.py:37-82: the pickle / YAML / JSON one-liners the sessions and scripts import by name
+def save_metrics(metrics, filename): _dump(metrics, filename, "wb", pickle.dump)
+def load_metrics(filename): return _read(filename, "rb", pickle.load)
+def load_json(json_path): return _read(json_path, "r", json.load)
+def save_json(json_dict, save_path): _dump(json_dict, save_path, "w", json.dump)
 
 
 def load_yaml(filepath):
-    import yaml
-    with open(filepath, "r") as stream:
-        return yaml.safe_load(stream)
-
-
-def load_json(json_path):
-    with open(json_path, "r") as f:
-        return json.load(f)
-
-
-def save_json(json_dict, save_path):
-    with open(save_path, "w") as out:
-        json.dump(json_dict, out)
+    import yaml                      # only needed by the training-side scripts
+    return _read(filepath, "r", yaml.safe_load)
 
 
 def resize_to_height(img, height):
