@@ -65,6 +65,14 @@ typedef struct sd_plan {
   int32_t n_lines;
 } sd_plan;
 
+/* Where one tile's columns live in the packed line planes: column c < width of tile row y goes to
+ * d_dst[y * pitch + c].  Filled by sd_tile_dst_table; consumed by sd_unet_forward_lines. */
+typedef struct sd_tile_dst {
+  uint8_t* d_dst;     /* device address of (row 0, first covered column) in the line's mask plane */
+  int32_t pitch;      /* sd_line.pitch                                                            */
+  int32_t width;      /* un-padded tile width (helper/split.py:31-34; <= tile_w)                   */
+} sd_tile_dst;
+
 /* Conv slots of the Attention-UNet (folded conv+BN), in execution order.
  * Weights are handed over as fp32 OIHW + fp32 bias; the library packs them. */
 enum sd_slot {
@@ -117,6 +125,11 @@ int64_t sd_group_lines(const int32_t* h_stats, const int64_t* h_stat_off, const 
                        int n_lines, const int64_t* h_order, int margin, int img_h, int64_t target_w,
                        int64_t* h_groups, int32_t* h_group_of, int64_t* h_line_group_start,
                        int64_t* h_canvas_bytes);
+
+/* Host: one sd_tile_dst per tile of the batch (stack order) for planes that start at device address
+ * d_planes_base: the paste positions of reconstruct_images (helper/split.py:109-119: tile k of a line
+ * lands at column k * wu with its un-padded width). */
+int sd_tile_dst_table(const sd_line* h_lines, int n_lines, uint8_t* d_planes_base, sd_tile_dst* h_out);
 
 /* ---- bandwidth-bound device stages --------------------------------------- */
 /* K1a: split_image + pad_image + HWC->CHW stack (helper/split.py:10-54,81-84):
@@ -206,6 +219,13 @@ int sd_engine_set_head_bias(sd_engine* e, float bias);
  * d_prob_f16: same in fp16; d_mask_u8: 255 * (prob > bin_thr). */
 int sd_unet_forward(sd_engine* e, const void* d_tiles_nhwc8, int n_tiles, float bin_thr,
                     float* d_prob_f32, void* d_prob_f16, uint8_t* d_mask_u8, void* stream);
+/* The same forward with reconstruct_images (helper/split.py:89-124) + both thresholds
+ * (evaluate_binarize.py:103, main.py:108) fused into the head: every tile ORs 255 * (prob > bin_thr) for its
+ * un-padded columns straight into the packed line planes named by d_dst (one entry per tile, same order as
+ * d_tiles).  The planes must be ZERO before the first tile of a line is processed (cudaMemsetAsync on the
+ * same stream); tiles of one line may arrive in different calls. */
+int sd_unet_forward_lines(sd_engine* e, const void* d_tiles_nhwc8, int n_tiles, float bin_thr,
+                          const sd_tile_dst* d_dst, void* stream);
 /* Copies an intermediate activation of the last forward (NHWC fp16) into
  * d_out; returns channels via *c, spatial dims via *h,*w. */
 int sd_unet_read_tap(sd_engine* e, int tap, int n_tiles, void* d_out, size_t out_bytes,

@@ -52,6 +52,7 @@ EXPORTS = {
     "sd_cuda_available": (C.c_int, []),
     "sd_launch_count": (C.c_int64, []),
     "sd_plan_lines": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Plan)]),
+    "sd_tile_dst_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_group_intervals": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "sd_group_lines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -77,6 +78,7 @@ EXPORTS = {
     "sd_engine_set_head_bias": (C.c_int, [C.c_void_p, C.c_float]),
     "sd_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "sd_unet_forward_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "sd_unet_read_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "sd_engine_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
@@ -128,6 +130,20 @@ def plan_lines(widths, tile_w: int = 384, overlap: int = 64):
     plan = Plan()
     check(lib().sd_plan_lines(w.ctypes.data, len(w), tile_w, overlap, lines.ctypes.data, C.byref(plan)), "sd_plan_lines")
     return lines, plan
+
+
+# numpy mirror of `struct sd_tile_dst`
+TILE_DST_DTYPE = np.dtype([("d_dst", "<u8"), ("pitch", "<i4"), ("width", "<i4")], align=True)
+assert TILE_DST_DTYPE.itemsize == 16
+
+
+def tile_dst_table(lines, planes_ptr: int):
+    """-> structured array (n_tiles,) of sd_tile_dst for planes starting at device address `planes_ptr`."""
+    n_tiles = int(lines["n_tiles"].sum()) if len(lines) else 0
+    out = np.zeros(max(n_tiles, 1), dtype=TILE_DST_DTYPE)
+    lines = np.ascontiguousarray(lines)
+    check(lib().sd_tile_dst_table(lines.ctypes.data, len(lines), planes_ptr, out.ctypes.data), "sd_tile_dst_table")
+    return out[:n_tiles]
 
 
 def group_intervals(intervals, width: int):

@@ -57,6 +57,7 @@ struct ConvParams {
   const float* head_w;         // [cout]
   float head_b, thr;
   float* prob_f32; __half* prob_f16; uint8_t* mask_u8;
+  const sd_tile_dst* tile_dst; // head: per tile, where its columns live in the packed line planes (glue fused into the head)
   int* err_flag;               // set when a barrier wait times out
 };
 
@@ -465,8 +466,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
           for (int j = 0; j < 32; ++j) {
             float a = v[j] + s_bias[c * 32 + j];
             if (EPI == EPI_GATE || p.relu) a = fmaxf(a, 0.f);
-            // head: the unfused graph stores d2 in fp16 before the 1x1 conv; keep that rounding point
-            if (EPI == EPI_HEAD) a = __half2float(__float2half_rn(a));
             dot = fmaf(a, s_vec[c * 32 + j], dot);
           }
         }
@@ -540,6 +539,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             if (p.prob_f32) p.prob_f32[pix] = pr;
             if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
             if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
+            if (p.tile_dst && pr > p.thr) {            // glue: OR into the pre-zeroed line plane
+              const sd_tile_dst td = p.tile_dst[n];
+              if (x < td.width) td.d_dst[(int64_t)y * td.pitch + x] = 255;
+            }
           }
         }
       }
@@ -1012,6 +1015,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
       const int sx = w % segs; int rest = w / segs;
       const int b = rest % bands; const int n = rest / bands;
       const int y0 = b * kBandRows, y1 = min(y0 + kBandRows, p.H);
+      uint8_t* line_dst = nullptr; int line_pitch = 0;
+      if (EPI == EPI_HEAD && p.tile_dst) {              // this tile's columns in the packed line planes
+        const sd_tile_dst td = p.tile_dst[n];
+        if (sx * 128 + row < td.width) { line_dst = td.d_dst + sx * 128 + row; line_pitch = td.pitch; }
+      }
       for (int y = y0; y < y1; ++y, ++g) {
         const int slot = g & 7;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64);
@@ -1073,8 +1081,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
             tmem_st32_zero(taddr + c * 32);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float a = fmaxf(v[j] + p.bias_c[c * 32 + j], 0.f);
-              a = __half2float(__float2half_rn(a));
+              const float a = fmaxf(v[j] + p.bias_c[c * 32 + j], 0.f);   // stays fp32 into the 1x1 conv (the oracle is fp32)
               dot = fmaf(a, p.vec_c[c * 32 + j], dot);
             }
           }
@@ -1086,6 +1093,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
           if (p.prob_f32) p.prob_f32[pix] = pr;
           if (p.prob_f16) p.prob_f16[pix] = __float2half_rn(pr);
           if (p.mask_u8) p.mask_u8[pix] = pr > p.thr ? 255 : 0;
+          // glue fused into the head (helper/split.py:109-119): planes are pre-zeroed, every covering tile ORs its
+          // foreground pixels in; equal bytes from two tiles of an overlap are a benign race
+          if (line_dst && pr > p.thr) line_dst[(int64_t)y * line_pitch] = 255;
         }
       }
     }

@@ -200,12 +200,13 @@ __global__ void __launch_bounds__(64) glue_kernel(
     if (x0 < ln.width) {
       const int xl = min(x0 + 15, ln.width - 1);
       const int iA = (ln.n_tiles == 1) ? 0 : min(xl / ln.wu, ln.n_tiles - 1);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      // every tile that covers the run: two at the default 384 / 64 geometry (wu >= 192 > overlap), more when
+      // overlap > wu (helper/split.py accepts any 0 <= overlap < tile_w)
+      for (int t = 0; t <= iA; ++t) {
         const int i = iA - t;
-        if (i < 0) break;
         const int start = (ln.n_tiles == 1) ? 0 : i * ln.wu;
         const int wd = tile_width(ln, i);
+        if (start + wd <= x0) break;                  // tile ends left of the run; so do all earlier tiles
         // valid run positions k: 0 <= x0 + k - start < wd  and x0 + k < W
         const int lo = max(0, start - x0), hi = min(min(16, start + wd - x0), ln.width - x0);
         if (lo >= hi) continue;
@@ -1020,6 +1021,22 @@ extern "C" int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, i
   return SD_OK;
 }
 
+extern "C" int sd_tile_dst_table(const sd_line* h_lines, int n_lines, uint8_t* d_planes_base, sd_tile_dst* h_out) {
+  SD_REQUIRE(n_lines >= 0 && (n_lines == 0 || (h_lines && h_out)), "sd_tile_dst_table: null argument");
+  for (int l = 0; l < n_lines; ++l) {
+    const sd_line& ln = h_lines[l];
+    for (int i = 0; i < ln.n_tiles; ++i) {
+      const int start = ln.n_tiles == 1 ? 0 : i * ln.wu;            // helper/split.py:119: s += width_k - overlap == k * wu
+      int end = ln.n_tiles == 1 ? ln.width : std::min((i + 1) * ln.wu + ln.overlap, ln.width);
+      sd_tile_dst& t = h_out[ln.first_tile + i];
+      t.d_dst = d_planes_base + ln.px_off + start;
+      t.pitch = ln.pitch;
+      t.width = std::min(end - start, ln.tile_w);
+    }
+  }
+  return SD_OK;
+}
+
 namespace sd {
 // group_intervals + group_connections + add_to_group (helper/partition.py:248-358).
 // iv: n pairs (a,b) sorted by a.  Appends member indices to `members`, group ends to `ends`.
@@ -1225,7 +1242,7 @@ static int ccl_label_grid() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_strip_label_kernel, 256, 0);
     grid = sms * (per_sm > 0 ? per_sm : 1);
-    if (const char* g = getenv("SD_CCL_GRID")) grid = atoi(g);      // debug: e.g. a huge value = one strip per CTA
+    if (const char* g = getenv("SD_CCL_GRID")) grid = std::max(atoi(g), 1);   // debug: e.g. a huge value = one strip per CTA
   }
   return grid;
 }

@@ -237,6 +237,7 @@ struct sd_engine {
   // per-call outputs (captured by the head op)
   const void* in_tiles = nullptr;
   float thr = 0.5f; float* o32 = nullptr; __half* o16 = nullptr; uint8_t* omask = nullptr;
+  const sd_tile_dst* odst = nullptr;   // head writes straight into the packed line planes (sd_unet_forward_lines)
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -254,6 +255,13 @@ struct sd_engine {
 };
 
 namespace sd {
+
+// the C ABI never leaves the caller's current device changed (a process may drive several GPUs)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int dev_alloc(sd_engine* e, void** p, size_t bytes) {
   SD_CUDA_CHECK(cudaMalloc(p, bytes));
@@ -479,7 +487,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.B = B;
       if (epi == EPI_HEAD) {
         p.head_b = e->head_b; p.thr = e->thr;
-        p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
+        p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask; p.tile_dst = e->odst;
       }
       const int n_work = B * ((H + kBandRows - 1) / kBandRows) * segs;
       return dispatch_band(p, cb, epi, n_work < nsm ? n_work : nsm, s);
@@ -596,7 +604,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     p.m_tiles = per_img * ((B + box_n - 1) / box_n);
     if (epi == EPI_HEAD) {
       p.head_b = e->head_b; p.thr = e->thr;
-      p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask;
+      p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask; p.tile_dst = e->odst;
     }
     if (cta2) return launch_conv2(p, nsm, s);
     const int n_work = ((p.m_tiles + mt - 1) / mt) * p.n_tiles * p.n_phases;
@@ -658,7 +666,6 @@ extern "C" int sd_engine_create(int device, int max_tiles, int tile_h, int tile_
     return SD_ECUDA;
   }
   SD_REQUIRE(device >= 0 && device < ndev, "sd_engine_create: device %d of %d", device, ndev);
-  SD_CUDA_CHECK(cudaSetDevice(device));
   cudaDeviceProp prop;
   SD_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -674,7 +681,7 @@ extern "C" int sd_engine_create(int device, int max_tiles, int tile_h, int tile_
 
 extern "C" void sd_engine_destroy(sd_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceGuard guard(e->device);
   for (void* p : e->allocs) cudaFree(p);
   if (e->err_flag_host) cudaFreeHost(e->err_flag_host);
   for (auto ev : e->ev) cudaEventDestroy(ev);
@@ -701,7 +708,7 @@ extern "C" int sd_engine_set_head_bias(sd_engine* e, float bias) {
 extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   SD_REQUIRE(e && !e->finalized, "sd_engine_finalize: bad state");
   SD_REQUIRE(impl == 0 || impl == 1, "sd_engine_finalize: impl %d", impl);
-  SD_CUDA_CHECK(cudaSetDevice(e->device));
+  DeviceGuard guard(e->device);
   // expected shapes
   static const int exp_shape[SD_NUM_SLOTS][3] = {
       {64, 3, 3}, {64, 64, 3}, {128, 64, 3}, {128, 128, 3}, {256, 128, 3}, {256, 256, 3}, {512, 256, 3}, {512, 512, 3},
@@ -971,19 +978,27 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   return SD_OK;
 }
 
-extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, float bin_thr, float* d_prob_f32,
-                               void* d_prob_f16, uint8_t* d_mask_u8, void* stream) {
+static int unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, float bin_thr, float* d_prob_f32, void* d_prob_f16,
+                        uint8_t* d_mask_u8, const sd_tile_dst* d_dst, void* stream) {
   SD_REQUIRE(e && e->finalized, "sd_unet_forward: engine not finalized");
   SD_REQUIRE(n_tiles >= 0 && n_tiles <= e->max_tiles, "sd_unet_forward: n_tiles %d exceeds max_tiles %d", n_tiles, e->max_tiles);
   if (n_tiles == 0) return SD_OK;   // evaluate_binarize.py:93-100 feeds an empty last minibatch when B % 8 == 0
   SD_REQUIRE(d_tiles, "sd_unet_forward: null input");
+  SD_REQUIRE(!d_dst || e->impl == 0, "sd_unet_forward_lines: the debug implementation has no fused glue");
   cudaStream_t s = (cudaStream_t)stream;
   e->in_tiles = d_tiles; e->thr = bin_thr;
-  e->o32 = d_prob_f32; e->o16 = reinterpret_cast<__half*>(d_prob_f16); e->omask = d_mask_u8;
+  e->o32 = d_prob_f32; e->o16 = reinterpret_cast<__half*>(d_prob_f16); e->omask = d_mask_u8; e->odst = d_dst;
   for (size_t i = 0; i < e->ops.size(); ++i) {
     if (e->timing) SD_CUDA_CHECK(cudaEventRecord(e->ev[i], s));
     int r = e->ops[i].run(n_tiles, s);
-    if (r) return r;
+    if (r) {
+      // a trapped kernel (bounded mbarrier wait) surfaces as a sticky CUDA error at the next call: name the wait
+      if (r == SD_ECUDA && e->err_flag_host && *e->err_flag_host) {
+        std::string msg = sd_last_error();
+        set_error("%s [tcgen05 barrier timeout, wait code %d]", msg.c_str(), *e->err_flag_host);
+      }
+      return r;
+    }
 #ifdef SD_CONV_STATS
     if (e->timing) {   // debug build: per-op mbarrier wait cycles, printed as JSON lines on stderr
       unsigned long long wc[8];
@@ -1005,6 +1020,17 @@ extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, f
     SD_REQUIRE(flag == 0, "sd_unet_forward: kernel barrier timeout (code %d)", flag);
   }
   return SD_OK;
+}
+
+extern "C" int sd_unet_forward(sd_engine* e, const void* d_tiles, int n_tiles, float bin_thr, float* d_prob_f32,
+                               void* d_prob_f16, uint8_t* d_mask_u8, void* stream) {
+  return unet_forward(e, d_tiles, n_tiles, bin_thr, d_prob_f32, d_prob_f16, d_mask_u8, nullptr, stream);
+}
+
+extern "C" int sd_unet_forward_lines(sd_engine* e, const void* d_tiles, int n_tiles, float bin_thr, const sd_tile_dst* d_dst,
+                                     void* stream) {
+  SD_REQUIRE(d_dst || n_tiles == 0, "sd_unet_forward_lines: null destination table");
+  return unet_forward(e, d_tiles, n_tiles, bin_thr, nullptr, nullptr, nullptr, d_dst, stream);
 }
 
 extern "C" int sd_unet_read_tap(sd_engine* e, int tap, int n_tiles, void* d_out, size_t out_bytes, int* c, int* h, int* w,

@@ -118,6 +118,15 @@ class UNetEngine:
         _lib.check(_lib.lib().sd_unet_forward(self._h, tiles.data_ptr(), n, float(bin_thr), None, None,
                                               mask_out.data_ptr(), stream_ptr(self.device)), "sd_unet_forward")
 
+    def forward_lines(self, tiles: torch.Tensor, d_dst: torch.Tensor, bin_thr: float = 0.5):
+        """Forward with the glue fused into the head (sd_unet_forward_lines): tile k ORs its thresholded,
+        un-padded columns into the packed line planes named by entry k of `d_dst` (uint8 view of an
+        sd_tile_dst table on this GPU).  The planes must have been zeroed on the same stream."""
+        n = tiles.shape[0]
+        assert d_dst.dtype == torch.uint8 and d_dst.numel() >= 16 * n
+        _lib.check(_lib.lib().sd_unet_forward_lines(self._h, tiles.data_ptr(), n, float(bin_thr), d_dst.data_ptr(),
+                                                    stream_ptr(self.device)), "sd_unet_forward_lines")
+
     def read_tap(self, name: str, n: int) -> torch.Tensor:
         """Intermediate activation of the last forward as (n, H, W, C) fp16."""
         L = _lib.lib()

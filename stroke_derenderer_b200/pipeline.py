@@ -98,10 +98,10 @@ class LineSegmentationJob:
             # one tile stack for the whole job: UNet batches run across chunk boundaries, so only the
             # last batch of the job is partial
             self.tiles = torch.empty((max(t0, 1), TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
-            self.masks = torch.empty((max(t0, 1), TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+            # job-wide sd_tile_dst table: tile k of the stack pastes into its chunk's planes (glue fused into the head)
+            self.dst = torch.cat([ch.batch.tile_dst(ch.planes) for ch in self.chunks]) if self.chunks else None
             for ch in self.chunks:
                 ch.tiles = self.tiles[ch.t0:ch.t1]
-                ch.masks = self.masks[ch.t0:ch.t1]
         self.n_tiles = sum(c.batch.n_tiles for c in self.chunks)
         self.n_lines = sum(c.batch.n_lines for c in self.chunks)
 
@@ -127,15 +127,16 @@ class LineSegmentationJob:
                     if from_host:
                         ch.resize.run(src)
                     S.tile_extract_f16(ch.batch, src, out=ch.tiles)
+                    ch.planes.zero_()                 # the head ORs foreground bytes into the planes
                     last = k == len(self.chunks) - 1
                     while done + mt <= ch.t1 or (last and done < ch.t1):
                         n = min(mt, self.n_tiles - done)
-                        self.engine.forward_into(self.tiles[done:done + n], self.masks[done:done + n], self.seg.bin_thr)
+                        self.engine.forward_lines(self.tiles[done:done + n], self.dst[16 * done:16 * (done + n)], self.seg.bin_thr)
                         done += n
-                    while glued < len(self.chunks) and self.chunks[glued].t1 <= done:
-                        g = self.chunks[glued]
-                        S.glue_u8(g.batch, g.masks, out=g.planes)
-                        ev = torch.cuda.Event(); ev.record(self.s_unet)
+                    ev = None
+                    while glued < len(self.chunks) and self.chunks[glued].t1 <= done:   # chunks whose last tile is through
+                        if ev is None:
+                            ev = torch.cuda.Event(); ev.record(self.s_unet)
                         ready[glued] = ev
                         glued += 1
             results = []

@@ -46,6 +46,11 @@ class LineBatch:
         off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
         return buf[off:off + TILE_H * pitch].view(TILE_H, pitch)[:, :w]
 
+    def tile_dst(self, planes: torch.Tensor) -> torch.Tensor:
+        """Device sd_tile_dst table (uint8 view, 16 B per tile) that pastes this batch's tiles into `planes`."""
+        tab = _lib.tile_dst_table(self.lines, planes.data_ptr())
+        return torch.from_numpy(tab.view(np.uint8).reshape(-1).copy()).to(self.device, non_blocking=True)
+
     # bookkeeping lists of cut_and_stack (helper/split.py:66-78)
     def stack_indices(self):
         return [list(range(int(l["first_tile"]), int(l["first_tile"] + l["n_tiles"]))) for l in self.lines]
@@ -382,11 +387,13 @@ class Segmenter:
             elif d_rgb is None:
                 d_rgb = pack_lines_rgb(images, batch).to(self.device, non_blocking=True)
             tiles = tile_extract_f16(batch, d_rgb)
-            masks = torch.empty((batch.n_tiles, TILE_H, TILE_W), dtype=torch.uint8, device=self.device)
+            # reconstruct_images (helper/split.py:89-124) is fused into the UNet head: tiles OR their thresholded
+            # columns straight into the zeroed line planes, no tile-shaped mask and no glue pass exist
+            planes = torch.zeros(batch.px_total, dtype=torch.uint8, device=self.device)
+            dst = batch.tile_dst(planes)
             mt = self.engine.max_tiles
             for s in range(0, batch.n_tiles, mt):
-                self.engine.forward_into(tiles[s:s + mt], masks[s:s + mt], self.bin_thr)
-            planes = glue_u8(batch, masks)
+                self.engine.forward_lines(tiles[s:s + mt], dst[16 * s:16 * (s + mt)], self.bin_thr)
         return batch, planes
 
     def partition(self, batch: LineBatch, planes: torch.Tensor, canvases: str = "host", key="part",

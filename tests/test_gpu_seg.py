@@ -97,6 +97,29 @@ def test_glue_random_values_and_threshold(cuda_device):
         assert np.array_equal(batch.plane(pl, i).cpu().numpy(), ref[i][:, :, 0]), widths[i]
 
 
+def test_glue_large_overlap_three_or_more_covering_tiles(cuda_device):
+    """helper/split.py accepts any 0 <= overlap < tile_w; at overlap 200 / 300 a column is covered by 3 / 5 tiles and
+    reconstruct_images takes the max over all of them (glue used to look at two tiles only)."""
+    rng = np.random.default_rng(23)
+    for overlap in (0, 64, 200, 300, 380):
+        widths = [384, 500, 1000, 2000, 777]
+        batch = S.plan_batch(widths, torch.device("cuda", 0), overlap=overlap)
+        vals = rng.integers(0, 256, (batch.n_tiles, 1, 128, 384), dtype=np.uint8)
+        planes = S.glue_u8(batch, torch.from_numpy(vals[:, 0]).cuda().contiguous())
+        ref = O.reconstruct_images(vals, widths, batch.stack_indices(), batch.stack_widths(), overlap)
+        for i, w in enumerate(widths):
+            assert ref[i].shape[1] == w
+            assert np.array_equal(batch.plane(planes, i).cpu().numpy(), ref[i][:, :, 0]), (overlap, w)
+        # the paste table of the fused head names the same positions
+        tab = __import__("stroke_derenderer_b200._lib", fromlist=["x"]).tile_dst_table(batch.lines, 0)
+        k = 0
+        for ln, ws in zip(batch.lines, batch.stack_widths()):
+            for i, wd in enumerate(ws):
+                start = 0 if int(ln["n_tiles"]) == 1 else i * int(ln["wu"])
+                assert int(tab[k]["d_dst"]) == int(ln["px_off"]) + start and int(tab[k]["width"]) == min(wd, 384) and int(tab[k]["pitch"]) == int(ln["pitch"])
+                k += 1
+
+
 def test_cut_identity_glue_roundtrip_full_size(cuda_device):
     """Size-independent property at BASELINE config-3 scale: cut -> identity on channel 0 -> glue == input."""
     widths = config_widths(64)
