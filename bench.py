@@ -161,6 +161,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from stroke_derenderer_b200 import _lib
     from stroke_derenderer_b200.engine import UNetEngine
+    from stroke_derenderer_b200 import gather as G
     from stroke_derenderer_b200.pipeline import LineSegmentationJob, shard_lines
     from stroke_derenderer_b200.synth import config_widths
 
@@ -178,12 +179,45 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
 
-    n_total = LINES_PER_GPU * world
+    strong = args.lines_total > 0                       # fixed total work (BASELINE config 4: 4096 lines) instead of 512 per GPU
+    n_total = args.lines_total if strong else LINES_PER_GPU * world
     widths = config_widths(n_total)
-    mine = shard_lines(widths, world)[rank]
+    shards = shard_lines(widths, world)
+    mine = shards[rank]
     images = make_lines(mine, widths)
     engine = UNetEngine(parity_state(), device=local, max_tiles=args.max_tiles)
     job = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops)
+    # the end-to-end job starts from the plain numpy images (packing inside the step) and gathers on the host:
+    # every rank's D2H copies land in its page-locked region of one /dev/shm arena, rank 0 reads all lines in input order
+    job_e2e = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops, prepack=False)
+    caps = torch.tensor([job_e2e.arena_bytes() if r == rank else 0 for r in range(world)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(caps, op=dist.ReduceOp.SUM)
+    caps = [int(v) for v in caps.tolist()]
+    arena_name = f"sd_b200_gather_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}"
+    arena = G.ResultArena(arena_name, caps, rank, create=True) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    if arena is None:
+        arena = G.ResultArena(arena_name, caps, rank, create=False)
+    arena.register()
+    writer = G.RegionWriter(arena.region(rank), max(len(job_e2e.chunks), 1))
+    gather_ms = []
+
+    def e2e_step():
+        res = job_e2e.host_step(writer)                  # ends with a stream synchronize: this rank's bytes are in the arena
+        if world > 1:
+            dist.barrier()
+        if rank == 0:                                    # the caller now holds every line, in input order
+            t0 = time.perf_counter()
+            got = G.GatheredResults(arena, shards, widths, args.lines_per_chunk, step=writer.step)
+            probe = (0, n_total // 2, n_total - 1)
+            e2e_step.check = [(int(got.mask(i).shape[1]), got.num(i), int(got.crops(i).shape[0])) for i in probe]
+            gather_ms.append(1e3 * (time.perf_counter() - t0))
+            del got
+        if world > 1:
+            dist.barrier()                               # readers are done before the next step reuses the arena
+        return res
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,9 +258,10 @@ def run_gpu(args):
     launches = _lib.lib().sd_launch_count() - l0
     keep = None
     for _ in range(3):
-        keep = job.host_step()
+        keep = e2e_step()
     keep = None
-    ms_e2e, res = timed(job.host_step, args.steps)
+    gather_ms.clear()
+    ms_e2e, res = timed(e2e_step, args.steps)
     if os.environ.get("SD_BENCH_PROFILE"):             # one more resident step inside a profiler window (ncu launch list)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -237,7 +272,7 @@ def run_gpu(args):
     if not args.no_clock_sampler:
         sampler.join(timeout=2)
 
-    counts = torch.tensor([job.n_tiles, job.n_lines, job.h2d_bytes(), job.d2h_bytes(res), launches], dtype=torch.int64, device="cuda")
+    counts = torch.tensor([job.n_tiles, job.n_lines, job_e2e.h2d_bytes(), job_e2e.d2h_bytes(res), launches], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     tiles, lines, h2d, d2h, launches_all = (int(v) for v in counts.tolist())
@@ -275,18 +310,23 @@ def run_gpu(args):
         ach = GFLOP_PER_TILE * 1e9 * nb / (conv_ms / 1e3) / 1e12
         ach_burst = GFLOP_PER_TILE * 1e9 * nb / (umma_ms / 1e3) / 1e12
         traffic = None
-        tp = ROOT / "profiles" / "r01_conv_traffic.json"      # dram bytes of the same launches from one ncu --set full capture
-        if tp.exists():
+        traffic_src = None
+        for tp in (ROOT / "profiles" / "r02_conv_traffic.json", ROOT / "profiles" / "r01_conv_traffic.json"):
+            if not tp.exists():                      # dram bytes of the same launches from one ncu --set full capture
+                continue
             try:
-                tj = json.loads(tp.read_text())     # captured on a 128-tile pass; DRAM bytes scale with the tiles of a pass
-                traffic = tj["dram_bytes_per_launch"] * nb / tj.get("tiles_per_pass", 128)
+                tj = json.loads(tp.read_text())
+                cap_tiles = tj.get("tiles_per_pass", 128)
+                traffic = tj["dram_bytes_per_launch"] * nb / cap_tiles
+                traffic_src = f"{tp.name}: ncu --set full over a {cap_tiles}-tile pass" + ("" if cap_tiles == nb else f", scaled to {nb} tiles")
+                break
             except Exception:
                 traffic = None
         roof = {"bound": "tensor",
                 "kernel": f"tcgen05 conv family (conv_umma / conv_band / conv_first kernels: the {n_conv} conv, gate and head launches of one UNet pass)",
                 "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
                 "peak_source": peaks["source"] + ": sustained fp16/bf16 GEMM, because the passes are timed inside a long run",
-                "traffic": traffic, "launch_ms": conv_ms / n_conv, "launches_per_pass": n_conv, "pass_ms": pass_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "launch_ms": conv_ms / n_conv, "launches_per_pass": n_conv, "pass_ms": pass_ms,
                 "tiles_per_pass": nb, "algorithmic_gflop_per_tile": GFLOP_PER_TILE, "executed_gflop_per_tile": 83.53,
                 "burst": {"achieved": ach_burst, "peak": peaks["tflops_burst"], "frac": ach_burst / peaks["tflops_burst"],
                           "pass_ms": all_ms, "note": "each launch timed alone between CUDA events (clocks not power-capped)"}}
@@ -347,25 +387,81 @@ def run_gpu(args):
                "lines_per_s": t_lines / dt,
                "sample": desc + "; reference Python algorithm + torch-CPU fp32 stand-in for onnxruntime-CPU (absent offline)"}
 
+    api = fused_api = parity = None
+    if rank == 0 and not args.no_api:
+        # The reference-signature calls on plain (unpinned) numpy lists, rank 0's lines on its GPU:
+        #   masks = BinarizationSession.binarize_images(images, ort)      evaluate_binarize.py:130-140
+        #   img_bin = mask[:, :, 0] > 255 * bin_thr                       main.py:108
+        #   parts = StrokeEstimationSession.get_partitions_batch(...)     evaluate_strokes.py:186-224 per line
+        from stroke_derenderer_b200.evaluate_binarize import BinarizationSession
+        from stroke_derenderer_b200.evaluate_strokes import StrokeEstimationSession
+        from stroke_derenderer_b200.pipeline import segment_lines
+        bs = BinarizationSession(max_tiles=args.max_tiles, lines_per_chunk=args.lines_per_chunk, device=local)
+        se = StrokeEstimationSession(device=local)
+
+        def api_call():
+            masks = bs.binarize_images(images, engine)
+            bins = [m[:, :, 0] > (255 * bs.bin_thr) for m in masks]
+            parts = se.get_partitions_batch(bins)
+            return masks, parts
+        api_call()
+        t_api = []
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            m_api, p_api = api_call()
+            torch.cuda.synchronize(); t_api.append(time.perf_counter() - t0)
+        n_parts = sum(len(p) for p in p_api)
+        api = {"value": job.n_tiles / min(t_api), "unit": "tiles/s", "ms_per_call": 1e3 * min(t_api), "lines": len(images),
+               "partitions": n_parts, "what": "binarize_images(list of numpy) + main.py:108 threshold + get_partitions_batch(list of numpy), "
+               "fresh per-line arrays; image_input of a partition is materialised lazily on first access (f32 crops = 12x the u8 bytes)",
+               "vs_e2e_rank0": (job.n_tiles / min(t_api)) / (job.n_tiles * args.steps / (ms_e2e / 1e3))}
+        del m_api, p_api
+        segment_lines(engine, images, lines_per_chunk=args.lines_per_chunk)
+        t_f = []
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            segment_lines(engine, images, lines_per_chunk=args.lines_per_chunk)
+            torch.cuda.synchronize(); t_f.append(time.perf_counter() - t0)
+        fused_api = {"value": job.n_tiles / min(t_f), "unit": "tiles/s", "ms_per_call": 1e3 * min(t_f),
+                     "what": "pipeline.segment_lines(engine, list of numpy): one pipelined call, job construction and fresh per-line outputs included"}
+        # parity of BASELINE config 1 against the committed golden (oracle = torch-CPU fp32, UNPINNED: no onnxruntime offline)
+        gz = np.load(ROOT / "tests" / "golden" / "golden_arrays.npz")
+        x1 = np.random.default_rng(0).random((1, 3, 128, 384), dtype=np.float32)
+        pr = engine.run(None, {"input": x1})[0]
+        rf = gz["config1_prob"]
+        parity = {"config1_prob_max_abs": float(np.abs(pr - rf).max()), "prob_bar": 2e-2,
+                  "config1_mask_agree": float(((pr > 0.5) == (rf > 0.5)).mean()), "mask_bar": 0.999,
+                  "oracle": "torch-CPU fp32 of the published topology (parity unpinned: onnxruntime / the real graph are not available offline)",
+                  "line_images": "tests/test_gpu_parity.py: config 2 and a 77-tile config-3 sample, per-line minimum asserted >= 99.9 %"}
+
     if rank == 0:
         out = {
             "metric": "binarized_tiles_per_s", "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "lines_per_s": lines * args.steps / (ms_res / 1e3),
-            "config": {"workload": f"BASELINE config 3 per GPU: {LINES_PER_GPU} synthetic lines 128xW, W~U[1536,6144] "
-                                   f"({tiles} tiles over {world} GPU(s)); N=8 is config 4 (4096 lines)",
+            "config": {"workload": (f"BASELINE config 4, strong scaling: {n_total} synthetic lines 128xW, W~U[1536,6144] ({tiles} tiles) sharded over {world} GPU(s)"
+                                    if strong else
+                                    f"BASELINE config 3 per GPU: {LINES_PER_GPU} synthetic lines 128xW, W~U[1536,6144] "
+                                    f"({tiles} tiles over {world} GPU(s)); N=8 is config 4 (4096 lines)"),
                        "tile": "128x384, overlap 64", "unet_batch_tiles": args.max_tiles, "weights": "seeded parity init (random), fp16 operands / fp32 accumulate",
                        "cache": "inputs larger than L2 (>=760 MB of lines, >=9 GB of activations per pass); no L2 flush needed",
                        "parallelism": f"lines sharded over {world} GPU(s), no collective"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "lines_per_s": lines * args.steps / (ms_e2e / 1e3)},
+                    "ms_per_step": ms_e2e / args.steps, "lines_per_s": lines * args.steps / (ms_e2e / 1e3),
+                    "what": "per rank: plain numpy line images -> pack into page-locked staging -> H2D -> hot path -> D2H of masks, counts, "
+                            "stats, group tables, canvases and u8 crops straight into the rank's region of one /dev/shm arena; then "
+                            "rank 0 indexes all lines of all ranks in input order (host-side gather, no collective)",
+                    "gather": {"arena_bytes": int(sum(caps)), "rank0_index_ms": (sum(gather_ms) / len(gather_ms)) if gather_ms else None,
+                               "probe": getattr(e2e_step, "check", None)}},
+            "e2e_api": api, "e2e_fused_api": fused_api, "parity": parity,
             "gpu_launches": launches_all, "clocks": sampler.summary(),
         }
         out.update(extra)
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     engine.close()
+    arena.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -382,6 +478,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--no-crops", action="store_true", help="stop the step at the group canvases (no 224x224 crops)")
+    ap.add_argument("--no-api", action="store_true", help="skip the reference-signature API timing (e2e_api) on rank 0")
+    ap.add_argument("--lines-total", type=int, default=0,
+                    help="strong scaling: this many lines in total (4096 = BASELINE config 4) sharded over the GPUs, instead of 512 per GPU")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_gpu(args))
 

@@ -202,6 +202,14 @@ typedef struct sd_resize_job {
 int sd_resize_lines(const uint8_t* d_src, const sd_resize_job* d_jobs, int n_jobs, int max_dst_w,
                     uint8_t* d_rgb, void* stream);
 
+/* ---- host-side gather plumbing (results come back by D2H copies, no collective) ----------- */
+/* Page-locks caller memory (e.g. a /dev/shm mapping shared by the ranks of a job) so that D2H copies land in it
+ * directly at full PCIe rate; sd_host_unregister undoes it.  cudaHostRegister / cudaHostUnregister. */
+int sd_host_register(void* h_ptr, size_t bytes);
+int sd_host_unregister(void* h_ptr);
+/* cudaMemcpyAsync device -> host on `stream` (asynchronous only when h_dst is page-locked). */
+int sd_copy_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream);
+
 /* ---- Attention-UNet engine ------------------------------------------------ */
 /* Replaces onnxruntime.InferenceSession (evaluate_binarize.py:48-53) and its
  * .run() (:62, :100).  max_tiles bounds one sd_unet_forward call. */

@@ -49,25 +49,33 @@ def load_images(img_filepaths):
 
 
 def main(imgs, bs, ort_bs, se, orts_se, output_folder, strokes=True):
-    """main.py:91-136, segmentation part."""
+    """main.py:91-136, segmentation part.  The reference walks the images one at a time (:104); here ALL images of
+    the folder go through one pipelined job (tiles of different images share UNet passes), then the per-image
+    files are written exactly as the reference names them."""
+    from stroke_derenderer_b200 import segment as _seg
+    from stroke_derenderer_b200.pipeline import segment_lines
     Path(output_folder).mkdir(parents=True, exist_ok=True)
-    for img, filename in imgs:
-        start = time.time()
-        img_bin = bs.binarize_image(img, ort_bs)
-        img_bin = img_bin[:, :, 0] > (255 * bs.bin_thr)                    # main.py:108
-        t_bin = round(time.time() - start, 4)
+    images = [img for img, _ in imgs]
+    start = time.time()
+    default_se = (se.margin, se.img_size, list(se.mean), list(se.std)) == (_seg.MARGIN, _seg.IMG_SIZE, _seg.IMAGENET_MEAN, _seg.IMAGENET_STD)
+    if strokes and default_se and images:
+        masks, parts = segment_lines(ort_bs, images, bin_thr=bs.bin_thr, lines_per_chunk=bs.lines_per_chunk, seg=bs._segmenter(ort_bs))
+    else:
+        masks = bs.binarize_images(images, ort_bs)
+        parts = se.get_partitions_batch([m[:, :, 0] > (255 * bs.bin_thr) for m in masks]) if strokes else None
+    t_all = round(time.time() - start, 4)
+    print(f"{len(images)} images took {t_all} seconds to binarize" + (" and partition." if strokes else "."))
+    for k, (img, filename) in enumerate(imgs):
+        img_bin = masks[k][:, :, 0] > (255 * bs.bin_thr)                   # main.py:108
         bin_path = str(Path(output_folder) / f"{filename}_BINARIZED.png")
         save_image(normalize_image(img_bin.astype(np.uint8)), bin_path, grayscale=True)
-        print(f"{filename} took {t_bin} seconds to binarize. Result is saved to {bin_path}")
+        print(f"{filename}: result is saved to {bin_path}")
         if strokes:
-            start = time.time()
-            parts = se.get_partitions(img_bin)
-            t_se = round(time.time() - start, 4)
             out = [{"translate1": [int(p["translate1"][0]), int(p["translate1"][1])], "ratio": float(p["ratio"]),
-                    "translate2": [float(p["translate2"][0]), float(p["translate2"][1])]} for p in parts]
+                    "translate2": [float(p["translate2"][0]), float(p["translate2"][1])]} for p in parts[k]]
             path = str(Path(output_folder) / f"{filename}_PARTITIONS.json")
             save_json(out, path)
-            print(f"{filename} took {t_se} seconds to partition into {len(parts)} crops. Result is saved to {path}")
+            print(f"{filename}: {len(out)} crops, saved to {path}")
 
 
 if __name__ == "__main__":

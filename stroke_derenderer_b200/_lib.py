@@ -71,6 +71,9 @@ EXPORTS = {
     "sd_group_crops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "sd_resize_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sd_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "sd_host_unregister": (C.c_int, [C.c_void_p]),
+    "sd_copy_d2h_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sd_engine_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sd_engine_destroy": (None, [C.c_void_p]),
     "sd_engine_set_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -100,9 +103,7 @@ def lib() -> C.CDLL:
     """Loads (building first if needed) the native library; raises if impossible."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if not path.exists():
-            path = _build.build()
+        path = _build.build()          # no-op when the in-tree library matches the sources (digest stamp)
         handle = C.CDLL(str(path))
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)      # AttributeError if the symbol is missing

@@ -21,3 +21,20 @@ extern "C" int sd_cuda_available(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n > 0 ? 1 : 0;
 }
+
+extern "C" int sd_host_register(void* h_ptr, size_t bytes) {
+  SD_REQUIRE(h_ptr && bytes > 0, "sd_host_register: bad argument");
+  SD_CUDA_CHECK(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+  return SD_OK;
+}
+extern "C" int sd_host_unregister(void* h_ptr) {
+  SD_REQUIRE(h_ptr, "sd_host_unregister: null pointer");
+  SD_CUDA_CHECK(cudaHostUnregister(h_ptr));
+  return SD_OK;
+}
+extern "C" int sd_copy_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+  if (bytes == 0) return SD_OK;
+  SD_REQUIRE(h_dst && d_src, "sd_copy_d2h_async: null pointer");
+  SD_CUDA_CHECK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SD_OK;
+}

@@ -34,6 +34,7 @@ class BinarizationSession:
         self.minibatch = params.get("minibatch", MINIBATCH)
         self.device = params.get("device", 0)
         self.max_tiles = params.get("max_tiles", 64)
+        self.lines_per_chunk = params.get("lines_per_chunk", 32)
 
     def init_onnx_inference(self, onnxpath):
         """:48-53.  `onnxpath`: an exported `binarizer.onnx` (initializers read by `onnx_reader`, no
@@ -75,9 +76,23 @@ class BinarizationSession:
         but the input lines and the glued masks crosses PCIe."""
         if (self.height, self.width, self.overlap) != (HEIGHT, WIDTH, OVERLAP):
             raise ValueError("B200 path supports the default 128/384/64 geometry")
-        seg = _seg.Segmenter(ort, bin_thr=self.bin_thr)
-        batch, planes = seg.binarize(images)       # resize_to_height (:76) happens on the device, bit-exact with cv2
-        return [batch.plane(planes, i).cpu().numpy()[:, :, None].copy() for i in range(batch.n_lines)]
+        if not len(images):
+            return []
+        seg = self._segmenter(ort)
+        # chunks of lines flow through pack -> H2D -> cut -> UNet (glue fused) -> ONE D2H of the packed planes per
+        # chunk; resize_to_height (:76) happens on the device, bit-exact with cv2
+        from .pipeline import LineSegmentationJob
+        job = LineSegmentationJob(ort, images, bin_thr=self.bin_thr, lines_per_chunk=self.lines_per_chunk, crops=False,
+                                  prepack=False, seg=seg)
+        return job.binarize_step()
+
+    def _segmenter(self, ort):
+        """One Segmenter (streams' staging buffers) per engine, kept across calls."""
+        seg = getattr(ort, "_sd_segmenter", None)
+        if seg is None or seg.bin_thr != self.bin_thr:
+            seg = _seg.Segmenter(ort, bin_thr=self.bin_thr)
+            ort._sd_segmenter = seg
+        return seg
 
     def binarize_image(self, image, ort):
         """:143-150."""

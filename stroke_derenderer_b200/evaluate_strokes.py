@@ -9,7 +9,6 @@ import torch
 
 from . import segment as _seg
 from .common import load_json, normalize_image
-from .helper.partition import resize_and_pad_image
 
 # evaluate_strokes.py:24-31
 IMG_SIZE = 224
@@ -42,39 +41,61 @@ class StrokeEstimationSession:
         img_norm = normalize_image(img_bin.astype(np.uint8))
         return np.stack([(img_norm / 255. - self.mean[i]) / self.std[i] for i in range(3)], axis=0).astype(np.float32)
 
-    def partitions_from_canvases(self, canvases):
-        """:202-222 for one line's [(canvas, (top, left))]."""
-        parts = []
-        for img, (y, x) in canvases:
-            img_rs, ratio, (x2, y2) = resize_and_pad_image(normalize_image(img), self.tgt_shape, margin=1, pad_value=0)
-            parts.append({"image": img_rs, "image_input": self._normalize_image(img_rs),
-                          "translate1": (x, y), "ratio": ratio, "translate2": (x2, y2)})
-        return parts
-
     def get_partitions(self, img_bin):
         """:186-224 for one (128, W) binary image."""
         return self.get_partitions_batch([img_bin])[0]
 
-    def get_partitions_batch(self, imgs_bin):
-        """Many lines in one device pass (CCL, stats, canvases batched)."""
+    def _segmenter(self):
         dev = torch.device("cuda", self.device)
+        seg = getattr(self, "_seg_obj", None)
+        if seg is None or seg.margin != self.margin:
+            seg = self._seg_obj = _seg.Segmenter(None, margin=self.margin, device=dev)
+        return seg
+
+    def get_partitions_batch(self, imgs_bin, lines_per_chunk: int = 64, keep_device: bool = False):
+        """Many lines in one pipelined device pass: per chunk of lines one H2D of the packed masks, CCL, stats,
+        clustering, canvases and the 224x224 crops (sd_group_crops: cv2.normalize / cv2.resize / pad bit for bit),
+        one D2H of the u8 crops.  -> per line the list of partition dicts of :213-219; `image_input` is built on
+        first access (segment.LazyPartition), or stays on the GPU for the stroke-estimator front end
+        (`keep_device=True` adds `self.last_device_crops`: per chunk the (g, 3, size, size) f32 tensor)."""
+        if self.img_size % 2 or self.img_size > 256:
+            raise ValueError(f"B200 crop kernel supports even image sizes up to 256, got {self.img_size} (no CPU fallback)")
+        seg = self._segmenter()
+        dev = seg.device
+        lut = _seg.input_lut(self.mean, self.std)
+        out = []
+        self.last_device_crops = []
         with torch.cuda.device(dev):
-            batch = _seg.plan_batch([m.shape[1] for m in imgs_bin], dev)
-            host = np.zeros(batch.px_total, np.uint8)
-            for m, ln in zip(imgs_bin, batch.lines):
-                off, pitch = int(ln["px_off"]), int(ln["pitch"])
-                host[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)[:, :m.shape[1]] = np.asarray(m) != 0
-            planes = torch.from_numpy(host).to(dev)
-            if self.img_size % 2 or self.img_size > 256:
-                res = _seg.Segmenter(None, margin=self.margin, device=dev).partition(batch, planes)
-                return [self.partitions_from_canvases(c) for c in res.canvases]
-            # crops on the device too (sd_group_crops): cv2.normalize / cv2.resize / pad / mean-std bit for bit
-            seg = _seg.Segmenter(None, margin=self.margin, device=dev)
-            res = seg.partition(batch, planes, canvases="device", crops=True, crop_lut=_seg.input_lut(self.mean, self.std))
-            if self.img_size != _seg.IMG_SIZE and len(res["groups"]):
-                res["crops"] = _seg.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"], size=self.img_size,
-                                                lut=_seg.input_lut(self.mean, self.std))
-            return [res.line_partitions(l) for l in range(batch.n_lines)]
+            for c0 in range(0, len(imgs_bin), lines_per_chunk):
+                masks = imgs_bin[c0:c0 + lines_per_chunk]
+                key = ("chunk", (c0 // lines_per_chunk) & 1)           # two staging sets: pack k+1 while k is in flight
+                batch = _seg.plan_batch([m.shape[1] for m in masks], dev)
+                h = seg.staging.get_tensor((key, "masks"), batch.px_total)
+                hn = h.numpy()
+                hn[:] = 0
+                for m, ln in zip(masks, batch.lines):
+                    off, pitch = int(ln["px_off"]), int(ln["pitch"])
+                    hn[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)[:, :m.shape[1]] = np.asarray(m) != 0
+                planes = h.to(dev, non_blocking=True)
+                res = seg.partition(batch, planes, canvases="device", key=key, crops=True, crops_to_host=True,
+                                    crop_lut=lut if keep_device else None)
+                if self.img_size != _seg.IMG_SIZE and len(res["groups"]):
+                    res["crops"] = _seg.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"], size=self.img_size,
+                                                    lut=lut if keep_device else None)
+                    img = res["crops"]["image"]
+                    res["crops"]["image_host"] = _seg.copy_d2h(seg.staging.get((key, "crops"), img.numel()), img, dev).reshape(tuple(img.shape))
+                torch.cuda.current_stream(dev).synchronize()
+                cr, groups, lgs = res["crops"], res["groups"], res["line_group_start"]
+                if keep_device:
+                    self.last_device_crops.append(cr["image_input"] if cr is not None else None)
+                imgs_h = cr["image_host"].copy() if cr is not None and "image_host" in cr else None
+                for k in range(batch.n_lines):
+                    a, b = int(lgs[k]), int(lgs[k + 1])
+                    out.append([_seg.LazyPartition(lut, image=imgs_h[g], translate1=(groups[g, 1], groups[g, 2]),
+                                                   ratio=float(cr["ratio"][g]),
+                                                   translate2=(float(cr["translate2"][g, 0]), float(cr["translate2"][g, 1])))
+                                for g in range(a, b)])
+        return out
 
     def load_orts(self, filepaths):
         raise NotImplementedError("stroke-estimator graphs are outside the B200 segmentation path (SURVEY.md 2)")

@@ -3,8 +3,11 @@ GPU, no data-path collective: tiles and lines are independent) a
 runs the batched segmentation step on each.
 
 The hot-path step of one rank:
-   [H2D lines] -> tile_extract -> Attention-UNet (tcgen05) -> glue -> CCL -> stats
-   -> [D2H counts+stats] -> host interval grouping -> group canvases -> 224x224 crops -> [D2H results]
+   [pack + H2D lines] -> tile_extract -> Attention-UNet (tcgen05; glue + thresholds fused into its head) -> CCL
+   -> stats -> [D2H counts+stats] -> host interval grouping -> group canvases -> 224x224 crops -> [D2H results]
+Results are gathered on the host: every rank's D2H copies land in its region of one shared-memory arena
+(`gather.ResultArena`), the caller reads all lines in input order (reference: one process, one list of images in,
+results in input order out, /root/reference/main.py:91-136).
 """
 
 from __future__ import annotations
@@ -16,6 +19,7 @@ import time
 import numpy as np
 import torch
 
+from . import gather as G
 from . import segment as S
 from .engine import TILE_H, TILE_W, UNetEngine
 from .synth import n_tiles_for_width
@@ -37,7 +41,8 @@ def shard_lines(widths, world: int):
 
 
 def gather_in_order(local_results, local_indices, n_total, world, rank, group=None):
-    """Host-side gather of per-line results into input order (rank 0 gets the list)."""
+    """Object gather of small per-line results into input order (rank 0 gets the list).  Bulk results (masks,
+    crops) go through `gather.ResultArena` instead."""
     import torch.distributed as dist
     if world == 1:
         out = [None] * n_total
@@ -62,19 +67,24 @@ class _Chunk:
 
 class LineSegmentationJob:
     """One rank's share of a job, cut into chunks of lines that flow through three streams:
-    copy (H2D of packed lines) -> unet (tile_extract, Attention-UNet, glue) -> part (CCL, stats,
-    host grouping, canvases, D2H).  The UNet stream never waits for the host: while the host
+    copy (H2D of packed lines) -> unet (tile_extract, Attention-UNet with the glue in its head) -> part (CCL,
+    stats, host grouping, canvases, crops, D2H).  The UNet stream never waits for the host: while the host
     clusters the islands of chunk k, the tensor cores are already on chunk k+1.
 
-    `resident_step` times the hot path with inputs already in HBM; `host_step` is the call a
-    user makes with (pinned) host buffers: H2D of the lines and D2H of masks, stats and group
-    canvases are inside it."""
+    `resident_step` times the hot path with inputs already in HBM; `host_step` is the call a user makes with
+    host buffers: packing (when `prepack=False`), H2D of the lines and D2H of masks, stats, group tables,
+    canvases and crops are inside it.  With a `gather.RegionWriter` the host copies land in the rank's region of
+    the shared gather arena."""
 
-    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 64, crops: bool = True):
+    def __init__(self, engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 32, crops: bool = True,
+                 prepack: bool = True, seg: S.Segmenter | None = None):
         self.engine = engine
         self.crops = crops                  # also build the 224x224 stroke-estimator crops of every group
         self.device = engine.device
-        self.seg = S.Segmenter(engine, bin_thr=bin_thr)
+        self.seg = seg if seg is not None else S.Segmenter(engine, bin_thr=bin_thr)
+        self.staging = self.seg.staging
+        self.prepack = prepack
+        self.lines_per_chunk = lines_per_chunk
         self.chunks = []
         with torch.cuda.device(self.device):
             self.s_copy, self.s_unet, self.s_part = (torch.cuda.Stream(self.device) for _ in range(3))
@@ -83,17 +93,20 @@ class LineSegmentationJob:
                 imgs = images[c0:c0 + lines_per_chunk]
                 ch = _Chunk()
                 ch.index = len(self.chunks)
+                ch.imgs = imgs
                 ch.batch = S.plan_batch([S.resized_width(im) for im in imgs], self.device)
-                ch.h_rgb = S.pack_lines_rgb(imgs, ch.batch, pinned=True)
-                ch.d_rgb = ch.h_rgb.to(self.device)
-                ch.d_rgb_in = torch.empty_like(ch.d_rgb)
+                ch.h_rgb = self.staging.get_tensor((("chunk", ch.index), "rgb"), int(ch.batch.plan.img_bytes))
+                ch.d_rgb_in = torch.empty(int(ch.batch.plan.img_bytes), dtype=torch.uint8, device=self.device)
                 ch.resize = S.ResizePlan(imgs, ch.batch)            # lines whose height is not 128 (none in the configs)
-                ch.resize.upload()
-                ch.resize.run(ch.d_rgb)
+                ch.d_rgb = None
+                if prepack:
+                    S.pack_lines_rgb(imgs, ch.batch, out=ch.h_rgb)
+                    ch.d_rgb = ch.h_rgb.to(self.device)
+                    ch.resize.upload()
+                    ch.resize.run(ch.d_rgb)
                 ch.t0, ch.t1 = t0, t0 + ch.batch.n_tiles        # the chunk's range in the job-wide tile stack
                 t0 = ch.t1
                 ch.planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, device=self.device)
-                ch.h_planes = torch.empty(ch.batch.px_total, dtype=torch.uint8, pin_memory=True)
                 self.chunks.append(ch)
             # one tile stack for the whole job: UNet batches run across chunk boundaries, so only the
             # last batch of the job is partial
@@ -104,19 +117,24 @@ class LineSegmentationJob:
                 ch.tiles = self.tiles[ch.t0:ch.t1]
         self.n_tiles = sum(c.batch.n_tiles for c in self.chunks)
         self.n_lines = sum(c.batch.n_lines for c in self.chunks)
+        self.px_total = sum(c.batch.px_total for c in self.chunks)
 
-    def _run(self, from_host: bool, canvases: str):
+    def _run(self, from_host: bool, canvases: str, writer: G.RegionWriter | None = None):
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             for st in (self.s_copy, self.s_unet, self.s_part):
                 st.wait_stream(cur)
+            if writer is not None:
+                writer.begin_step()
             ready = [None] * len(self.chunks)
             mt = self.engine.max_tiles
             done = 0                      # tiles binarized so far
-            glued = 0                     # chunks glued so far
+            glued = 0                     # chunks whose planes are complete
             for k, ch in enumerate(self.chunks):
                 src = ch.d_rgb
                 if from_host:
+                    if not self.prepack:              # the caller's numpy images -> page-locked staging (host memcpy)
+                        S.pack_lines_rgb(ch.imgs, ch.batch, out=ch.h_rgb)
                     with torch.cuda.stream(self.s_copy):
                         ch.d_rgb_in.copy_(ch.h_rgb, non_blocking=True)
                         ch.resize.upload()
@@ -142,36 +160,89 @@ class LineSegmentationJob:
             results = []
             dbg = os.environ.get("SD_PIPE_DEBUG")
             t_dbg = [time.perf_counter()]
+            st = writer if writer is not None else self.staging
             with torch.cuda.stream(self.s_part):
                 for ch, ev in zip(self.chunks, ready):
                     self.s_part.wait_event(ev)
+                    key = ("chunk", ch.index)
+                    h_planes = None
                     if from_host:
-                        ch.h_planes.copy_(ch.planes, non_blocking=True)
-                    res = self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=("chunk", ch.index),
-                                             zero_copy=True, crops=self.crops)
-                    if from_host and self.crops and res["crops"] is not None:
-                        img = res["crops"]["image"]
-                        hb = S.pinned_buffer((("chunk", ch.index), "crops"), img.numel())[:img.numel()]
-                        hb.copy_(img.view(-1), non_blocking=True)
-                        res["crops"]["image_host"] = hb.numpy().reshape(tuple(img.shape))
-                        res["crops"]["input_host"] = None
+                        h_planes = S.copy_d2h(st.get((key, "planes"), ch.batch.px_total), ch.planes, self.device)
+                    res = self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=key, zero_copy=True,
+                                             crops=self.crops, staging=st, crops_to_host=from_host)
+                    res["planes_host"] = h_planes
+                    if writer is not None:
+                        writer.put(ch.index, "groups", res["groups"].reshape(-1, 6))
+                        writer.put(ch.index, "lgs", res["line_group_start"])
+                        writer.set(ch.index, n_lines=ch.batch.n_lines, px_total=ch.batch.px_total, n_rows=len(res["stats"]),
+                                   n_groups=len(res["groups"]), canvas_bytes=res["canvas_bytes"], crop_size=S.IMG_SIZE)
                     results.append(res)
                     t_dbg.append(time.perf_counter())
             cur.wait_stream(self.s_unet)
             cur.wait_stream(self.s_part)
             if from_host:
                 cur.synchronize()
+                if writer is not None:            # every byte of the step has landed in the arena
+                    for ch in self.chunks:
+                        writer.set(ch.index, done=1)
+                    writer.end_step()
             if dbg:
                 t_dbg.append(time.perf_counter())
                 print("[pipe] enqueue->partitions done (ms):", [round(1e3 * (b - a), 1) for a, b in zip(t_dbg, t_dbg[1:])],
                       file=sys.stderr, flush=True)
         return results
 
+    def binarize_step(self):
+        """Only the binarization half, from the caller's numpy images: -> [ (128, W', 1) u8 {0,255} ] in line order
+        (evaluate_binarize.py:130-140).  One packed D2H per chunk; the per-line arrays are fresh copies, made while
+        the GPU is still on later chunks."""
+        out = []
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            for st in (self.s_copy, self.s_unet, self.s_part):
+                st.wait_stream(cur)
+            mt = self.engine.max_tiles
+            done = glued = 0
+            evs = [None] * len(self.chunks)
+            hosts = [None] * len(self.chunks)
+            for k, ch in enumerate(self.chunks):
+                if not self.prepack:
+                    S.pack_lines_rgb(ch.imgs, ch.batch, out=ch.h_rgb)
+                with torch.cuda.stream(self.s_copy):
+                    ch.d_rgb_in.copy_(ch.h_rgb, non_blocking=True)
+                    ch.resize.upload()
+                    ev = torch.cuda.Event(); ev.record(self.s_copy)
+                self.s_unet.wait_event(ev)
+                with torch.cuda.stream(self.s_unet):
+                    ch.resize.run(ch.d_rgb_in)
+                    S.tile_extract_f16(ch.batch, ch.d_rgb_in, out=ch.tiles)
+                    ch.planes.zero_()
+                    last = k == len(self.chunks) - 1
+                    while done + mt <= ch.t1 or (last and done < ch.t1):
+                        n = min(mt, self.n_tiles - done)
+                        self.engine.forward_lines(self.tiles[done:done + n], self.dst[16 * done:16 * (done + n)], self.seg.bin_thr)
+                        done += n
+                    while glued < len(self.chunks) and self.chunks[glued].t1 <= done:
+                        g = self.chunks[glued]
+                        hosts[glued] = S.copy_d2h(self.staging.get((("chunk", g.index), "planes"), g.batch.px_total), g.planes, self.device)
+                        ev = torch.cuda.Event(); ev.record(self.s_unet)
+                        evs[glued] = ev
+                        glued += 1
+            for ch, ev, hp in zip(self.chunks, evs, hosts):
+                ev.synchronize()
+                for ln in ch.batch.lines:
+                    off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
+                    out.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None].copy())
+            cur.wait_stream(self.s_unet)
+        return out
+
     def resident_step(self):
+        if not self.prepack:
+            raise RuntimeError("resident_step needs a job built with prepack=True")
         return self._run(False, "device")
 
-    def host_step(self):
-        return self._run(True, "host")
+    def host_step(self, writer: G.RegionWriter | None = None):
+        return self._run(True, "host", writer)
 
     def h2d_bytes(self):
         return int(sum(c.batch.plan.img_bytes + (c.resize.h_src.numel() if c.resize.n else 0) for c in self.chunks))
@@ -181,3 +252,45 @@ class LineSegmentationJob:
         n += sum(r["num"].nbytes + r["stats"].nbytes + r["canvas_bytes"] for r in results)
         n += sum(r["crops"]["image"].numel() for r in results if r.get("crops") is not None)
         return int(n)
+
+    def arena_bytes(self) -> int:
+        """Capacity of this rank's gather-arena region for one step."""
+        return G.region_capacity(self.n_tiles, self.n_lines, self.px_total, max(len(self.chunks), 1))
+
+    # ---- per-line outputs in the reference's shapes ------------------------------------------------------------
+    def line_outputs(self, results, copy: bool = True, mean=None, std=None):
+        """After `host_step`: ([mask (128, W', 1) u8 {0,255}], [[partition dict]]) per line, in this job's line
+        order — what `BinarizationSession.binarize_images` (evaluate_binarize.py:130-140) and
+        `StrokeEstimationSession.get_partitions` (evaluate_strokes.py:186-224) return.  `image_input` of a partition
+        is materialised on first access (`LazyPartition`)."""
+        masks, parts = [], []
+        lut = S.input_lut(mean if mean is not None else S.IMAGENET_MEAN, std if std is not None else S.IMAGENET_STD)
+        for ch, res in zip(self.chunks, results):
+            hp = res["planes_host"]
+            cr = res["crops"]
+            img_host = cr["image_host"] if cr is not None and "image_host" in cr else None
+            groups, lgs = res["groups"], res["line_group_start"]
+            if img_host is not None and copy:
+                img_host = img_host.copy()
+            for k, ln in enumerate(ch.batch.lines):
+                off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
+                m = hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None]
+                masks.append(m.copy() if copy else m)
+                a, b = int(lgs[k]), int(lgs[k + 1])
+                pl = []
+                for g in range(a, b):
+                    pl.append(S.LazyPartition(lut, image=img_host[g], translate1=(groups[g, 1], groups[g, 2]),
+                                              ratio=float(cr["ratio"][g]),
+                                              translate2=(float(cr["translate2"][g, 0]), float(cr["translate2"][g, 1]))))
+                parts.append(pl)
+        return masks, parts
+
+
+def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_chunk: int = 32, seg: S.Segmenter | None = None,
+                  copy: bool = True):
+    """The fused public call on one GPU: a list of (h, w, 3) u8 line images (plain numpy) in, per line the
+    binarized mask and the stroke-estimator partitions out, in input order — `binarize_image` + `main.py:108` +
+    `get_partitions` of the reference for every image, as one pipelined job."""
+    job = LineSegmentationJob(engine, images, bin_thr=bin_thr, lines_per_chunk=lines_per_chunk, crops=True, prepack=False, seg=seg)
+    res = job.host_step()
+    return job.line_outputs(res, copy=copy)

@@ -77,10 +77,12 @@ def resized_width(img, height: int = TILE_H) -> int:
     return int(w) if h == height else int(w * (height / h))
 
 
-def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True) -> torch.Tensor:
-    """Host-packs (128, W, 3) u8 images at sd_line.img_off (pinned staging).  Lines of another height are left
-    out: `ResizePlan` fills their slots on the device."""
-    buf = torch.empty(int(batch.plan.img_bytes), dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Host-packs (128, W, 3) u8 images at sd_line.img_off (pinned staging; `out` = a staging tensor to fill).
+    Lines of another height are left out: `ResizePlan` fills their slots on the device."""
+    buf = out if out is not None else torch.empty(int(batch.plan.img_bytes), dtype=torch.uint8,
+                                                  pin_memory=pinned and torch.cuda.is_available())
+    assert buf.numel() >= int(batch.plan.img_bytes)
     nb = buf.numpy()
     for img, ln in zip(images, batch.lines):
         if img.shape[0] != TILE_H:
@@ -266,6 +268,8 @@ def group_canvases(batch: LineBatch, labels: torch.Tensor, stat_off: np.ndarray,
 
 
 IMG_SIZE = 224      # evaluate_strokes.py:25
+IMAGENET_MEAN = [0.485, 0.456, 0.406]   # evaluate_strokes.py:27-28
+IMAGENET_STD = [0.229, 0.224, 0.225]
 CROP_MARGIN = 1     # evaluate_strokes.py:207 (resize_and_pad_image(..., margin=1))
 
 
@@ -310,16 +314,51 @@ def group_crops(device, canvas: torch.Tensor, d_groups: torch.Tensor, groups: np
     return {"image": image, "image_input": inp, "ratio": ratio, "translate2": t2, "rs_dims": rs}
 
 
-_PINNED = {}
+class PinnedStaging:
+    """Grow-only pinned host staging buffers, one per purpose (`key`), owned by ONE Segmenter / job (two
+    Segmenters driven from different threads, one per GPU, never share a buffer).  `get` returns a uint8 numpy
+    view; device-to-host copies into it go through sd_copy_d2h_async."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get_tensor(self, key, nbytes: int) -> torch.Tensor:
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            self._bufs[key] = buf
+        return buf[:nbytes]
+
+    def get(self, key, nbytes: int) -> np.ndarray:
+        return self.get_tensor(key, nbytes).numpy()
 
 
-def pinned_buffer(key, nbytes: int) -> torch.Tensor:
-    """Grow-only pinned host staging buffers (one per purpose), reused across calls."""
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
-        _PINNED[key] = buf
-    return buf
+def copy_d2h(dst: np.ndarray, src: torch.Tensor, device) -> np.ndarray:
+    """Asynchronous device -> (page-locked) host copy on the current stream of `device`; returns `dst`."""
+    assert dst.flags.c_contiguous and src.is_contiguous() and dst.nbytes == src.numel() * src.element_size(), (dst.nbytes, src.shape)
+    _lib.check(_lib.lib().sd_copy_d2h_async(dst.ctypes.data, src.data_ptr(), dst.nbytes, stream_ptr(device)), "sd_copy_d2h_async")
+    return dst
+
+
+class LazyPartition(dict):
+    """One partition dict of get_partitions (evaluate_strokes.py:213-219): `image`, `translate1`, `ratio`,
+    `translate2` are stored; `image_input` ((3, size, size) f32, 12x the bytes of `image`) is built on first
+    `part["image_input"]` from `image` exactly like `_normalize_image` (:58-69: MINMAX to 0..255, then per channel
+    (v / 255. - mean) / std through the same float64 table).  On the device path the f32 tensor of ALL crops is
+    available without crossing PCIe (`PartitionResult["crops"]["image_input"]`)."""
+
+    def __init__(self, lut, **kw):
+        super().__init__(**kw)
+        self._lut = lut
+
+    def __missing__(self, key):
+        if key != "image_input":
+            raise KeyError(key)
+        import cv2
+        norm = cv2.normalize(np.ascontiguousarray(self["image"]), None, 0, 255, norm_type=cv2.NORM_MINMAX)
+        v = self._lut[:, norm]
+        self[key] = v
+        return v
 
 
 class PartitionResult(dict):
@@ -376,6 +415,7 @@ class Segmenter:
         self.device = engine.device if engine is not None else torch.device(device)
         self.bin_thr = bin_thr
         self.margin = margin
+        self.staging = PinnedStaging()
 
     def binarize(self, images, d_rgb: torch.Tensor | None = None, batch: LineBatch | None = None):
         """-> (batch, mask planes u8 {0,255} packed on device)."""
@@ -397,24 +437,28 @@ class Segmenter:
         return batch, planes
 
     def partition(self, batch: LineBatch, planes: torch.Tensor, canvases: str = "host", key="part",
-                  zero_copy: bool = False, crops: bool = False, crop_lut: np.ndarray | None = None) -> PartitionResult:
+                  zero_copy: bool = False, crops: bool = False, crop_lut: np.ndarray | None = None,
+                  staging=None, crops_to_host: bool = False) -> PartitionResult:
         """mask planes -> labels, island stats, groups and group canvases for every line.
-        canvases: "host" (copied to pinned host memory), "device" (left in HBM) or "none".
-        zero_copy: host arrays alias the reusable pinned staging buffers of `key` (valid until
-        the next call with the same key) instead of being copied out."""
+        canvases: "host" (copied to page-locked host memory), "device" (left in HBM) or "none".
+        staging: where host copies land (`get(key, nbytes) -> uint8 numpy view`): this Segmenter's pinned buffers
+        by default, a gather arena region for multi-GPU jobs.  zero_copy: host arrays alias the staging memory
+        (valid until the next call with the same key) instead of being copied out.
+        crops_to_host: also copy the u8 crops (`image`) to the staging memory."""
+        st = staging if staging is not None else self.staging
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
             labels, num = ccl_label(batch, planes)
-            h_num = pinned_buffer((key, "num"), batch.n_lines * 4)[:batch.n_lines * 4].view(torch.int32)
-            h_num.copy_(num, non_blocking=True)
+            h_num = copy_d2h(st.get((key, "num"), batch.n_lines * 4), num, self.device).view(np.int32)
             stream.synchronize()
-            num_h = h_num.numpy().copy()
+            num_h = h_num if zero_copy else h_num.copy()
             stats, stat_off, d_off = island_stats(batch, labels, num_h)
             rows = int(stat_off[-1])
-            h_stats = pinned_buffer((key, "stats"), max(rows, 1) * 20)[:rows * 20].view(torch.int32).view(rows, 5)
-            h_stats.copy_(stats, non_blocking=True)
+            h_stats = st.get((key, "stats"), rows * 20).view(np.int32).reshape(rows, 5)
+            if rows:
+                copy_d2h(h_stats, stats, self.device)
             stream.synchronize()
-            stats_h = h_stats.numpy().copy()
+            stats_h = h_stats if zero_copy else h_stats.copy()
             groups, group_of, lgs, cbytes = _lib.group_lines(stats_h, stat_off, batch.widths, self.margin, TILE_H, TILE_H)
             res = PartitionResult(labels=labels, num=num_h, stats=stats_h, stat_off=stat_off, groups=groups,
                                   group_of=group_of, line_group_start=lgs, canvas=None, canvas_host=None,
@@ -430,11 +474,14 @@ class Segmenter:
                 res["_keep"] = (d_table, d_gof, d_off)
                 if crops:     # 224x224 stroke-estimator crops straight from the device canvases
                     res["crops"] = group_crops(self.device, canvas, d_table, groups, lut=crop_lut)
+                    if crops_to_host:
+                        img = res["crops"]["image"]
+                        res["crops"]["image_host"] = copy_d2h(st.get((key, "crops"), img.numel()), img, self.device).reshape(tuple(img.shape))
+                        res["crops"]["input_host"] = None
                 if canvases == "host":
-                    hb = pinned_buffer((key, "canvas"), cbytes)[:cbytes]
-                    hb.copy_(res["canvas"], non_blocking=True)
+                    hb = copy_d2h(st.get((key, "canvas"), cbytes), res["canvas"], self.device)
                     stream.synchronize()
-                    res["canvas_host"] = hb.numpy() if zero_copy else hb.numpy().copy()
+                    res["canvas_host"] = hb if zero_copy else hb.copy()
             elif canvases != "none":
                 res["canvas"] = torch.empty(0, dtype=torch.uint8, device=self.device)
                 res["canvas_host"] = np.zeros(0, np.uint8)

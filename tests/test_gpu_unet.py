@@ -212,6 +212,61 @@ def test_pipeline_job_equals_direct_segmentation(cuda_device, parity_state):
         e.close()
 
 
+def test_api_calls_from_numpy_and_gather_arena(cuda_device, parity_state):
+    """The reference-signature calls from plain numpy lists (`binarize_images`, `get_partitions_batch`), the fused
+    `segment_lines` call and the shared-memory gather arena all return what one direct Segmenter pass returns."""
+    import os
+    from stroke_derenderer_b200 import gather as G
+    from stroke_derenderer_b200.evaluate_binarize import BinarizationSession
+    from stroke_derenderer_b200.evaluate_strokes import StrokeEstimationSession
+    from stroke_derenderer_b200.pipeline import LineSegmentationJob, segment_lines
+    from stroke_derenderer_b200.segment import Segmenter
+    widths = [700, 1536, 333, 2048, 4000, 384, 1000, 3072, 640, 2222, 1234]
+    lines = [synth_line(w, seed=150 + i) for i, w in enumerate(widths)]
+    bs = BinarizationSession(max_tiles=16, lines_per_chunk=4)
+    e = bs.init_onnx_inference(parity_state)
+    try:
+        ref = Segmenter(e).segment(lines)
+        masks = bs.binarize_images(lines, e)
+        for i, m in enumerate(masks):
+            assert m.shape == (128, widths[i], 1) and m.dtype == np.uint8
+            assert np.array_equal(m[:, :, 0], ref["batch"].plane(ref["planes"], i).cpu().numpy()), i
+        se = StrokeEstimationSession()
+        parts = se.get_partitions_batch([m[:, :, 0] > 127 for m in masks], lines_per_chunk=3)
+        m2, p2 = segment_lines(e, lines, lines_per_chunk=4)
+        assert all(np.array_equal(a, b) for a, b in zip(masks, m2))
+        from oracle import segmentation_ref as O
+        for i in range(len(lines)):
+            want = O.get_partitions((masks[i][:, :, 0] > 127).astype(np.uint8))
+            for got in (parts[i], p2[i]):
+                assert len(got) == len(want), i
+                for p, w in zip(got, want):
+                    assert np.array_equal(p["image"], w["image"]) and np.array_equal(p["image_input"], w["image_input"])
+                    assert (int(p["translate1"][0]), int(p["translate1"][1])) == (int(w["translate1"][0]), int(w["translate1"][1]))
+                    assert p["ratio"] == w["ratio"] and tuple(p["translate2"]) == tuple(w["translate2"])
+        # gather arena, one rank: D2H lands in the (page-locked) shared-memory region, the reader sees input order
+        job = LineSegmentationJob(e, lines, lines_per_chunk=4, prepack=False)
+        arena = G.ResultArena(f"sd_test_{os.getpid()}", [job.arena_bytes()], rank=0, create=True)
+        try:
+            arena.register()
+            wr = G.RegionWriter(arena.region(0), len(job.chunks))
+            for step in (1, 2):
+                job.host_step(wr)
+                got = G.GatheredResults(arena, [list(range(len(lines)))], widths, 4, step=step)
+                for i in range(len(lines)):
+                    assert np.array_equal(got.mask(i), masks[i][:, :, 0]), i
+                    assert got.num(i) == int(ref["num"][i])
+                    assert np.array_equal(got.crops(i), np.stack([p["image"] for p in p2[i]]) if len(p2[i]) else np.zeros((0, 224, 224), np.uint8))
+                    cv = got.canvases(i)
+                    rc = ref.line_canvases(i)
+                    assert len(cv) == len(rc) and all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(cv, rc))
+            del got, cv
+        finally:
+            arena.close()
+    finally:
+        e.close()
+
+
 def test_main_cli_dropin(cuda_device, parity_state, tmp_path):
     """B1 boundary: the root main.py (initialize_sessions / load_images / main) with a `binarizer.onnx` read by the
     dependency-free reader, PNG input, `_BINARIZED.png` + `_PARTITIONS.json` output."""
