@@ -164,6 +164,14 @@ int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines,
                  int64_t px_total, int64_t blk_total, int32_t* d_labels, int32_t* d_num,
                  void* d_work, void* stream);
 
+/* K7 + K8 in one pass: the labels of sd_ccl_label plus the cv2 `stats` rows of sd_island_stats without a second
+ * read of the labels (the island statistics are reduced while the labels are written).  d_stat_off: int64[n_lines+1]
+ * OUT, row offset of every line (exclusive scan of num - 1; [n_lines] = total rows).  d_stats: int32[cap_rows][5];
+ * rows beyond cap_rows are dropped: the caller checks d_stat_off[n_lines] <= cap_rows and retries with more room. */
+int sd_ccl_label_stats(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
+                       int64_t blk_total, int32_t* d_labels, int32_t* d_num, int64_t* d_stat_off,
+                       int32_t* d_stats, int64_t cap_rows, void* d_work, void* stream);
+
 /* K8: cv2 `stats` rows (x, y, w, h, area) int32 for labels 1..N of every line
  * (== cv2.boundingRect(labels == n), helper/partition.py:18-19).
  * d_stat_off[l] = row offset of line l in d_stats (row k-1 holds label k). */

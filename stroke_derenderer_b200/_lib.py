@@ -64,6 +64,8 @@ EXPORTS = {
     "sd_ccl_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "sd_ccl_label": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
+    "sd_ccl_label_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sd_island_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_void_p]),
     "sd_group_canvas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,0 +1,497 @@
+// K7 + K8, second generation: connected-component labelling with OpenCV's numbering and the cv2
+// `stats` rows in the same pass.  Replaces the strip-per-CTA kernels of round 1 (320 k thread-instructions per
+// 128 x 128 strip, IPC ~1 behind five __syncthreads) with a WARP per strip and no CTA barrier at all:
+//
+//   1. ccl_warp_label_kernel (warp = strip of 128 x 128 px = 64 x 64 blocks of 2 x 2 px).  The mask streams in
+//      with coalesced 16-byte loads; every load becomes 8 "even column" + 8 "odd column" bits (dp4a), so pixel row r
+//      of the strip is two 64-bit words Xe / Xo whose bit k is the left / right pixel of block k.  Lane L owns block
+//      rows 2L and 2L+1: occupancy, horizontal links, run starts and the contacts with the block row above are
+//      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row), unions
+//      are shared-memory atomicMin (min-root: the root of a component is its first block in raster order, which is
+//      what OpenCV's numbering sorts by); paths are flattened only after the union phase (a compressing store can
+//      undo a concurrent union, the round-1 lost-link race).  Outputs per strip: the Xe / Xo words (2 KB), the
+//      run-start masks (512 B) and one 16-bit root per run (bit 15 = the root touches a neighbouring strip):
+//      ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that touch no other strip are final
+//      (root bitmap); the others register in the sparse global parent array.
+//   2. ccl_line_kernel (CTA = line): unions across the strip seams of the line, marks the surviving seam roots,
+//      exclusive scan of the root bitmap (label = 1 + #roots before the root), island count; the last CTA to
+//      finish also scans the counts of all lines into the stats row offsets.
+//   3. ccl_warp_write_kernel (warp = strip): run roots -> final labels (shared-memory table), int32 labels out as
+//      512-byte row segments, and, fused, the cv2 stats: every run's extent / area is reduced over the lanes that
+//      hold runs of the same label (match_any + redux) before one set of global atomics per (label, lane group).
+// HBM traffic: 1 B/px mask read + 4 B/px labels written + ~0.4 B/px of records; no second pass over the labels.
+#pragma once
+#include "common.cuh"
+
+namespace sd {
+
+constexpr int kCw = 4;                       // warps (strips) per CTA
+constexpr int kBigCoord = 0x3fffffff;        // stats rows keep (kBigCoord - max) so that every field is a min / add
+constexpr int kStatFill = 0x7f7f7f7f;        // cudaMemsetAsync(0x7f) start value of every stats field
+
+struct CclWarpWork {
+  int* parent;          // [blk_total]       sparse: seam-touching local roots only (global block index -> parent)
+  uint32_t* bitmap;     // [blk_total / 32]  bit = block is the root (first block) of a component
+  int* prefix;          // [blk_total / 32]  exclusive count of root bits before this word, per line
+  uint4* pix;           // [strips][128]     {Xe.lo, Xe.hi, Xo.lo, Xo.hi} of every pixel row of the strip
+  uint2* rs;            // [strips][64]      run-start mask of every block row
+  uint16_t* roots;      // [strips][4096]    one entry per run, block-row major: local root block | touch << 15
+  int* bnd_root;        // [strips][2][64]   global index of the root of each seam block (left / right column), -1 if none
+  uint32_t* bnd_bits;   // [strips][2][4]    seam pixel columns: bit L of word r = pixel row 4L + r
+  unsigned int* ticket; // [1]               lines finished (the last line CTA builds the stats offsets)
+};
+
+__device__ __forceinline__ uint32_t cw_nzflags(uint32_t w) {   // 0x80 in every non-zero byte
+  return (w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+}
+// 16 mask bytes -> 8 even-column bits (bit k = byte 2k non-zero) and 8 odd-column bits
+__device__ __forceinline__ void cw_bits16(uint4 v, uint32_t& e, uint32_t& o) {
+  const uint32_t f0 = cw_nzflags(v.x), f1 = cw_nzflags(v.y), f2 = cw_nzflags(v.z), f3 = cw_nzflags(v.w);
+  e = __dp4a(f0, 0x00020001u, __dp4a(f1, 0x00080004u, __dp4a(f2, 0x00200010u, __dp4a(f3, 0x00800040u, 0u)))) >> 7;
+  o = __dp4a(f0, 0x02000100u, __dp4a(f1, 0x08000400u, __dp4a(f2, 0x20001000u, __dp4a(f3, 0x80004000u, 0u)))) >> 7;
+}
+__device__ __forceinline__ uint64_t cw_shfl_up64(uint64_t v, int lane) {
+  const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, 1), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), 1);
+  return lane ? (((uint64_t)hi << 32) | lo) : 0ull;
+}
+// block column of the run start that owns block k: highest run-start bit at or below k
+__device__ __forceinline__ int cw_run_start(uint64_t rs, int k) { return 63 - __clzll((long long)(rs & ((2ull << k) - 1ull))); }
+
+__device__ __forceinline__ int cw_find(volatile int* p, int a) {
+  int q;
+  while ((q = p[a]) != a) a = q;
+  return a;
+}
+// min-root union; completes only when its atomicMin hit a true root.  No compression while unions are in flight.
+__device__ __forceinline__ void cw_union(int* p, int a, int b) {
+  while (true) {
+    a = cw_find(p, a);
+    b = cw_find(p, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&p[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// contacts of a block row (top pixel row Te / To, links hl, run starts rs) with the pixel row above it (Ue / Uo; links
+// hlU and run starts rsU of that block row): one union per distinct (run, upper run) pair
+__device__ __forceinline__ void cw_contacts(int* parent, int base, int baseU, uint64_t Te, uint64_t To, uint64_t Ue, uint64_t Uo,
+                                            uint64_t hl, uint64_t hlU, uint64_t rs, uint64_t rsU) {
+  const uint64_t vu0 = (Te | To) & (Ue | Uo);                 // block k - upper block k
+  uint64_t vl = Te & (Uo << 1);                               // block k - upper block k-1 (diagonal)
+  uint64_t vr = To & (Ue >> 1);                               // block k - upper block k+1 (diagonal)
+  vl &= ~(vu0 & hlU) & ~((vu0 << 1) & hl);
+  vr &= ~(vu0 & (hlU >> 1)) & ~((vu0 >> 1) & (hl >> 1));
+  uint64_t vu = vu0 & ~((vu0 << 1) & hl & hlU);
+  while (vu | vl | vr) {
+    int k, dk;
+    if (vu) { k = __ffsll((long long)vu) - 1; vu &= vu - 1; dk = 0; }
+    else if (vl) { k = __ffsll((long long)vl) - 1; vl &= vl - 1; dk = -1; }
+    else { k = __ffsll((long long)vr) - 1; vr &= vr - 1; dk = 1; }
+    cw_union(parent, base + cw_run_start(rs, k), baseU + cw_run_start(rsU, k + dk));
+  }
+}
+
+struct __align__(16) CwLabelSmem {
+  int parent[kStripBlocks];        // node = block row * 64 + first block of the run
+  uint8_t e[128][8], o[128][8];    // Xe / Xo of every pixel row, one byte per 16-pixel load
+  uint32_t touch[kStripBlocks / 32];
+};
+
+// warp-cooperative: #lines whose block offset is <= off, minus one (lines are sorted by offset)
+__device__ __forceinline__ int cw_find_line(const sd_line* __restrict__ L, int n, int64_t off, int lane) {
+  int cnt = 0;
+  for (int i = lane; i < n; i += 32) cnt += (L[i].blk_off <= off) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  return cnt - 1;
+}
+
+__global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t* __restrict__ mask, const sd_line* __restrict__ L,
+                                                                  int n_lines, int n_strips, CclWarpWork w) {
+  extern __shared__ __align__(16) uint8_t cw_smem[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  CwLabelSmem& sm = reinterpret_cast<CwLabelSmem*>(cw_smem)[wp];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *w.ticket = 0u;
+  for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
+    const int64_t blk0 = (int64_t)strip * kStripBlocks;
+    const sd_line ln = L[cw_find_line(L, n_lines, blk0, lane)];
+    const int s = (int)((blk0 - ln.blk_off) >> 12), ns = ln.bw >> 6;
+    const uint8_t* src = mask + ln.px_off + s * 128;
+    // ---- mask bytes -> Xe / Xo bits (a warp instruction moves 4 rows x 128 B) ----
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (b * 8 + i) * 4 + (lane >> 3);
+        v[i] = __ldcs(reinterpret_cast<const uint4*>(src + (int64_t)row * ln.pitch + (lane & 7) * 16));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (b * 8 + i) * 4 + (lane >> 3);
+        uint32_t e, o;
+        cw_bits16(v[i], e, o);
+        sm.e[row][lane & 7] = (uint8_t)e;
+        sm.o[row][lane & 7] = (uint8_t)o;
+      }
+    }
+    sm.touch[lane] = 0u; sm.touch[lane + 32] = 0u; sm.touch[lane + 64] = 0u; sm.touch[lane + 96] = 0u;
+    __syncwarp();
+    // ---- lane L: block rows a = 2L (pixel rows 4L, 4L+1) and b = 2L+1 (4L+2, 4L+3) ----
+    const uint64_t* E = reinterpret_cast<const uint64_t*>(&sm.e[4 * lane][0]);
+    const uint64_t* O = reinterpret_cast<const uint64_t*>(&sm.o[4 * lane][0]);
+    const uint64_t Tea = E[0], Bea = E[1], Teb = E[2], Beb = E[3];
+    const uint64_t Toa = O[0], Boa = O[1], Tob = O[2], Bob = O[3];
+    {
+      uint4* pp = w.pix + (int64_t)strip * 128 + 4 * lane;
+      pp[0] = make_uint4((uint32_t)Tea, (uint32_t)(Tea >> 32), (uint32_t)Toa, (uint32_t)(Toa >> 32));
+      pp[1] = make_uint4((uint32_t)Bea, (uint32_t)(Bea >> 32), (uint32_t)Boa, (uint32_t)(Boa >> 32));
+      pp[2] = make_uint4((uint32_t)Teb, (uint32_t)(Teb >> 32), (uint32_t)Tob, (uint32_t)(Tob >> 32));
+      pp[3] = make_uint4((uint32_t)Beb, (uint32_t)(Beb >> 32), (uint32_t)Bob, (uint32_t)(Bob >> 32));
+    }
+    const uint64_t Pea = Tea | Bea, Poa = Toa | Boa, Peb = Teb | Beb, Pob = Tob | Bob;
+    const uint64_t occa = Pea | Poa, occb = Peb | Pob;
+    const uint64_t hla = Pea & (Poa << 1), hlb = Peb & (Pob << 1);       // block k touches block k-1
+    const uint64_t rsa = occa & ~hla, rsb = occb & ~hlb;                  // run starts
+    w.rs[(int64_t)strip * 64 + 2 * lane] = make_uint2((uint32_t)rsa, (uint32_t)(rsa >> 32));
+    w.rs[(int64_t)strip * 64 + 2 * lane + 1] = make_uint2((uint32_t)rsb, (uint32_t)(rsb >> 32));
+    const int na = 2 * lane * 64, nb = na + 64;                           // node bases of the two block rows
+    for (uint64_t t = rsa; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[na + k] = na + k; }
+    for (uint64_t t = rsb; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[nb + k] = nb + k; }
+    // the block row above row a belongs to lane L-1 (its row b)
+    const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
+    const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
+    __syncwarp();
+    cw_contacts(sm.parent, na, na - 64, Tea, Toa, Ue, Uo, hla, hlU, rsa, rsU);
+    cw_contacts(sm.parent, nb, na, Teb, Tob, Bea, Boa, hlb, hla, rsb, rsa);
+    __syncwarp();
+    // ---- flatten: afterwards parent[run start] is the run's root ----
+    {
+      volatile int* vp = sm.parent;
+      for (uint64_t t = rsa; t; t &= t - 1) { const int n = na + __ffsll((long long)t) - 1; vp[n] = cw_find(vp, n); }
+      for (uint64_t t = rsb; t; t &= t - 1) { const int n = nb + __ffsll((long long)t) - 1; vp[n] = cw_find(vp, n); }
+    }
+    __syncwarp();
+    // ---- seam blocks: their roots touch a neighbouring strip ----
+    const int gbase = (int)ln.blk_off + s * 64;                          // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
+    {
+      volatile int* vp = sm.parent;
+      int* br = w.bnd_root + (int64_t)strip * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t occ = h ? occb : occa, rs = h ? rsb : rsa;
+        const int nbase = h ? nb : na, row = 2 * lane + h;
+        int left = -1, right = -1;
+        if (s > 0 && (occ & 1ull)) {
+          const int r = vp[nbase];                                       // block 0 has no left neighbour: it starts its run
+          atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
+          left = gbase + (r >> 6) * ln.bw + (r & 63);
+        }
+        if (s < ns - 1 && (occ >> 63)) {
+          const int r = vp[nbase + cw_run_start(rs, 63)];
+          atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
+          right = gbase + (r >> 6) * ln.bw + (r & 63);
+        }
+        br[row] = left; br[64 + row] = right;
+      }
+      // seam pixel columns 0 and 127 of the four pixel rows of this lane
+      const uint32_t l0 = __ballot_sync(0xffffffffu, Tea & 1ull), l1 = __ballot_sync(0xffffffffu, Bea & 1ull);
+      const uint32_t l2 = __ballot_sync(0xffffffffu, Teb & 1ull), l3 = __ballot_sync(0xffffffffu, Beb & 1ull);
+      const uint32_t r0 = __ballot_sync(0xffffffffu, Toa >> 63), r1 = __ballot_sync(0xffffffffu, Boa >> 63);
+      const uint32_t r2 = __ballot_sync(0xffffffffu, Tob >> 63), r3 = __ballot_sync(0xffffffffu, Bob >> 63);
+      if (lane == 0) {
+        uint4* bb = reinterpret_cast<uint4*>(w.bnd_bits + (int64_t)strip * 8);
+        bb[0] = make_uint4(l0, l1, l2, l3);
+        bb[1] = make_uint4(r0, r1, r2, r3);
+      }
+    }
+    __syncwarp();
+    // ---- one root entry per run (block-row major); interior roots -> bitmap, seam roots -> global parents ----
+    {
+      const int cnt = __popcll(rsa) + __popcll(rsb);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      uint16_t* out = w.roots + (int64_t)strip * kStripBlocks + (inc - cnt);
+      volatile int* vp = sm.parent;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nbase = h ? nb : na, row = 2 * lane + h;
+        uint64_t rootbits = 0ull;
+        for (uint64_t t = h ? rsb : rsa; t; t &= t - 1) {
+          const int k = __ffsll((long long)t) - 1;
+          const int r = vp[nbase + k];
+          const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
+          *out++ = (uint16_t)(r | (tch << 15));
+          if (r == nbase + k) {
+            if (tch) { const int g = gbase + row * ln.bw + k; w.parent[g] = g; }
+            else rootbits |= 1ull << k;
+          }
+        }
+        *reinterpret_cast<uint2*>(w.bitmap + (ln.blk_off >> 5) + (int64_t)row * (ln.bw >> 5) + s * 2) =
+            make_uint2((uint32_t)rootbits, (uint32_t)(rootbits >> 32));
+      }
+    }
+    __syncwarp();                                                          // shared memory is reused by the next strip
+  }
+}
+
+__device__ __forceinline__ int cw_uf_find(const int* __restrict__ parent, int a) {
+  int p = __ldcg(parent + a);
+  while (p != a) { a = p; p = __ldcg(parent + a); }
+  return a;
+}
+__device__ __forceinline__ void cw_uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = cw_uf_find(parent, a);
+    b = cw_uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+__device__ __forceinline__ uint32_t cw_col_bit(const uint32_t* __restrict__ p, int row) { return (p[row & 3] >> (row >> 2)) & 1u; }
+
+// CTA = line: seam unions, seam roots -> bitmap, exclusive scan of the root counts, island count; the last CTA to
+// finish turns the counts of all lines into stats row offsets (stat_off[l] = sum over lines < l of (num - 1)).
+__global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restrict__ L, int n_lines, CclWarpWork w,
+                                                        int* __restrict__ num_out, int64_t* __restrict__ stat_off) {
+  const int l = blockIdx.x, tid = threadIdx.x;
+  const sd_line ln = L[l];
+  const int ns = ln.bw >> 6;
+  const int64_t first = ln.blk_off >> 12;                               // first strip of the line
+  // 8-connectivity across the seams: pixel column 127 of strip sg-1 against pixel column 0 of strip sg
+  for (int i = tid; i < (ns - 1) * 64; i += blockDim.x) {
+    const int64_t sg = first + 1 + (i >> 6);
+    const int br = i & 63;
+    const int a = w.bnd_root[(sg - 1) * 128 + 64 + br];
+    if (a < 0) continue;
+    const int* Rr = w.bnd_root + sg * 128;
+    const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
+    const uint32_t* Rb = w.bnd_bits + sg * 8;
+    const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
+    const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
+    if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, Rr[br]);
+    if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, Rr[br - 1]);
+    if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, Rr[br + 1]);
+  }
+  __threadfence();
+  __syncthreads();
+  for (int i = tid; i < ns * 128; i += blockDim.x) {
+    const int k = w.bnd_root[first * 128 + i];
+    if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
+  }
+  __threadfence();
+  __syncthreads();
+  const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
+  int* prefix = w.prefix + (ln.blk_off >> 5);
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ int s_last;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  const int words = 2 * ln.bw;
+  for (int c = 0; c < words; c += blockDim.x * 4) {
+    const int i = c + tid * 4;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i < words) v = __ldcg(reinterpret_cast<const uint4*>(bitmap + i));
+    const int n0 = __popc(v.x), n1 = __popc(v.y), n2 = __popc(v.z), n3 = __popc(v.w);
+    const int tot = n0 + n1 + n2 + n3;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    int wv = (tid < 32) ? s_warp[tid] : 0;
+    if (tid < 32) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wv, o);
+        if (tid >= o) wv += t;
+      }
+    }
+    const int carry = s_carry;
+    __syncthreads();
+    if (tid < 32) s_warp[tid] = wv;
+    __syncthreads();
+    const int woff = (tid >> 5) ? s_warp[(tid >> 5) - 1] : 0;
+    const int ex = carry + woff + inc - tot;
+    if (i < words) *reinterpret_cast<int4*>(prefix + i) = make_int4(ex, ex + n0, ex + n0 + n1, ex + n0 + n1 + n2);
+    if (tid == blockDim.x - 1) s_carry = carry + woff + inc;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    num_out[l] = s_carry + 1;                                             // cv2 counts the background label
+    __threadfence();
+    s_last = (atomicAdd(w.ticket, 1u) == (unsigned)gridDim.x - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!stat_off || !s_last) return;
+  __threadfence();
+  // every line's count is final: exclusive scan over the lines (warp 0; a few thousand lines at most)
+  if (tid < 32) {
+    int64_t carry = 0;
+    for (int base = 0; base < n_lines; base += 32) {
+      const int i = base + tid;
+      const int64_t v = i < n_lines ? (int64_t)(__ldcg(num_out + i) - 1) : 0;
+      int64_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (i < n_lines) stat_off[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (tid == 0) stat_off[n_lines] = carry;
+  }
+}
+
+struct __align__(16) CwWriteSmem {
+  int lab[kStripBlocks];           // node (block row * 64 + first block of the run) -> final label
+  uint4 pix[128];
+  uint2 rs[64];
+};
+
+// statistics of one run, merged over the lanes whose current run carries the same label, then one set of atomics
+__device__ __forceinline__ void cw_stats_flush(int32_t* __restrict__ st_rows, int64_t cap_rows, int64_t row, uint32_t grp, int lane,
+                                               int minx, int miny, int maxx, int maxy, int area) {
+  minx = __reduce_min_sync(grp, minx); miny = __reduce_min_sync(grp, miny);
+  maxx = __reduce_max_sync(grp, maxx); maxy = __reduce_max_sync(grp, maxy);
+  area = __reduce_add_sync(grp, area);
+  if (lane == __ffs(grp) - 1 && row < cap_rows) {
+    int32_t* r = st_rows + row * 5;
+    atomicMin(r + 0, minx); atomicMin(r + 1, miny);
+    atomicMin(r + 2, kBigCoord - maxx); atomicMin(r + 3, kBigCoord - maxy);
+    atomicAdd(r + 4, area);
+  }
+}
+
+__global__ void __launch_bounds__(32 * kCw) ccl_warp_write_kernel(const sd_line* __restrict__ L, int n_lines, int n_strips, CclWarpWork w,
+                                                                  int* __restrict__ labels, const int64_t* __restrict__ stat_off,
+                                                                  int32_t* __restrict__ stats, int64_t cap_rows) {
+  extern __shared__ __align__(16) uint8_t cw_smem[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  CwWriteSmem& sm = reinterpret_cast<CwWriteSmem*>(cw_smem)[wp];
+  for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
+    const int64_t blk0 = (int64_t)strip * kStripBlocks;
+    const int li = cw_find_line(L, n_lines, blk0, lane);
+    const sd_line ln = L[li];
+    const int s = (int)((blk0 - ln.blk_off) >> 12);
+    const int gbase = (int)ln.blk_off + s * 64;
+    // ---- records of the strip: own rows in registers, everything in shared memory for the expansion ----
+    uint4 px[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { px[i] = __ldcs(w.pix + (int64_t)strip * 128 + 4 * lane + i); sm.pix[4 * lane + i] = px[i]; }
+    const uint2 ra2 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane), rb2 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane + 1);
+    sm.rs[2 * lane] = ra2; sm.rs[2 * lane + 1] = rb2;
+    const uint64_t rsa = ((uint64_t)ra2.y << 32) | ra2.x, rsb = ((uint64_t)rb2.y << 32) | rb2.x;
+    const int na = 2 * lane * 64, nb = na + 64;
+    const int cnt = __popcll(rsa) + __popcll(rsb);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const uint16_t* rt = w.roots + (int64_t)strip * kStripBlocks + (inc - cnt);
+    // pass 1: runs that are roots compute their final label
+    {
+      const uint16_t* p = rt;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nbase = h ? nb : na, row = 2 * lane + h;
+        for (uint64_t t = h ? rsb : rsa; t; t &= t - 1) {
+          const int k = __ffsll((long long)t) - 1;
+          const uint32_t rr = __ldg(p++);
+          if ((int)(rr & 0x7fffu) == nbase + k) {
+            int g = gbase + row * ln.bw + k;
+            if (rr >> 15) g = cw_uf_find(w.parent, g);
+            sm.lab[nbase + k] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // pass 2: every other run copies the label of its root; fused island statistics
+    {
+      const uint16_t* p = rt;
+      const bool do_stats = stats != nullptr;
+      int32_t* st_rows = do_stats ? stats : nullptr;
+      const int64_t row0 = do_stats ? __ldg(stat_off + li) : 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nbase = h ? nb : na, row = 2 * lane + h;
+        const uint64_t rs = h ? rsb : rsa;
+        const uint64_t Te = ((uint64_t)px[2 * h].y << 32) | px[2 * h].x, To = ((uint64_t)px[2 * h].w << 32) | px[2 * h].z;
+        const uint64_t Be = ((uint64_t)px[2 * h + 1].y << 32) | px[2 * h + 1].x, Bo = ((uint64_t)px[2 * h + 1].w << 32) | px[2 * h + 1].z;
+        const uint64_t occ = Te | To | Be | Bo;
+        for (uint64_t t = rs; t; t &= t - 1) {
+          const int k = __ffsll((long long)t) - 1;
+          const int root = (int)(__ldg(p++) & 0x7fffu);
+          const int lab = sm.lab[root];
+          if (root != nbase + k) sm.lab[nbase + k] = lab;
+          if (do_stats) {
+            // blocks of the run: occupied blocks from k up to the next run start
+            const uint64_t nxt = t & (t - 1);
+            const uint64_t upto = nxt ? ((nxt & (~nxt + 1ull)) - 1ull) : ~0ull;
+            const uint64_t M = occ & upto & ~((1ull << k) - 1ull);
+            const uint64_t Me = (Te | Be) & M, Mo = (To | Bo) & M;
+            int minx = 1 << 20, maxx = -1;
+            if (Me) { minx = 2 * (__ffsll((long long)Me) - 1); maxx = 2 * (63 - __clzll((long long)Me)); }
+            if (Mo) { minx = min(minx, 2 * (__ffsll((long long)Mo) - 1) + 1); maxx = max(maxx, 2 * (63 - __clzll((long long)Mo)) + 1); }
+            const bool top = ((Te | To) & M) != 0ull, bot = ((Be | Bo) & M) != 0ull;
+            const int miny = 2 * row + (top ? 0 : 1), maxy = 2 * row + (bot ? 1 : 0);
+            const int area = __popcll(Te & M) + __popcll(To & M) + __popcll(Be & M) + __popcll(Bo & M);
+            // the lanes that are at a run right now (trip counts differ) pool the runs that carry the same label
+            const uint32_t act = __activemask();
+            const uint32_t grp = __match_any_sync(act, lab);
+            cw_stats_flush(st_rows, cap_rows, row0 + lab - 1, grp, lane, s * 128 + minx, miny, s * 128 + maxx, maxy, area);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- expansion: one block row (two pixel rows) per iteration, a warp store = one 512-byte row segment ----
+    int* out = labels + ln.px_off + s * 128 + lane * 4;
+#pragma unroll 2
+    for (int br = 0; br < 64; ++br) {
+      const uint2 r2 = sm.rs[br];
+      const uint64_t rs = ((uint64_t)r2.y << 32) | r2.x;
+      const uint4 t4 = sm.pix[2 * br], b4 = sm.pix[2 * br + 1];
+      const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
+      const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
+      const uint32_t te = (uint32_t)(Te >> (2 * lane)) & 3u, to = (uint32_t)(To >> (2 * lane)) & 3u;
+      const uint32_t be = (uint32_t)(Be >> (2 * lane)) & 3u, bo = (uint32_t)(Bo >> (2 * lane)) & 3u;
+      int l0 = 0, l1 = 0;
+      if ((te | to | be | bo) & 1u) l0 = sm.lab[br * 64 + cw_run_start(rs, 2 * lane)];
+      if ((te | to | be | bo) & 2u) l1 = sm.lab[br * 64 + cw_run_start(rs, 2 * lane + 1)];
+      int4 a, b;
+      a.x = (te & 1u) ? l0 : 0; a.y = (to & 1u) ? l0 : 0; a.z = (te & 2u) ? l1 : 0; a.w = (to & 2u) ? l1 : 0;
+      b.x = (be & 1u) ? l0 : 0; b.y = (bo & 1u) ? l0 : 0; b.z = (be & 2u) ? l1 : 0; b.w = (bo & 2u) ? l1 : 0;
+      __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * br) * ln.pitch), a);
+      __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * br + 1) * ln.pitch), b);
+    }
+    __syncwarp();
+  }
+}
+
+// stats rows -> cv2 layout (x, y, w, h, area); grid-stride over the rows actually used
+__global__ void __launch_bounds__(256) ccl_stats_finish_kernel(int32_t* __restrict__ st, const int64_t* __restrict__ stat_off, int n_lines,
+                                                               int64_t cap_rows) {
+  int64_t rows = stat_off[n_lines];
+  if (rows > cap_rows) rows = cap_rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t* r = st + i * 5;
+    const int minx = r[0], miny = r[1], maxx = kBigCoord - r[2], maxy = kBigCoord - r[3];
+    r[2] = maxx - minx + 1; r[3] = maxy - miny + 1;
+    r[4] = (int32_t)((uint32_t)r[4] - (uint32_t)kStatFill);
+  }
+}
+
+}  // namespace sd

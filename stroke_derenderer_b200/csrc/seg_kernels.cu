@@ -703,6 +703,10 @@ __global__ void __launch_bounds__(256) ccl_strip_write_kernel(
   }
 }
 
+}  // namespace sd
+#include "ccl_warp.cuh"
+namespace sd {
+
 // ---------------------------------------------------------------------------
 // K8: island stats.  A thread scans 16 pixels of one row, merges equal-label
 // runs locally, then issues one set of atomics per run.
@@ -1006,6 +1010,13 @@ extern "C" int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, i
     ln.width = W;
     if (W < tile_w) { ln.n_tiles = 1; ln.wu = W; }               // helper/split.py:19-21
     else { ln.n_tiles = W / (tile_w - overlap) + 1; ln.wu = W / ln.n_tiles; }   // :25-26
+    // reconstruct_images pastes tile k at sum_{j<k} (width_j - overlap) (helper/split.py:119), which is k * wu only
+    // while no tile before the last one is clipped at the image edge, and the gather-form glue / fused head assume
+    // at most two tiles per column.  True for the default 384 / 64 geometry (wu >= 192); anything else is refused
+    // loudly instead of pasted differently from the reference.
+    SD_REQUIRE(ln.n_tiles == 1 || (overlap <= ln.wu && (int64_t)(ln.n_tiles - 1) * ln.wu + overlap <= W),
+               "sd_plan_lines: line %d (width %d): overlap %d is too large for tile stride %d (clipped inner tiles are not supported)",
+               i, W, overlap, ln.wu);
     ln.first_tile = tiles;
     ln.tile_w = tile_w; ln.overlap = overlap;
     ln.pitch = (W + 127) / 128 * 128;                 // whole 128-px CCL strips; rows start 128-B aligned
@@ -1248,9 +1259,72 @@ static int ccl_label_grid() {
 }
 }  // namespace sd
 
+namespace sd {
+// second-generation workspace (ccl_warp.cuh)
+static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
+  const size_t strips = (size_t)(blk_total / kStripBlocks);
+  size_t off = 0;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += up256(bytes); return r; };
+  int* parent = reinterpret_cast<int*>(take((size_t)blk_total * 4));
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(take((size_t)blk_total / 32 * 4));
+  int* prefix = reinterpret_cast<int*>(take((size_t)blk_total / 32 * 4));
+  uint4* pix = reinterpret_cast<uint4*>(take(strips * 128 * 16));
+  uint2* rs = reinterpret_cast<uint2*>(take(strips * 64 * 8));
+  uint16_t* roots = reinterpret_cast<uint16_t*>(take(strips * kStripBlocks * 2));
+  int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
+  uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(take(256));
+  if (w) { w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots;
+           w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; w->ticket = ticket; }
+  return off;
+}
+
+static int ccl_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// label (+ stats) with the warp-per-strip kernels
+static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t blk_total, int32_t* d_labels,
+                        int32_t* d_num, int64_t* d_stat_off, int32_t* d_stats, int64_t cap_rows, void* d_work, cudaStream_t s) {
+  CclWarpWork w;
+  ccl_warp_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
+  const int strips = (int)(blk_total / kStripBlocks);
+  const int smem_l = kCw * (int)sizeof(CwLabelSmem), smem_w = kCw * (int)sizeof(CwWriteSmem);
+  static PerDeviceOnce attr_once;
+  static int per_sm_l = 0, per_sm_w = 0, sms = 148;
+  if (attr_once.first()) {
+    SD_CUDA_CHECK(cudaFuncSetAttribute(ccl_warp_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));
+    SD_CUDA_CHECK(cudaFuncSetAttribute(ccl_warp_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, ccl_warp_label_kernel, 32 * kCw, smem_l);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, ccl_warp_write_kernel, 32 * kCw, smem_w);
+    if (per_sm_l < 1) per_sm_l = 1;
+    if (per_sm_w < 1) per_sm_w = 1;
+  }
+  const int ctas = (strips + kCw - 1) / kCw;
+  if (d_stats && cap_rows > 0) SD_CUDA_CHECK(cudaMemsetAsync(d_stats, 0x7f, (size_t)cap_rows * 20, s));
+  ccl_warp_label_kernel<<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
+  SD_LAUNCH_CHECK("ccl_warp_label_kernel");
+  ccl_line_kernel<<<n_lines, 1024, 0, s>>>(d_lines, n_lines, w, d_num, d_stat_off);
+  SD_LAUNCH_CHECK("ccl_line_kernel");
+  ccl_warp_write_kernel<<<std::min(ctas, sms * per_sm_w), 32 * kCw, smem_w, s>>>(d_lines, n_lines, strips, w, d_labels, d_stat_off,
+                                                                               d_stats, cap_rows);
+  SD_LAUNCH_CHECK("ccl_warp_write_kernel");
+  if (d_stats && cap_rows > 0) {
+    ccl_stats_finish_kernel<<<sms * 2, 256, 0, s>>>(d_stats, d_stat_off, n_lines, cap_rows);
+    SD_LAUNCH_CHECK("ccl_stats_finish_kernel");
+  }
+  return SD_OK;
+}
+}  // namespace sd
+
 extern "C" size_t sd_ccl_workspace_bytes(int64_t blk_total, int n_lines) {
   (void)n_lines;
-  return ccl_carve(nullptr, blk_total, nullptr) + 256;
+  return std::max(ccl_carve(nullptr, blk_total, nullptr), ccl_warp_carve(nullptr, blk_total, nullptr)) + 256;
 }
 
 extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
@@ -1260,6 +1334,8 @@ extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n
              "sd_ccl_label: bad totals");
   SD_REQUIRE(((uintptr_t)d_mask & 15) == 0 && ((uintptr_t)d_labels & 15) == 0, "sd_ccl_label: planes must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
+  if (ccl_env("SD_CCL_V1", 0) == 0)
+    return ccl_warp_run(d_mask, d_lines, n_lines, blk_total, d_labels, d_num, nullptr, nullptr, 0, d_work, s);
   CclWork w;
   ccl_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
   const int strips = (int)(blk_total / kStripBlocks);
@@ -1277,6 +1353,17 @@ extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n
   ccl_strip_write_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels);
   SD_LAUNCH_CHECK("ccl_strip_write_kernel");
   return SD_OK;
+}
+
+extern "C" int sd_ccl_label_stats(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
+                                  int64_t blk_total, int32_t* d_labels, int32_t* d_num, int64_t* d_stat_off,
+                                  int32_t* d_stats, int64_t cap_rows, void* d_work, void* stream) {
+  SD_REQUIRE(d_mask && d_lines && d_labels && d_num && d_stat_off && d_stats && d_work && n_lines > 0, "sd_ccl_label_stats: null argument");
+  SD_REQUIRE(blk_total > 0 && blk_total % SD_CCL_CHUNK == 0 && px_total == blk_total * 4 && blk_total < INT_MAX,
+             "sd_ccl_label_stats: bad totals");
+  SD_REQUIRE(cap_rows > 0, "sd_ccl_label_stats: cap_rows %lld", (long long)cap_rows);
+  SD_REQUIRE(((uintptr_t)d_mask & 15) == 0 && ((uintptr_t)d_labels & 15) == 0, "sd_ccl_label_stats: planes must be 16-byte aligned");
+  return ccl_warp_run(d_mask, d_lines, n_lines, blk_total, d_labels, d_num, d_stat_off, d_stats, cap_rows, d_work, (cudaStream_t)stream);
 }
 
 extern "C" int sd_island_stats(const int32_t* d_labels, const sd_line* d_lines, int n_lines, int64_t px_total,

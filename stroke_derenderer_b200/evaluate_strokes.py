@@ -72,10 +72,15 @@ class StrokeEstimationSession:
                 batch = _seg.plan_batch([m.shape[1] for m in masks], dev)
                 h = seg.staging.get_tensor((key, "masks"), batch.px_total)
                 hn = h.numpy()
-                hn[:] = 0
                 for m, ln in zip(masks, batch.lines):
-                    off, pitch = int(ln["px_off"]), int(ln["pitch"])
-                    hn[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)[:, :m.shape[1]] = np.asarray(m) != 0
+                    off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(m.shape[1])
+                    view = hn[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)
+                    m = np.asarray(m)
+                    if m.dtype == np.bool_:
+                        view[:, :w] = m                   # img_bin.astype(np.uint8) of :193
+                    else:
+                        np.not_equal(m, 0, out=view[:, :w], casting="unsafe")
+                    view[:, w:] = 0                       # pad columns of the plane must be zero (CCL strips)
                 planes = h.to(dev, non_blocking=True)
                 res = seg.partition(batch, planes, canvases="device", key=key, crops=True, crops_to_host=True,
                                     crop_lut=lut if keep_device else None)

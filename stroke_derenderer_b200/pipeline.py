@@ -119,7 +119,7 @@ class LineSegmentationJob:
         self.n_lines = sum(c.batch.n_lines for c in self.chunks)
         self.px_total = sum(c.batch.px_total for c in self.chunks)
 
-    def _run(self, from_host: bool, canvases: str, writer: G.RegionWriter | None = None):
+    def _run(self, from_host: bool, canvases: str, writer: G.RegionWriter | None = None, collect=None):
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             for st in (self.s_copy, self.s_unet, self.s_part):
@@ -171,6 +171,10 @@ class LineSegmentationJob:
                     res = self.seg.partition(ch.batch, ch.planes, canvases=canvases, key=key, zero_copy=True,
                                              crops=self.crops, staging=st, crops_to_host=from_host)
                     res["planes_host"] = h_planes
+                    if collect is not None:           # per-line outputs of this chunk, built while the GPU is on later chunks
+                        if canvases != "host":
+                            self.s_part.synchronize()
+                        collect(ch, res)
                     if writer is not None:
                         writer.put(ch.index, "groups", res["groups"].reshape(-1, 6))
                         writer.put(ch.index, "lgs", res["line_group_start"])
@@ -230,9 +234,10 @@ class LineSegmentationJob:
                         glued += 1
             for ch, ev, hp in zip(self.chunks, evs, hosts):
                 ev.synchronize()
+                hp = hp.copy()                        # one fresh array per chunk; a line's mask is a view into it
                 for ln in ch.batch.lines:
                     off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
-                    out.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None].copy())
+                    out.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
             cur.wait_stream(self.s_unet)
         return out
 
@@ -258,31 +263,36 @@ class LineSegmentationJob:
         return G.region_capacity(self.n_tiles, self.n_lines, self.px_total, max(len(self.chunks), 1))
 
     # ---- per-line outputs in the reference's shapes ------------------------------------------------------------
-    def line_outputs(self, results, copy: bool = True, mean=None, std=None):
-        """After `host_step`: ([mask (128, W', 1) u8 {0,255}], [[partition dict]]) per line, in this job's line
-        order — what `BinarizationSession.binarize_images` (evaluate_binarize.py:130-140) and
-        `StrokeEstimationSession.get_partitions` (evaluate_strokes.py:186-224) return.  `image_input` of a partition
-        is materialised on first access (`LazyPartition`)."""
+    def chunk_outputs(self, ch, res, lut, copy: bool = True):
+        """([mask (128, W', 1) u8 {0,255}], [[partition dict]]) for the lines of one finished chunk — what
+        `BinarizationSession.binarize_images` (evaluate_binarize.py:130-140) and
+        `StrokeEstimationSession.get_partitions` (evaluate_strokes.py:186-224) return.  `image_input` of a
+        partition is materialised on first access (`segment.LazyPartition`)."""
         masks, parts = [], []
-        lut = S.input_lut(mean if mean is not None else S.IMAGENET_MEAN, std if std is not None else S.IMAGENET_STD)
-        for ch, res in zip(self.chunks, results):
-            hp = res["planes_host"]
-            cr = res["crops"]
-            img_host = cr["image_host"] if cr is not None and "image_host" in cr else None
-            groups, lgs = res["groups"], res["line_group_start"]
-            if img_host is not None and copy:
+        hp = res["planes_host"]
+        cr = res["crops"]
+        img_host = cr["image_host"] if cr is not None and "image_host" in cr else None
+        groups, lgs = res["groups"], res["line_group_start"]
+        if copy:
+            hp = hp.copy()
+            if img_host is not None:
                 img_host = img_host.copy()
-            for k, ln in enumerate(ch.batch.lines):
-                off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
-                m = hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None]
-                masks.append(m.copy() if copy else m)
-                a, b = int(lgs[k]), int(lgs[k + 1])
-                pl = []
-                for g in range(a, b):
-                    pl.append(S.LazyPartition(lut, image=img_host[g], translate1=(groups[g, 1], groups[g, 2]),
-                                              ratio=float(cr["ratio"][g]),
-                                              translate2=(float(cr["translate2"][g, 0]), float(cr["translate2"][g, 1]))))
-                parts.append(pl)
+        ratio, t2 = (cr["ratio"], cr["translate2"]) if cr is not None else (None, None)
+        for k, ln in enumerate(ch.batch.lines):
+            off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
+            masks.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
+            a, b = int(lgs[k]), int(lgs[k + 1])
+            parts.append([S.LazyPartition(lut, image=img_host[g], translate1=(groups[g, 1], groups[g, 2]), ratio=float(ratio[g]),
+                                          translate2=(float(t2[g, 0]), float(t2[g, 1]))) for g in range(a, b)])
+        return masks, parts
+
+    def line_outputs(self, results, copy: bool = True, mean=None, std=None):
+        """After `host_step`: per-line masks and partitions of the whole job, in this job's line order."""
+        lut = S.input_lut(mean if mean is not None else S.IMAGENET_MEAN, std if std is not None else S.IMAGENET_STD)
+        masks, parts = [], []
+        for ch, res in zip(self.chunks, results):
+            m, p = self.chunk_outputs(ch, res, lut, copy)
+            masks += m; parts += p
         return masks, parts
 
 
@@ -290,7 +300,14 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
                   copy: bool = True):
     """The fused public call on one GPU: a list of (h, w, 3) u8 line images (plain numpy) in, per line the
     binarized mask and the stroke-estimator partitions out, in input order — `binarize_image` + `main.py:108` +
-    `get_partitions` of the reference for every image, as one pipelined job."""
+    `get_partitions` of the reference for every image, as one pipelined job.  A mask is a (128, W', 1) view into one
+    fresh array per chunk of lines (`copy=False`: into the reused page-locked staging, valid until the next call)."""
     job = LineSegmentationJob(engine, images, bin_thr=bin_thr, lines_per_chunk=lines_per_chunk, crops=True, prepack=False, seg=seg)
-    res = job.host_step()
-    return job.line_outputs(res, copy=copy)
+    lut = S.input_lut(S.IMAGENET_MEAN, S.IMAGENET_STD)
+    masks, parts = [], []
+
+    def collect(ch, res):
+        m, p = job.chunk_outputs(ch, res, lut, copy)
+        masks.extend(m); parts.extend(p)
+    job._run(True, "device", collect=collect)
+    return masks, parts

@@ -193,6 +193,29 @@ def ccl_label(batch: LineBatch, planes: torch.Tensor, work: torch.Tensor | None 
     return labels, num
 
 
+def stats_capacity(batch: LineBatch) -> int:
+    """Rows reserved for the fused island statistics: ~6x the island density of handwriting-like lines
+    (~20 islands per 1000 px of line width); a batch that needs more is re-run with the exact count."""
+    return int(batch.px_total // (TILE_H * 8)) + 1024
+
+
+def ccl_label_stats(batch: LineBatch, planes: torch.Tensor, cap_rows: int, work: torch.Tensor | None = None):
+    """Labels + cv2-layout island stats in one pass (sd_ccl_label_stats).
+    -> (labels int32 packed planes, meta uint8 = [stat_off int64 (n_lines+1) | num int32 (n_lines)], stats int32 (cap_rows, 5))."""
+    L = _lib.lib()
+    need = L.sd_ccl_workspace_bytes(batch.blk_total, batch.n_lines)
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=torch.uint8, device=batch.device)
+    n = batch.n_lines
+    labels = torch.empty(batch.px_total, dtype=torch.int32, device=batch.device)
+    meta = torch.empty(8 * (n + 1) + 4 * n, dtype=torch.uint8, device=batch.device)
+    stats = torch.empty((cap_rows, 5), dtype=torch.int32, device=batch.device)
+    _lib.check(L.sd_ccl_label_stats(planes.data_ptr(), batch.d_lines.data_ptr(), n, batch.px_total, batch.blk_total,
+                                    labels.data_ptr(), meta.data_ptr() + 8 * (n + 1), meta.data_ptr(), stats.data_ptr(), cap_rows,
+                                    work.data_ptr(), _s(batch)), "sd_ccl_label_stats")
+    return labels, meta, stats
+
+
 def island_stats(batch: LineBatch, labels: torch.Tensor, num_host: np.ndarray):
     """-> (stats int32 (rows,5) = x,y,w,h,area per label, stat_off int64[n_lines+1] host, d_stat_off)."""
     counts = np.asarray(num_host, dtype=np.int64) - 1
@@ -410,6 +433,8 @@ class Segmenter:
     + `get_binarized_islands` + `group_islands` of the reference, but every stage
     runs once over the whole batch."""
 
+    SPEC_ROWS = 16384       # stats rows copied to the host together with the counts (one sync for typical chunks)
+
     def __init__(self, engine: UNetEngine | None, bin_thr: float = 0.5, margin: int = MARGIN, device=None):
         self.engine = engine
         self.device = engine.device if engine is not None else torch.device(device)
@@ -448,16 +473,30 @@ class Segmenter:
         st = staging if staging is not None else self.staging
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device)
-            labels, num = ccl_label(batch, planes)
-            h_num = copy_d2h(st.get((key, "num"), batch.n_lines * 4), num, self.device).view(np.int32)
+            n = batch.n_lines
+            # labels and the cv2 stats rows in ONE pass (no second read of the labels); counts, row offsets and a
+            # first slice of the rows come back in one D2H + one sync
+            cap = stats_capacity(batch)
+            labels, meta, stats = ccl_label_stats(batch, planes, cap)
+            spec = min(cap, self.SPEC_ROWS)
+            h_meta = copy_d2h(self.staging.get((key, "meta"), meta.numel()), meta, self.device)
+            h_spec = copy_d2h(self.staging.get((key, "spec"), spec * 20), stats[:spec], self.device)
             stream.synchronize()
-            num_h = h_num if zero_copy else h_num.copy()
-            stats, stat_off, d_off = island_stats(batch, labels, num_h)
+            stat_off = h_meta[:8 * (n + 1)].view(np.int64).copy()
             rows = int(stat_off[-1])
+            if rows > cap:                            # denser than the reserve: once more with the exact room
+                labels, meta, stats = ccl_label_stats(batch, planes, rows)
+                cap, spec = rows, 0
+            h_num = st.get((key, "num"), n * 4).view(np.int32)
+            h_num[:] = h_meta[8 * (n + 1):].view(np.int32)
             h_stats = st.get((key, "stats"), rows * 20).view(np.int32).reshape(rows, 5)
-            if rows:
-                copy_d2h(h_stats, stats, self.device)
-            stream.synchronize()
+            if rows <= spec:
+                h_stats[:] = h_spec.view(np.int32).reshape(-1, 5)[:rows]
+            elif rows:
+                copy_d2h(h_stats, stats[:rows], self.device)
+                stream.synchronize()
+            d_off = meta[:8 * n].view(torch.int64)
+            num_h = h_num if zero_copy else h_num.copy()
             stats_h = h_stats if zero_copy else h_stats.copy()
             groups, group_of, lgs, cbytes = _lib.group_lines(stats_h, stat_off, batch.widths, self.margin, TILE_H, TILE_H)
             res = PartitionResult(labels=labels, num=num_h, stats=stats_h, stat_off=stat_off, groups=groups,

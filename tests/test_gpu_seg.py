@@ -97,11 +97,13 @@ def test_glue_random_values_and_threshold(cuda_device):
         assert np.array_equal(batch.plane(pl, i).cpu().numpy(), ref[i][:, :, 0]), widths[i]
 
 
-def test_glue_large_overlap_three_or_more_covering_tiles(cuda_device):
-    """helper/split.py accepts any 0 <= overlap < tile_w; at overlap 200 / 300 a column is covered by 3 / 5 tiles and
-    reconstruct_images takes the max over all of them (glue used to look at two tiles only)."""
+def test_glue_other_overlaps_and_paste_table(cuda_device):
+    """helper/split.py accepts any 0 <= overlap < tile_w.  Overlaps up to the tile stride are glued bit-exactly; beyond
+    that reconstruct_images pastes clipped inner tiles at shifted positions (s += width - overlap), which the gather
+    form does not reproduce: sd_plan_lines refuses those geometries instead of returning a different mask."""
+    from stroke_derenderer_b200 import _lib
     rng = np.random.default_rng(23)
-    for overlap in (0, 64, 200, 300, 380):
+    for overlap in (0, 64, 100, 150):
         widths = [384, 500, 1000, 2000, 777]
         batch = S.plan_batch(widths, torch.device("cuda", 0), overlap=overlap)
         vals = rng.integers(0, 256, (batch.n_tiles, 1, 128, 384), dtype=np.uint8)
@@ -111,13 +113,16 @@ def test_glue_large_overlap_three_or_more_covering_tiles(cuda_device):
             assert ref[i].shape[1] == w
             assert np.array_equal(batch.plane(planes, i).cpu().numpy(), ref[i][:, :, 0]), (overlap, w)
         # the paste table of the fused head names the same positions
-        tab = __import__("stroke_derenderer_b200._lib", fromlist=["x"]).tile_dst_table(batch.lines, 0)
+        tab = _lib.tile_dst_table(batch.lines, 0)
         k = 0
         for ln, ws in zip(batch.lines, batch.stack_widths()):
             for i, wd in enumerate(ws):
                 start = 0 if int(ln["n_tiles"]) == 1 else i * int(ln["wu"])
                 assert int(tab[k]["d_dst"]) == int(ln["px_off"]) + start and int(tab[k]["width"]) == min(wd, 384) and int(tab[k]["pitch"]) == int(ln["pitch"])
                 k += 1
+    for overlap in (200, 300, 380):
+        with pytest.raises(_lib.SdError):
+            S.plan_batch([384, 1000], torch.device("cuda", 0), overlap=overlap)
 
 
 def test_cut_identity_glue_roundtrip_full_size(cuda_device):
@@ -191,6 +196,40 @@ def test_ccl_dense_config5(cuda_device):
         n, ref = cv2.connectedComponents(m)
         assert int(num[i].item()) == n
         assert np.array_equal(batch.plane(labels, i).cpu().numpy(), ref)
+
+
+def test_ccl_label_stats_fused_vs_cv2(cuda_device):
+    """sd_ccl_label_stats: labels AND the cv2 stats rows (x, y, w, h, area) from one pass, bit-exact against
+    cv2.connectedComponentsWithStats on text-like, random, dense and degenerate masks; row offsets = exclusive scan
+    of the island counts; a too-small row reserve is reported through stat_off[n_lines] (rows beyond it dropped)."""
+    import cv2
+    rng = np.random.default_rng(77)
+    masks = [ink_mask(synth_line(int(w), seed=300 + i)) for i, w in enumerate([700, 3072, 129, 6144, 128, 2222])]
+    for k in range(10):
+        W = int(rng.integers(1, 1500))
+        m = (rng.random((128, W)) < rng.choice([0.02, 0.2, 0.5, 0.8])).astype(np.uint8)
+        masks.append(cv2.dilate(m, np.ones((2, 2), np.uint8)) if k % 2 else m)
+    masks += [synth_dense_mask(4096, 0.01, 5), np.zeros((128, 300), np.uint8), np.ones((128, 257), np.uint8),
+              np.eye(128, dtype=np.uint8), np.fliplr(np.eye(128, dtype=np.uint8))]
+    batch, planes = _pack_masks(masks)
+    for cap in (S.stats_capacity(batch) * 4, 100):
+        labels, meta, stats = S.ccl_label_stats(batch, planes, cap)
+        torch.cuda.synchronize()
+        n = batch.n_lines
+        meta_h = meta.cpu().numpy()
+        stat_off, num = meta_h[:8 * (n + 1)].view(np.int64), meta_h[8 * (n + 1):].view(np.int32)
+        st = stats.cpu().numpy()
+        exp_off = 0
+        for i, m in enumerate(masks):
+            rn, rl, rs, _ = cv2.connectedComponentsWithStats(m)
+            assert int(num[i]) == rn and int(stat_off[i]) == exp_off, i
+            assert np.array_equal(batch.plane(labels, i).cpu().numpy(), rl), i
+            a, b = exp_off, min(exp_off + rn - 1, cap)
+            if b > a:
+                assert np.array_equal(st[a:b], rs[1:1 + b - a]), (i, cap)
+            exp_off += rn - 1
+        assert int(stat_off[n]) == exp_off
+        assert exp_off > 100                          # the second round really overflows its reserve
 
 
 def test_partition_matches_reference_golden(cuda_device, golden, golden_arrays):
