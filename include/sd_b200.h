@@ -96,6 +96,9 @@ typedef struct sd_engine sd_engine;
 
 const char* sd_last_error(void);
 int sd_version(void);
+/* "f16" or "bf16": the 16-bit operand type this library was built for (activations, packed weights, the tiles of
+ * sd_tile_extract_f16 and the taps of sd_unet_read_tap); accumulation is fp32 either way. */
+const char* sd_operand_dtype(void);
 /* 1 if a CUDA device is usable from this process, else 0. */
 int sd_cuda_available(void);
 

@@ -49,6 +49,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "sd_last_error": (C.c_char_p, []),
     "sd_version": (C.c_int, []),
+    "sd_operand_dtype": (C.c_char_p, []),
     "sd_cuda_available": (C.c_int, []),
     "sd_launch_count": (C.c_int64, []),
     "sd_plan_lines": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(Plan)]),
@@ -101,11 +102,24 @@ class SdError(RuntimeError):
 _lib = None
 
 
+def operand_dtype() -> str:
+    """Operand type of the UNet in this process: "f16" (default, the parity build) or "bf16" (SD_DTYPE=bf16 selects
+    libsd_b200_bf16.so, the same sources built with -DSD_BF16)."""
+    import os
+    dt = os.environ.get("SD_DTYPE", "f16").lower()
+    return {"fp16": "f16", "half": "f16", "bfloat16": "bf16"}.get(dt, dt)
+
+
+def torch_dtype():
+    import torch
+    return torch.bfloat16 if operand_dtype() == "bf16" else torch.float16
+
+
 def lib() -> C.CDLL:
     """Loads (building first if needed) the native library; raises if impossible."""
     global _lib
     if _lib is None:
-        path = _build.build()          # no-op when the in-tree library matches the sources (digest stamp)
+        path = _build.build(dtype=operand_dtype())   # no-op when the in-tree library matches the sources (digest stamp)
         handle = C.CDLL(str(path))
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)      # AttributeError if the symbol is missing

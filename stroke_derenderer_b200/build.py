@@ -16,7 +16,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "libsd_b200.so"
+LIB = HERE / "libsd_b200.so"                 # fp16 operands (the parity build)
+LIB_BF16 = HERE / "libsd_b200_bf16.so"       # same sources with -DSD_BF16 (bf16 operands)
 SOURCES = ["sd_api.cu", "seg_kernels.cu", "unet.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -40,20 +41,24 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compiles csrc/*.cu for sm_100a and links libsd_b200.so (no-op if up to date)."""
-    stamp = HERE / "csrc" / "build" / "stamp"
+def build(force: bool = False, verbose: bool = False, dtype: str = "f16") -> Path:
+    """Compiles csrc/*.cu for sm_100a and links the library of the given operand type (no-op if up to date)."""
+    if dtype not in ("f16", "bf16"):
+        raise ValueError(f"dtype {dtype!r}: f16 or bf16")
+    lib = LIB if dtype == "f16" else LIB_BF16
+    extra = [] if dtype == "f16" else ["-DSD_BF16"]
+    bdir = CSRC / "build" / dtype
+    stamp = bdir / "stamp"
     digest = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
-        return LIB
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == digest:
+        return lib
     nvcc = _nvcc()
-    bdir = CSRC / "build"
-    bdir.mkdir(exist_ok=True)
+    bdir.mkdir(parents=True, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = bdir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -64,13 +69,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out, file=sys.stderr)
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", str(lib), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
     stamp.write_text(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    for dt in ("f16", "bf16"):
+        print(build(force="--force" in sys.argv, verbose=True, dtype=dt))

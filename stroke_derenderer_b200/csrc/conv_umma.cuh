@@ -46,12 +46,12 @@ struct ConvParams {
   int relu;
   int8_t dy[4][9], dx[4][9];
   const float* bias;           // [cout]
-  __half* out;                 // NHWC fp16, channels = out_c
+  act_t* out;                 // NHWC fp16, channels = out_c
   int out_c;
   // gate epilogue
   const float* psi_w;          // [cout] fp32
   float psi_b;
-  const __half* gate_x;        // skip tensor to scale, NHWC with gate_c channels
+  const act_t* gate_x;        // skip tensor to scale, NHWC with gate_c channels
   int gate_c;
   // head epilogue
   const float* head_w;         // [cout]
@@ -180,7 +180,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
-  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  act2_t r = __hmax2(*reinterpret_cast<act2_t*>(&a), *reinterpret_cast<act2_t*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ uint4 hmax2_v4(uint4 a, uint4 b) {
@@ -208,7 +208,7 @@ template <int BN, int EPI, int MT = 1> struct ConvCfg {
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTmemCols = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // 64,128,256,512: powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + kMiscBytes;
-  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(kStages >= 3, "pipeline too shallow");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(EPI != EPI_STORE || BN % 64 == 0, "store epilogue writes 64-channel boxes");
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
                   const int col = j4 * 8 + j * 2;
                   float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
                   if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                  __half2 h = __floats2half2_rn(a, b);
+                  act2_t h = floats2act2(a, b);
                   pk[j] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 const uint32_t chunk = (uint32_t)(cc * 4 + j4);
@@ -493,11 +493,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
               for (int j = 0; j < 8; ++j) {
                 const uint32_t addr = sw128(buf, row, j);
                 uint4 t = ld_shared_v4(addr);
-                __half2* h = reinterpret_cast<__half2*>(&t);
+                act2_t* h = reinterpret_cast<act2_t*>(&t);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float2 f = __half22float2(h[k]);
-                  h[k] = __floats2half2_rn(f.x * sc, f.y * sc);
+                  float2 f = act22float2(h[k]);
+                  h[k] = floats2act2(f.x * sc, f.y * sc);
                 }
                 st_shared_v4(addr, t);
               }
@@ -519,11 +519,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 uint4 t = xpre[c];
-                __half2* h = reinterpret_cast<__half2*>(&t);
+                act2_t* h = reinterpret_cast<act2_t*>(&t);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  float2 f = __half22float2(h[j]);
-                  h[j] = __floats2half2_rn(f.x * sc, f.y * sc);
+                  float2 f = act22float2(h[j]);
+                  h[j] = floats2act2(f.x * sc, f.y * sc);
                 }
                 xo[c0 + c] = t;
               }
@@ -579,7 +579,7 @@ struct Conv2Cfg {
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;   // 6
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kMiscBytes;
-  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = 256
+  static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = 256
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -769,7 +769,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
               const int col = j4 * 8 + j * 2;
               float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
               if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              __half2 h = __floats2half2_rn(a, b);
+              act2_t h = floats2act2(a, b);
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
             const uint32_t chunk = (uint32_t)(cc * 4 + j4);
@@ -975,8 +975,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
             tc_fence_after();
           }
           const int n1 = min(nr, 8 - s_lo), n2 = nr - n1;   // window split at the end of the ring
-          const uint32_t idesc1 = (1u << 4) | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
-          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc1 = kIdescBase | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc2 = kIdescBase | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
           const uint32_t d1 = tmem_base + (uint32_t)(s_lo * 64);
           for (int cb = 0; cb < CB; ++cb) {
             mbar_wait(full_bar(stage), phase, p.err_flag, 3);
@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
               for (int j = 0; j < 4; ++j) {
                 const int col = j4 * 8 + j * 2;
                 float a = fmaxf(v[col] + p.bias_c[c * 32 + col], 0.f), b2 = fmaxf(v[col + 1] + p.bias_c[c * 32 + col + 1], 0.f);
-                __half2 h = __floats2half2_rn(a, b2);
+                act2_t h = floats2act2(a, b2);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
               }
               const uint32_t chunk = (uint32_t)(c * 4 + j4);
@@ -1226,8 +1226,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
           const Up4Tap tp = up4_tap(t);
           const int first = tp.first, count = tp.count;
           const int n1 = count < 4 - first ? count : 4 - first, n2 = count - n1;       // split where the slot ring wraps
-          const uint32_t idesc1 = (1u << 4) | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
-          const uint32_t idesc2 = (1u << 4) | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc1 = kIdescBase | ((uint32_t)(n1 * 8) << 17) | ((128u >> 4) << 24);
+          const uint32_t idesc2 = kIdescBase | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
           for (int cb = 0; cb < cbs; ++cb) {
             mbar_wait(full_bar(stage), phase, p.err_flag, 3);
             tc_fence_after();
@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
             for (int j = 0; j < 4; ++j) {
               const int col = j4 * 8 + j * 2;
               float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
-              __half2 h = __floats2half2_rn(a, b);
+              act2_t h = floats2act2(a, b);
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
             const uint32_t chunk = (uint32_t)(c * 4 + j4);
@@ -1352,7 +1352,7 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv_first_umma_kernel(const __
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC1Stages + 2 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 248);
   float* s_bias = reinterpret_cast<float*>(misc + 256);
-  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -1453,7 +1453,7 @@ __global__ void __launch_bounds__(kC1Threads, 2) conv_first_umma_kernel(const __
           for (int j = 0; j < 4; ++j) {
             const int col = j4 * 8 + j * 2;
             float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
-            __half2 h = __floats2half2_rn(a, b);
+            act2_t h = floats2act2(a, b);
             pk[j] = *reinterpret_cast<uint32_t*>(&h);
           }
           const uint32_t chunk = (uint32_t)(c * 4 + j4);

@@ -14,7 +14,8 @@ void set_error(const char* fmt, ...) {
 }  // namespace sd
 
 extern "C" const char* sd_last_error(void) { return sd::g_err; }
-extern "C" int sd_version(void) { return 100; }
+extern "C" int sd_version(void) { return 200; }
+extern "C" const char* sd_operand_dtype(void) { return SD_DTYPE_NAME; }
 extern "C" int64_t sd_launch_count(void) { return sd::g_launches.load(); }
 extern "C" int sd_cuda_available(void) {
   int n = 0;

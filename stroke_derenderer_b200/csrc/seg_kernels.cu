@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(128) tile_extract_f16_kernel(
       // x/255 is never within an f32 ulp of an fp16 rounding boundary, so the
       // f32 division rounds to the same half as numpy's float64 path (tested
       // for all 256 values).
-      __half2 rg = __floats2half2_rn((float)px[r][0] / 255.f, (float)px[r][1] / 255.f);
-      __half2 b0 = __floats2half2_rn((float)px[r][2] / 255.f, 0.f);
+      act2_t rg = floats2act2((float)px[r][0] / 255.f, (float)px[r][1] / 255.f);
+      act2_t b0 = floats2act2((float)px[r][2] / 255.f, 0.f);
       uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&rg), *reinterpret_cast<uint32_t*>(&b0), 0u, 0u);
       out[((int64_t)tile * SD_TILE_H + row0 + r) * tile_w + x] = v;
     }

@@ -23,7 +23,7 @@ namespace sd {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) conv_first_kernel(
     const uint2* __restrict__ in /* NHWC8: 16 B/px, first 8 B = r,g,b,0 */, const float* __restrict__ w /* [27][64] */,
-    const float* __restrict__ bias, __half* __restrict__ out, int B, int H, int W) {
+    const float* __restrict__ bias, act_t* __restrict__ out, int B, int H, int W) {
   __shared__ float4 sw[27 * 16];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(128) conv_first_kernel(
       float c[3] = {0.f, 0.f, 0.f};
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
         const uint2 v = __ldg(in + (pix + (int64_t)(ky - 1) * W + (kx - 1)) * 2);
-        const __half2 rg = *reinterpret_cast<const __half2*>(&v.x);
-        const __half2 b0 = *reinterpret_cast<const __half2*>(&v.y);
+        const act2_t rg = *reinterpret_cast<const act2_t*>(&v.x);
+        const act2_t b0 = *reinterpret_cast<const act2_t*>(&v.y);
         c[0] = __low2float(rg); c[1] = __high2float(rg); c[2] = __low2float(b0);
       }
 #pragma unroll
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(
     uint32_t* tw = reinterpret_cast<uint32_t*>(&t);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      __half2 h = __floats2half2_rn(fmaxf(acc[8 * j + 2 * k], 0.f), fmaxf(acc[8 * j + 2 * k + 1], 0.f));
+      act2_t h = floats2act2(fmaxf(acc[8 * j + 2 * k], 0.f), fmaxf(acc[8 * j + 2 * k + 1], 0.f));
       tw[k] = *reinterpret_cast<uint32_t*>(&h);
     }
     o[j] = t;
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const uint4* __restrict__ 
   const int Wi = 2 * Wo;
   const uint4* p = in + (((n * 2 * Ho + 2 * y) * Wi + 2 * x) * C8 + c);
   uint4 a = __ldg(p), b = __ldg(p + C8), d = __ldg(p + (int64_t)Wi * C8), e = __ldg(p + (int64_t)Wi * C8 + C8);
-  __half2* ha = reinterpret_cast<__half2*>(&a); const __half2* hb = reinterpret_cast<const __half2*>(&b);
-  const __half2* hd = reinterpret_cast<const __half2*>(&d); const __half2* he = reinterpret_cast<const __half2*>(&e);
+  act2_t* ha = reinterpret_cast<act2_t*>(&a); const act2_t* hb = reinterpret_cast<const act2_t*>(&b);
+  const act2_t* hd = reinterpret_cast<const act2_t*>(&d); const act2_t* he = reinterpret_cast<const act2_t*>(&e);
 #pragma unroll
   for (int k = 0; k < 4; ++k) ha[k] = __hmax2(__hmax2(ha[k], hb[k]), __hmax2(hd[k], he[k]));
   out[i] = a;
@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const uint4* __restrict__ 
 // nearest-x2 gather.  64 px x 64 cout per CTA, 4x4 per thread.
 // ---------------------------------------------------------------------------
 struct SimtConv {
-  const __half* in0; const __half* in1; int c0, c1;
-  const __half* w;           // [taps][c0+c1][cout]
+  const act_t* in0; const act_t* in1; int c0, c1;
+  const act_t* w;           // [taps][c0+c1][cout]
   const float* bias;
-  __half* out; float* out32;
+  act_t* out; float* out32;
   int B, H, W, cout, ks, up, relu;
 };
 
@@ -133,12 +133,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConv a) {
       float2 av = make_float2(0.f, 0.f);
       if (inb) {
         const int c = cb + lc;
-        const __half* src = (c < a.c0) ? a.in0 + ip * a.c0 + c : a.in1 + ip * a.c1 + (c - a.c0);
-        av = __half22float2(*reinterpret_cast<const __half2*>(src));
+        const act_t* src = (c < a.c0) ? a.in0 + ip * a.c0 + c : a.in1 + ip * a.c1 + (c - a.c0);
+        av = act22float2(*reinterpret_cast<const act2_t*>(src));
       }
       As[lc][lp] = av.x; As[lc + 1][lp] = av.y;
       float2 wv = make_float2(0.f, 0.f);
-      if (n0 + wn < a.cout) wv = __half22float2(*reinterpret_cast<const __half2*>(a.w + ((int64_t)t * cin + cb + wc) * a.cout + n0 + wn));
+      if (n0 + wn < a.cout) wv = act22float2(*reinterpret_cast<const act2_t*>(a.w + ((int64_t)t * cin + cb + wc) * a.cout + n0 + wn));
       Ws[wc][wn] = wv.x; Ws[wc][wn + 1] = wv.y;
       __syncthreads();
 #pragma unroll
@@ -164,27 +164,27 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConv a) {
       float v = acc[i][j] + a.bias[n];
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.out32) a.out32[m * a.cout + n] = v;
-      else a.out[m * a.cout + n] = __float2half_rn(v);
+      else a.out[m * a.cout + n] = f2act(v);
     }
   }
 }
 
 __global__ void gate_apply_kernel(const float* __restrict__ q, const float* __restrict__ psi_w, float psi_b,
-                                  const __half* __restrict__ x, __half* __restrict__ out, int64_t M, int fint, int fl) {
+                                  const act_t* __restrict__ x, act_t* __restrict__ out, int64_t M, int fint, int fl) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float dot = 0.f;
   for (int j = 0; j < fint; ++j) dot = fmaf(q[m * fint + j], psi_w[j], dot);
   const float s = 1.f / (1.f + expf(-(dot + psi_b)));
-  for (int c = 0; c < fl; ++c) out[m * fl + c] = __float2half_rn(__half2float(x[m * fl + c]) * s);
+  for (int c = 0; c < fl; ++c) out[m * fl + c] = f2act(act2f(x[m * fl + c]) * s);
 }
 
-__global__ void head_kernel(const __half* __restrict__ d2, const float* __restrict__ w, float b, float thr,
+__global__ void head_kernel(const act_t* __restrict__ d2, const float* __restrict__ w, float b, float thr,
                             float* __restrict__ p32, __half* __restrict__ p16, uint8_t* __restrict__ mask, int64_t M, int c) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float dot = 0.f;
-  for (int j = 0; j < c; ++j) dot = fmaf(__half2float(d2[m * c + j]), w[j], dot);
+  for (int j = 0; j < c; ++j) dot = fmaf(act2f(d2[m * c + j]), w[j], dot);
   const float pr = 1.f / (1.f + expf(-(dot + b)));
   if (p32) p32[m] = pr;
   if (p16) p16[m] = __float2half_rn(pr);
@@ -199,7 +199,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Act {
-  __half* p = nullptr;
+  act_t* p = nullptr;
   int C = 0, H = 0, W = 0;
 };
 
@@ -221,8 +221,8 @@ struct sd_engine {
   std::vector<float> hw[SD_NUM_SLOTS], hb[SD_NUM_SLOTS];
   int cout[SD_NUM_SLOTS] = {}, cin[SD_NUM_SLOTS] = {}, ks[SD_NUM_SLOTS] = {};
   // device weights
-  __half* w_umma[SD_NUM_SLOTS] = {};   // [phases*cout][K]
-  __half* w_simt[SD_NUM_SLOTS] = {};   // [taps][cin][cout]
+  act_t* w_umma[SD_NUM_SLOTS] = {};   // [phases*cout][K]
+  act_t* w_simt[SD_NUM_SLOTS] = {};   // [taps][cin][cout]
   float* w_f32[SD_NUM_SLOTS] = {};     // first conv [27][64]; psi / head vectors
   float* bias[SD_NUM_SLOTS] = {};
   float psi_b[4] = {}, head_b = 0.f;
@@ -271,7 +271,7 @@ static int dev_alloc(sd_engine* e, void** p, size_t bytes) {
 
 static int alloc_act(sd_engine* e, Act& a, int lvl, int C) {
   a.C = C; a.H = e->lv[lvl].H; a.W = e->lv[lvl].W;
-  return dev_alloc(e, (void**)&a.p, (size_t)e->cap_tiles * a.H * a.W * C * sizeof(__half));
+  return dev_alloc(e, (void**)&a.p, (size_t)e->cap_tiles * a.H * a.W * C * sizeof(act_t));
 }
 
 static int make_tmap_act(sd_engine* e, CUtensorMap* tm, const Act& a, const Level& box) {  // box.box_* only
@@ -279,18 +279,18 @@ static int make_tmap_act(sd_engine* e, CUtensorMap* tm, const Act& a, const Leve
   cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
   cuuint32_t boxd[4] = {64, (cuuint32_t)box.box_w, (cuuint32_t)box.box_h, (cuuint32_t)box.box_n};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = e->encode(tm, SD_TMAP_DTYPE, 4, a.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d) failed: %d", a.C, a.W, a.H, (int)r); return SD_ECUDA; }
   return SD_OK;
 }
 
-static int make_tmap_w(sd_engine* e, CUtensorMap* tm, const __half* w, int rows, int K, int bn) {
+static int make_tmap_w(sd_engine* e, CUtensorMap* tm, const act_t* w, int rows, int K, int bn) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t boxd[2] = {64, (cuuint32_t)bn};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = e->encode(tm, SD_TMAP_DTYPE, 2, (void*)w, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights rows=%d K=%d) failed: %d", rows, K, (int)r); return SD_ECUDA; }
   return SD_OK;
@@ -312,7 +312,7 @@ static int make_tmap_out(sd_engine* e, CUtensorMap* tm, const Act& o, const Leve
   }
   cuuint32_t boxd[4] = {64, (cuuint32_t)box.box_w, (cuuint32_t)box.box_h, (cuuint32_t)box.box_n};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = e->encode(tm, SD_TMAP_DTYPE, 4, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out C=%d W=%d H=%d up=%d) failed: %d", o.C, o.W, o.H, (int)up, (int)r); return SD_ECUDA; }
   return SD_OK;
@@ -324,7 +324,7 @@ static int make_tmap_pool(sd_engine* e, CUtensorMap* tm, const Act& o, int bw, i
   cuuint64_t strides[3] = {(cuuint64_t)o.C * 2, (cuuint64_t)o.W * o.C * 2, (cuuint64_t)o.H * o.W * o.C * 2};
   cuuint32_t boxd[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = e->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, o.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = e->encode(tm, SD_TMAP_DTYPE, 4, o.p, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pool C=%d W=%d H=%d) failed: %d", o.C, o.W, o.H, (int)r); return SD_ECUDA; }
   return SD_OK;
@@ -396,17 +396,17 @@ static void phase_taps(int par, int t, int& k_lo, int& k_hi, int& d) {
 }
 
 // fp32 OIHW -> fp16 [phase*cout + co][tap*cin + ci]
-static void pack_umma(const float* w, int cout, int cin, int ks, bool up, std::vector<__half>& out) {
+static void pack_umma(const float* w, int cout, int cin, int ks, bool up, std::vector<act_t>& out) {
   if (!up) {
     const int taps = ks * ks, K = taps * cin;
-    out.assign((size_t)cout * K, __float2half(0.f));
+    out.assign((size_t)cout * K, f2act(0.f));
     for (int co = 0; co < cout; ++co)
       for (int ci = 0; ci < cin; ++ci)
         for (int t = 0; t < taps; ++t)
-          out[(size_t)co * K + t * cin + ci] = __float2half_rn(w[((size_t)co * cin + ci) * taps + t]);
+          out[(size_t)co * K + t * cin + ci] = f2act(w[((size_t)co * cin + ci) * taps + t]);
   } else {
     const int K = 4 * cin;
-    out.assign((size_t)4 * cout * K, __float2half(0.f));
+    out.assign((size_t)4 * cout * K, f2act(0.f));
     for (int ph = 0; ph < 4; ++ph)
       for (int ty = 0; ty < 2; ++ty)
         for (int tx = 0; tx < 2; ++tx) {
@@ -418,7 +418,7 @@ static void pack_umma(const float* w, int cout, int cin, int ks, bool up, std::v
               float s = 0.f;
               for (int ky = y0; ky <= y1; ++ky)
                 for (int kx = x0; kx <= x1; ++kx) s += w[((size_t)co * cin + ci) * 9 + ky * 3 + kx];
-              out[((size_t)ph * cout + co) * K + (ty * 2 + tx) * cin + ci] = __float2half_rn(s);
+              out[((size_t)ph * cout + co) * K + (ty * 2 + tx) * cin + ci] = f2act(s);
             }
         }
   }
@@ -549,8 +549,8 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     // order][co] rows of 64 halves, so a stage's B operand is one box of 64 / 128 / 256 rows (three maps).
     {
       const int cbs = cin_total / 64;
-      std::vector<__half> wp((size_t)16 * cbs * 64 * 64);
-      std::vector<__half> src((size_t)4 * co * K);
+      std::vector<act_t> wp((size_t)16 * cbs * 64 * 64);
+      std::vector<act_t> src((size_t)4 * co * K);
       SD_CUDA_CHECK(cudaMemcpy(src.data(), e->w_umma[slot], src.size() * 2, cudaMemcpyDeviceToHost));
       for (int t = 0; t < 9; ++t) {
         const Up4Tap tp = up4_tap(t);
@@ -564,7 +564,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
                 wp[(row0 + c2) * 64 + k] = src[((size_t)ph * co + c2) * K + (size_t)(ty * 2 + tx) * cin_total + cb * 64 + k];
           }
       }
-      __half* d_wp = nullptr;
+      act_t* d_wp = nullptr;
       if ((r = upload(e, (void**)&d_wp, wp.data(), wp.size() * 2))) return r;
       const int rows = 16 * cbs * 64;
       if ((r = make_tmap_w(e, &p.tmB, d_wp, rows, 64, 64))) return r;
@@ -769,33 +769,33 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
           for (int k = 0; k < 9; ++k) t[(k * 3 + ci) * 64 + co] = e->hw[s][((size_t)co * 3 + ci) * 9 + k];
       if ((r = upload(e, (void**)&e->w_f32[s], t.data(), t.size() * 4))) return r;
       // tensor-core form: [64 x K=80] fp16 in the canonical no-swizzle K-major layout, k = tap * 8 + ci
-      std::vector<__half> c1((size_t)kC1BBytes / 2, __float2half(0.f));
+      std::vector<act_t> c1((size_t)kC1BBytes / 2, f2act(0.f));
       for (int co = 0; co < 64; ++co)
         for (int ci = 0; ci < 3; ++ci)
           for (int k = 0; k < 9; ++k)
-            c1[(size_t)(co >> 3) * (kC1GroupBytes / 2) + k * 64 + (co & 7) * 8 + ci] = __float2half_rn(e->hw[s][((size_t)co * 3 + ci) * 9 + k]);
+            c1[(size_t)(co >> 3) * (kC1GroupBytes / 2) + k * 64 + (co & 7) * 8 + ci] = f2act(e->hw[s][((size_t)co * 3 + ci) * 9 + k]);
       if ((r = upload(e, (void**)&e->w_umma[s], c1.data(), c1.size() * 2))) return r;
     }
     const int co = e->cout[s], ci = e->cin[s], taps = e->ks[s] * e->ks[s];
     if (impl == 1) {
       const int cip = (s == SD_CONV1_0) ? 8 : ci;
-      std::vector<__half> t((size_t)taps * cip * co, __float2half(0.f));
+      std::vector<act_t> t((size_t)taps * cip * co, f2act(0.f));
       for (int o = 0; o < co; ++o)
         for (int i = 0; i < ci; ++i)
-          for (int k = 0; k < taps; ++k) t[((size_t)k * cip + i) * co + o] = __float2half_rn(e->hw[s][((size_t)o * ci + i) * taps + k]);
+          for (int k = 0; k < taps; ++k) t[((size_t)k * cip + i) * co + o] = f2act(e->hw[s][((size_t)o * ci + i) * taps + k]);
       if ((r = upload(e, (void**)&e->w_simt[s], t.data(), t.size() * 2))) return r;
     } else if (s != SD_CONV1_0) {
       const bool is_gx = (s == SD_ATT5_X || s == SD_ATT4_X || s == SD_ATT3_X || s == SD_ATT2_X);
       const bool is_gg = (s == SD_ATT5_G || s == SD_ATT4_G || s == SD_ATT3_G || s == SD_ATT2_G);
       if (is_gx) continue;   // packed together with the G slot below
-      std::vector<__half> t;
+      std::vector<act_t> t;
       if (is_gg) {
         // gate GEMM: K = [g channels | x channels], weights [W_g | W_x], bias b_g + b_x
         const int fg = ci, fl = e->cin[s + 1];
-        t.assign((size_t)co * (fg + fl), __float2half(0.f));
+        t.assign((size_t)co * (fg + fl), f2act(0.f));
         for (int o = 0; o < co; ++o) {
-          for (int i = 0; i < fg; ++i) t[(size_t)o * (fg + fl) + i] = __float2half_rn(e->hw[s][(size_t)o * fg + i]);
-          for (int i = 0; i < fl; ++i) t[(size_t)o * (fg + fl) + fg + i] = __float2half_rn(e->hw[s + 1][(size_t)o * fl + i]);
+          for (int i = 0; i < fg; ++i) t[(size_t)o * (fg + fl) + i] = f2act(e->hw[s][(size_t)o * fg + i]);
+          for (int i = 0; i < fl; ++i) t[(size_t)o * (fg + fl) + fg + i] = f2act(e->hw[s + 1][(size_t)o * fl + i]);
         }
       } else {
         pack_umma(e->hw[s].data(), co, ci, e->ks[s], is_up, t);
@@ -862,7 +862,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   } else {
     first.run = [e](int B, cudaStream_t s) -> int {
       SimtConv a;
-      a.in0 = reinterpret_cast<const __half*>(e->in_tiles); a.c0 = 8; a.in1 = nullptr; a.c1 = 0;
+      a.in0 = reinterpret_cast<const act_t*>(e->in_tiles); a.c0 = 8; a.in1 = nullptr; a.c1 = 0;
       a.w = e->w_simt[SD_CONV1_0]; a.bias = e->bias[SD_CONV1_0]; a.out = e->c1a.p; a.out32 = nullptr;
       a.B = B; a.H = e->H; a.W = e->W; a.cout = 64; a.ks = 3; a.up = 0; a.relu = 1;
       dim3 grid((unsigned)((int64_t)B * e->H * e->W / 64), 1);
@@ -917,10 +917,10 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
     for (int a = 0; a < 4; ++a) {
       const int sg = SD_ATT5_G + 6 * a, sx = sg + 1;
       const int fint = e->cout[sg], fg = e->cin[sg], fl = e->cin[sx];
-      std::vector<__half> t((size_t)(fg + fl) * fint);
+      std::vector<act_t> t((size_t)(fg + fl) * fint);
       for (int o = 0; o < fint; ++o) {
-        for (int i = 0; i < fg; ++i) t[(size_t)i * fint + o] = __float2half_rn(e->hw[sg][(size_t)o * fg + i]);
-        for (int i = 0; i < fl; ++i) t[(size_t)(fg + i) * fint + o] = __float2half_rn(e->hw[sx][(size_t)o * fl + i]);
+        for (int i = 0; i < fg; ++i) t[(size_t)i * fint + o] = f2act(e->hw[sg][(size_t)o * fg + i]);
+        for (int i = 0; i < fl; ++i) t[(size_t)(fg + i) * fint + o] = f2act(e->hw[sx][(size_t)o * fl + i]);
       }
       e->w_simt[sg] = nullptr;
       if ((r = upload(e, (void**)&e->w_simt[sg], t.data(), t.size() * 2))) return r;
@@ -1043,7 +1043,7 @@ extern "C" int sd_unet_read_tap(sd_engine* e, int tap, int n_tiles, void* d_out,
   if (h) *h = a.H;
   if (w) *w = a.W;
   if (!d_out) return SD_OK;
-  const size_t need = (size_t)n_tiles * a.H * a.W * a.C * sizeof(__half);
+  const size_t need = (size_t)n_tiles * a.H * a.W * a.C * sizeof(act_t);
   SD_REQUIRE(out_bytes >= need, "sd_unet_read_tap: buffer too small (%zu < %zu)", out_bytes, need);
   SD_CUDA_CHECK(cudaMemcpyAsync(d_out, a.p, need, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SD_OK;

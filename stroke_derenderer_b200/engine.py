@@ -95,7 +95,7 @@ class UNetEngine:
     def forward(self, tiles: torch.Tensor, bin_thr: float = 0.5, want_prob32=False, want_prob16=False, want_mask=True):
         """tiles: (n, 128, 384, 8) fp16 NHWC on this GPU, n <= max_tiles.
         Returns dict with any of prob32 (n,128,384) f32, prob16 f16, mask u8 {0,255}."""
-        assert tiles.is_cuda and tiles.dtype == torch.float16 and tiles.is_contiguous()
+        assert tiles.is_cuda and tiles.dtype == _lib.torch_dtype() and tiles.is_contiguous()
         assert tuple(tiles.shape[1:]) == (TILE_H, TILE_W, CIN_PAD), tiles.shape
         n = tiles.shape[0]
         out = {}
@@ -133,7 +133,7 @@ class UNetEngine:
         idx = _lib.TAPS.index(name)
         c, h, w = C.c_int(), C.c_int(), C.c_int()
         _lib.check(L.sd_unet_read_tap(self._h, idx, n, None, 0, C.byref(c), C.byref(h), C.byref(w), None), "sd_unet_read_tap")
-        out = torch.empty((n, h.value, w.value, c.value), dtype=torch.float16, device=self.device)
+        out = torch.empty((n, h.value, w.value, c.value), dtype=_lib.torch_dtype(), device=self.device)
         _lib.check(L.sd_unet_read_tap(self._h, idx, n, out.data_ptr(), out.numel() * 2, C.byref(c), C.byref(h), C.byref(w),
                                       stream_ptr(self.device)), "sd_unet_read_tap")
         return out
@@ -143,8 +143,8 @@ class UNetEngine:
     def pack_input(x: torch.Tensor) -> torch.Tensor:
         """(B,3,H,W) f32 in [0,1] on GPU -> (B,H,W,8) fp16 NHWC, channels 3..7 zero."""
         b, c, h, w = x.shape
-        t = torch.zeros((b, h, w, CIN_PAD), dtype=torch.float16, device=x.device)
-        t[..., :c] = x.permute(0, 2, 3, 1).to(torch.float16)
+        t = torch.zeros((b, h, w, CIN_PAD), dtype=_lib.torch_dtype(), device=x.device)
+        t[..., :c] = x.permute(0, 2, 3, 1).to(_lib.torch_dtype())
         return t
 
     def run(self, output_names, feeds):

@@ -110,7 +110,7 @@ class LineSegmentationJob:
                 self.chunks.append(ch)
             # one tile stack for the whole job: UNet batches run across chunk boundaries, so only the
             # last batch of the job is partial
-            self.tiles = torch.empty((max(t0, 1), TILE_H, TILE_W, 8), dtype=torch.float16, device=self.device)
+            self.tiles = torch.empty((max(t0, 1), TILE_H, TILE_W, 8), dtype=S._lib.torch_dtype(), device=self.device)
             # job-wide sd_tile_dst table: tile k of the stack pastes into its chunk's planes (glue fused into the head)
             self.dst = torch.cat([ch.batch.tile_dst(ch.planes) for ch in self.chunks]) if self.chunks else None
             for ch in self.chunks:

@@ -149,7 +149,7 @@ def _s(batch): return stream_ptr(batch.device)
 
 def tile_extract_f16(batch: LineBatch, d_rgb: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     if out is None:
-        out = torch.empty((batch.n_tiles, TILE_H, TILE_W, CIN_PAD), dtype=torch.float16, device=batch.device)
+        out = torch.empty((batch.n_tiles, TILE_H, TILE_W, CIN_PAD), dtype=_lib.torch_dtype(), device=batch.device)
     _lib.check(_lib.lib().sd_tile_extract_f16(d_rgb.data_ptr(), batch.d_lines.data_ptr(), batch.n_lines, batch.n_tiles,
                                               out.data_ptr(), _s(batch)), "sd_tile_extract_f16")
     return out
