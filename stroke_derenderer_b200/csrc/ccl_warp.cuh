@@ -13,12 +13,13 @@
 //      run-start masks (512 B) and one 16-bit root per run (bit 15 = the root touches a neighbouring strip):
 //      ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that touch no other strip are final
 //      (root bitmap); the others register in the sparse global parent array.
-//   2. ccl_line_kernel (CTA = line): unions across the strip seams of the line, marks the surviving seam roots,
+//   2. ccl_seam_merge_kernel / ccl_seam_mark_kernel (thread = seam block row): unions across the strip seams on the
+//      sparse global parents; seam roots that survive are marked in the bitmap.  ccl_line_kernel (CTA = line):
 //      exclusive scan of the root bitmap (label = 1 + #roots before the root), island count; the last CTA to
 //      finish also scans the counts of all lines into the stats row offsets.
-//   3. ccl_warp_write_kernel (warp = strip): run roots -> final labels (shared-memory table), int32 labels out as
-//      512-byte row segments, and, fused, the cv2 stats: every run's extent / area is reduced over the lanes that
-//      hold runs of the same label (match_any + redux) before one set of global atomics per (label, lane group).
+//   3. ccl_strip_write2_kernel (CTA = strip, 256 threads): run roots -> final labels (shared-memory table), int32
+//      labels out as 512-byte row segments, and, fused, the cv2 stats: every run's extent / area is reduced over the
+//      lanes that hold runs of the same label (match_any + redux) before one set of global atomics per group.
 // HBM traffic: 1 B/px mask read + 4 B/px labels written + ~0.4 B/px of records; no second pass over the labels.
 #pragma once
 #include "common.cuh"
@@ -57,27 +58,31 @@ __device__ __forceinline__ uint64_t cw_shfl_up64(uint64_t v, int lane) {
 // block column of the run start that owns block k: highest run-start bit at or below k
 __device__ __forceinline__ int cw_run_start(uint64_t rs, int k) { return 63 - __clzll((long long)(rs & ((2ull << k) - 1ull))); }
 
-__device__ __forceinline__ int cw_find(volatile int* p, int a) {
+// Union-find over the runs of one strip, in shared memory.  Parents are 16-bit (node ids are < 4096): 8 KB per strip
+// instead of 16 KB, which is what bounds the number of resident warps.
+typedef unsigned short cw_node_t;
+__device__ __forceinline__ int cw_find(volatile cw_node_t* p, int a) {
   int q;
   while ((q = p[a]) != a) a = q;
   return a;
 }
-// min-root union; completes only when its atomicMin hit a true root.  No compression while unions are in flight.
-__device__ __forceinline__ void cw_union(int* p, int a, int b) {
+// min-root union: the larger root is hung under the smaller one with a compare-and-swap that only succeeds while it
+// still IS a root, so a link can never be overwritten.  No path compression while unions are in flight.
+__device__ __forceinline__ void cw_union(cw_node_t* p, int a, int b) {
   while (true) {
     a = cw_find(p, a);
     b = cw_find(p, b);
     if (a == b) return;
     if (a < b) { const int t = a; a = b; b = t; }
-    const int old = atomicMin(&p[a], b);
+    const int old = atomicCAS(&p[a], (cw_node_t)a, (cw_node_t)b);
     if (old == a) return;
-    a = old;
+    a = old;                                      // somebody re-parented a meanwhile; retry from its new parent
   }
 }
 
 // contacts of a block row (top pixel row Te / To, links hl, run starts rs) with the pixel row above it (Ue / Uo; links
 // hlU and run starts rsU of that block row): one union per distinct (run, upper run) pair
-__device__ __forceinline__ void cw_contacts(int* parent, int base, int baseU, uint64_t Te, uint64_t To, uint64_t Ue, uint64_t Uo,
+__device__ __forceinline__ void cw_contacts(cw_node_t* parent, int base, int baseU, uint64_t Te, uint64_t To, uint64_t Ue, uint64_t Uo,
                                             uint64_t hl, uint64_t hlU, uint64_t rs, uint64_t rsU) {
   const uint64_t vu0 = (Te | To) & (Ue | Uo);                 // block k - upper block k
   uint64_t vl = Te & (Uo << 1);                               // block k - upper block k-1 (diagonal)
@@ -95,7 +100,7 @@ __device__ __forceinline__ void cw_contacts(int* parent, int base, int baseU, ui
 }
 
 struct __align__(16) CwLabelSmem {
-  int parent[kStripBlocks];        // node = block row * 64 + first block of the run
+  cw_node_t parent[kStripBlocks];  // node = block row * 64 + first block of the run
   uint8_t e[128][8], o[128][8];    // Xe / Xo of every pixel row, one byte per 16-pixel load
   uint32_t touch[kStripBlocks / 32];
 };
@@ -159,8 +164,8 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     w.rs[(int64_t)strip * 64 + 2 * lane] = make_uint2((uint32_t)rsa, (uint32_t)(rsa >> 32));
     w.rs[(int64_t)strip * 64 + 2 * lane + 1] = make_uint2((uint32_t)rsb, (uint32_t)(rsb >> 32));
     const int na = 2 * lane * 64, nb = na + 64;                           // node bases of the two block rows
-    for (uint64_t t = rsa; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[na + k] = na + k; }
-    for (uint64_t t = rsb; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[nb + k] = nb + k; }
+    for (uint64_t t = rsa; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[na + k] = (cw_node_t)(na + k); }
+    for (uint64_t t = rsb; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[nb + k] = (cw_node_t)(nb + k); }
     // the block row above row a belongs to lane L-1 (its row b)
     const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
     const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
@@ -168,17 +173,10 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     cw_contacts(sm.parent, na, na - 64, Tea, Toa, Ue, Uo, hla, hlU, rsa, rsU);
     cw_contacts(sm.parent, nb, na, Teb, Tob, Bea, Boa, hlb, hla, rsb, rsa);
     __syncwarp();
-    // ---- flatten: afterwards parent[run start] is the run's root ----
-    {
-      volatile int* vp = sm.parent;
-      for (uint64_t t = rsa; t; t &= t - 1) { const int n = na + __ffsll((long long)t) - 1; vp[n] = cw_find(vp, n); }
-      for (uint64_t t = rsb; t; t &= t - 1) { const int n = nb + __ffsll((long long)t) - 1; vp[n] = cw_find(vp, n); }
-    }
-    __syncwarp();
     // ---- seam blocks: their roots touch a neighbouring strip ----
     const int gbase = (int)ln.blk_off + s * 64;                          // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
     {
-      volatile int* vp = sm.parent;
+      volatile cw_node_t* vp = sm.parent;
       int* br = w.bnd_root + (int64_t)strip * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -186,12 +184,12 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
         const int nbase = h ? nb : na, row = 2 * lane + h;
         int left = -1, right = -1;
         if (s > 0 && (occ & 1ull)) {
-          const int r = vp[nbase];                                       // block 0 has no left neighbour: it starts its run
+          const int r = cw_find(vp, nbase);                              // block 0 has no left neighbour: it starts its run
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
           left = gbase + (r >> 6) * ln.bw + (r & 63);
         }
         if (s < ns - 1 && (occ >> 63)) {
-          const int r = vp[nbase + cw_run_start(rs, 63)];
+          const int r = cw_find(vp, nbase + cw_run_start(rs, 63));
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
           right = gbase + (r >> 6) * ln.bw + (r & 63);
         }
@@ -216,14 +214,15 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
       uint16_t* out = w.roots + (int64_t)strip * kStripBlocks + (inc - cnt);
-      volatile int* vp = sm.parent;
+      volatile cw_node_t* vp = sm.parent;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int nbase = h ? nb : na, row = 2 * lane + h;
         uint64_t rootbits = 0ull;
         for (uint64_t t = h ? rsb : rsa; t; t &= t - 1) {
           const int k = __ffsll((long long)t) - 1;
-          const int r = vp[nbase + k];
+          const int r = cw_find(vp, nbase + k);                          // every union is done: roots are final
+          vp[nbase + k] = (cw_node_t)r;                                  // shortens the walks of the runs that follow
           const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
           *out++ = (uint16_t)(r | (tch << 15));
           if (r == nbase + k) {
@@ -257,37 +256,40 @@ __device__ __forceinline__ void cw_uf_union(int* parent, int a, int b) {
 }
 __device__ __forceinline__ uint32_t cw_col_bit(const uint32_t* __restrict__ p, int row) { return (p[row & 3] >> (row >> 2)) & 1u; }
 
-// CTA = line: seam unions, seam roots -> bitmap, exclusive scan of the root counts, island count; the last CTA to
+// thread = one block row of one strip seam: 8-connectivity between pixel column 127 of strip sg-1 and pixel column 0
+// of strip sg (bnd_root of the right side of a line's last strip is -1, so lines never merge)
+__global__ void __launch_bounds__(256) ccl_seam_merge_kernel(CclWarpWork w, int n_strips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_strips * 64) return;
+  const int64_t sg = i >> 6;
+  const int br = i & 63;
+  if (sg == 0) return;
+  const int a = w.bnd_root[(sg - 1) * 128 + 64 + br];
+  if (a < 0) return;
+  const int* Rr = w.bnd_root + sg * 128;
+  const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
+  const uint32_t* Rb = w.bnd_bits + sg * 8;
+  const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
+  const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
+  if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, Rr[br]);
+  if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, Rr[br - 1]);
+  if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, Rr[br + 1]);
+}
+
+// seam roots that are still roots after the merge are component roots
+__global__ void __launch_bounds__(256) ccl_seam_mark_kernel(CclWarpWork w, int n_strips) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_strips * 128) return;
+  const int k = w.bnd_root[i];
+  if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
+}
+
+// CTA = line: exclusive scan of the root bitmap (label = 1 + #roots before the root), island count; the last CTA to
 // finish turns the counts of all lines into stats row offsets (stat_off[l] = sum over lines < l of (num - 1)).
 __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restrict__ L, int n_lines, CclWarpWork w,
                                                         int* __restrict__ num_out, int64_t* __restrict__ stat_off) {
   const int l = blockIdx.x, tid = threadIdx.x;
   const sd_line ln = L[l];
-  const int ns = ln.bw >> 6;
-  const int64_t first = ln.blk_off >> 12;                               // first strip of the line
-  // 8-connectivity across the seams: pixel column 127 of strip sg-1 against pixel column 0 of strip sg
-  for (int i = tid; i < (ns - 1) * 64; i += blockDim.x) {
-    const int64_t sg = first + 1 + (i >> 6);
-    const int br = i & 63;
-    const int a = w.bnd_root[(sg - 1) * 128 + 64 + br];
-    if (a < 0) continue;
-    const int* Rr = w.bnd_root + sg * 128;
-    const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
-    const uint32_t* Rb = w.bnd_bits + sg * 8;
-    const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
-    const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
-    if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, Rr[br]);
-    if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, Rr[br - 1]);
-    if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, Rr[br + 1]);
-  }
-  __threadfence();
-  __syncthreads();
-  for (int i = tid; i < ns * 128; i += blockDim.x) {
-    const int k = w.bnd_root[first * 128 + i];
-    if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
-  }
-  __threadfence();
-  __syncthreads();
   const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
   int* prefix = w.prefix + (ln.blk_off >> 5);
   __shared__ int s_warp[32];
@@ -359,6 +361,8 @@ struct __align__(16) CwWriteSmem {
   int lab[kStripBlocks];           // node (block row * 64 + first block of the run) -> final label
   uint4 pix[128];
   uint2 rs[64];
+  int rowoff[64];                  // first run ordinal of every block row
+  int line;
 };
 
 // statistics of one run, merged over the lanes whose current run carries the same label, then one set of atomics
@@ -375,109 +379,109 @@ __device__ __forceinline__ void cw_stats_flush(int32_t* __restrict__ st_rows, in
   }
 }
 
-__global__ void __launch_bounds__(32 * kCw) ccl_warp_write_kernel(const sd_line* __restrict__ L, int n_lines, int n_strips, CclWarpWork w,
-                                                                  int* __restrict__ labels, const int64_t* __restrict__ stat_off,
-                                                                  int32_t* __restrict__ stats, int64_t cap_rows) {
-  extern __shared__ __align__(16) uint8_t cw_smem[];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  CwWriteSmem& sm = reinterpret_cast<CwWriteSmem*>(cw_smem)[wp];
-  for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
-    const int64_t blk0 = (int64_t)strip * kStripBlocks;
+// CTA = strip, 256 threads.  Thread (block row br = tid >> 2, quarter q = tid & 3) owns the runs that START in its 16
+// blocks: run roots -> final labels in shared memory, the fused cv2 stats of those runs; then warp wp expands block rows
+// 8 wp .. 8 wp + 7, one 512-byte row segment per store instruction.
+__global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __restrict__ L, int n_lines, CclWarpWork w,
+                                                               int* __restrict__ labels, const int64_t* __restrict__ stat_off,
+                                                               int32_t* __restrict__ stats, int64_t cap_rows) {
+  __shared__ CwWriteSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int strip = blockIdx.x;
+  const int64_t blk0 = (int64_t)strip * kStripBlocks;
+  if (wp == 0) {
     const int li = cw_find_line(L, n_lines, blk0, lane);
-    const sd_line ln = L[li];
-    const int s = (int)((blk0 - ln.blk_off) >> 12);
-    const int gbase = (int)ln.blk_off + s * 64;
-    // ---- records of the strip: own rows in registers, everything in shared memory for the expansion ----
-    uint4 px[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { px[i] = __ldcs(w.pix + (int64_t)strip * 128 + 4 * lane + i); sm.pix[4 * lane + i] = px[i]; }
-    const uint2 ra2 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane), rb2 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane + 1);
-    sm.rs[2 * lane] = ra2; sm.rs[2 * lane + 1] = rb2;
-    const uint64_t rsa = ((uint64_t)ra2.y << 32) | ra2.x, rsb = ((uint64_t)rb2.y << 32) | rb2.x;
-    const int na = 2 * lane * 64, nb = na + 64;
-    const int cnt = __popcll(rsa) + __popcll(rsb);
-    int inc = cnt;
+    if (lane == 0) sm.line = li;
+    // first run ordinal of every block row: exclusive scan of the run counts (two rows per lane)
+    const uint2 r0 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane), r1 = __ldcs(w.rs + (int64_t)strip * 64 + 2 * lane + 1);
+    sm.rs[2 * lane] = r0; sm.rs[2 * lane + 1] = r1;
+    const int c0 = __popc(r0.x) + __popc(r0.y), c1 = __popc(r1.x) + __popc(r1.y);
+    int inc = c0 + c1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    const uint16_t* rt = w.roots + (int64_t)strip * kStripBlocks + (inc - cnt);
-    // pass 1: runs that are roots compute their final label
-    {
-      const uint16_t* p = rt;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nbase = h ? nb : na, row = 2 * lane + h;
-        for (uint64_t t = h ? rsb : rsa; t; t &= t - 1) {
-          const int k = __ffsll((long long)t) - 1;
-          const uint32_t rr = __ldg(p++);
-          if ((int)(rr & 0x7fffu) == nbase + k) {
-            int g = gbase + row * ln.bw + k;
-            if (rr >> 15) g = cw_uf_find(w.parent, g);
-            sm.lab[nbase + k] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
-          }
-        }
+    sm.rowoff[2 * lane] = inc - c0 - c1; sm.rowoff[2 * lane + 1] = inc - c1;
+  } else if (tid >= 128) {
+    sm.pix[tid - 128] = __ldcs(w.pix + (int64_t)strip * 128 + (tid - 128));
+  }
+  __syncthreads();
+  const int li = sm.line;
+  const sd_line ln = L[li];
+  const int s = (int)((blk0 - ln.blk_off) >> 12);
+  const int gbase = (int)ln.blk_off + s * 64;
+  const int br = tid >> 2, q = tid & 3;
+  const uint2 r2 = sm.rs[br];
+  const uint64_t rs = ((uint64_t)r2.y << 32) | r2.x;
+  const uint64_t mine = rs & (0xFFFFull << (16 * q));                    // run starts inside this thread's 16 blocks
+  const uint16_t* rt = w.roots + (int64_t)strip * kStripBlocks + sm.rowoff[br] + __popcll(rs & ((1ull << (16 * q)) - 1ull));
+  const int nbase = br * 64;
+  // pass 1: runs that are roots compute their final label
+  {
+    const uint16_t* p = rt;
+    for (uint64_t t = mine; t; t &= t - 1) {
+      const int k = __ffsll((long long)t) - 1;
+      const uint32_t rr = __ldg(p++);
+      if ((int)(rr & 0x7fffu) == nbase + k) {
+        int g = gbase + br * ln.bw + k;
+        if (rr >> 15) g = cw_uf_find(w.parent, g);
+        sm.lab[nbase + k] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
       }
     }
-    __syncwarp();
-    // pass 2: every other run copies the label of its root; fused island statistics
-    {
-      const uint16_t* p = rt;
-      const bool do_stats = stats != nullptr;
-      int32_t* st_rows = do_stats ? stats : nullptr;
-      const int64_t row0 = do_stats ? __ldg(stat_off + li) : 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nbase = h ? nb : na, row = 2 * lane + h;
-        const uint64_t rs = h ? rsb : rsa;
-        const uint64_t Te = ((uint64_t)px[2 * h].y << 32) | px[2 * h].x, To = ((uint64_t)px[2 * h].w << 32) | px[2 * h].z;
-        const uint64_t Be = ((uint64_t)px[2 * h + 1].y << 32) | px[2 * h + 1].x, Bo = ((uint64_t)px[2 * h + 1].w << 32) | px[2 * h + 1].z;
-        const uint64_t occ = Te | To | Be | Bo;
-        for (uint64_t t = rs; t; t &= t - 1) {
-          const int k = __ffsll((long long)t) - 1;
-          const int root = (int)(__ldg(p++) & 0x7fffu);
-          const int lab = sm.lab[root];
-          if (root != nbase + k) sm.lab[nbase + k] = lab;
-          if (do_stats) {
-            // blocks of the run: occupied blocks from k up to the next run start
-            const uint64_t nxt = t & (t - 1);
-            const uint64_t upto = nxt ? ((nxt & (~nxt + 1ull)) - 1ull) : ~0ull;
-            const uint64_t M = occ & upto & ~((1ull << k) - 1ull);
-            const uint64_t Me = (Te | Be) & M, Mo = (To | Bo) & M;
-            int minx = 1 << 20, maxx = -1;
-            if (Me) { minx = 2 * (__ffsll((long long)Me) - 1); maxx = 2 * (63 - __clzll((long long)Me)); }
-            if (Mo) { minx = min(minx, 2 * (__ffsll((long long)Mo) - 1) + 1); maxx = max(maxx, 2 * (63 - __clzll((long long)Mo)) + 1); }
-            const bool top = ((Te | To) & M) != 0ull, bot = ((Be | Bo) & M) != 0ull;
-            const int miny = 2 * row + (top ? 0 : 1), maxy = 2 * row + (bot ? 1 : 0);
-            const int area = __popcll(Te & M) + __popcll(To & M) + __popcll(Be & M) + __popcll(Bo & M);
-            // the lanes that are at a run right now (trip counts differ) pool the runs that carry the same label
-            const uint32_t act = __activemask();
-            const uint32_t grp = __match_any_sync(act, lab);
-            cw_stats_flush(st_rows, cap_rows, row0 + lab - 1, grp, lane, s * 128 + minx, miny, s * 128 + maxx, maxy, area);
-          }
-        }
+  }
+  __syncthreads();
+  // pass 2: every other run copies the label of its root; fused island statistics of the runs of this thread
+  {
+    const uint16_t* p = rt;
+    const bool do_stats = stats != nullptr;
+    const int64_t row0 = do_stats ? __ldg(stat_off + li) : 0;
+    const uint4 t4 = sm.pix[2 * br], b4 = sm.pix[2 * br + 1];
+    const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
+    const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
+    const uint64_t occ = Te | To | Be | Bo;
+    for (uint64_t t = mine; t; t &= t - 1) {
+      const int k = __ffsll((long long)t) - 1;
+      const int root = (int)(__ldg(p++) & 0x7fffu);
+      const int lab = sm.lab[root];
+      if (root != nbase + k) sm.lab[nbase + k] = lab;
+      if (do_stats) {
+        // blocks of the run: occupied blocks from k up to the next run start of the ROW (it may lie in another quarter)
+        const uint64_t above = rs & ~((2ull << k) - 1ull);
+        const uint64_t upto = above ? ((above & (~above + 1ull)) - 1ull) : ~0ull;
+        const uint64_t M = occ & upto & ~((1ull << k) - 1ull);
+        const uint64_t Me = (Te | Be) & M, Mo = (To | Bo) & M;
+        int minx = 1 << 20, maxx = -1;
+        if (Me) { minx = 2 * (__ffsll((long long)Me) - 1); maxx = 2 * (63 - __clzll((long long)Me)); }
+        if (Mo) { minx = min(minx, 2 * (__ffsll((long long)Mo) - 1) + 1); maxx = max(maxx, 2 * (63 - __clzll((long long)Mo)) + 1); }
+        const bool top = ((Te | To) & M) != 0ull, bot = ((Be | Bo) & M) != 0ull;
+        const int miny = 2 * br + (top ? 0 : 1), maxy = 2 * br + (bot ? 1 : 0);
+        const int area = __popcll(Te & M) + __popcll(To & M) + __popcll(Be & M) + __popcll(Bo & M);
+        // the lanes that are at a run right now (trip counts differ) pool the runs that carry the same label
+        const uint32_t act = __activemask();
+        const uint32_t grp = __match_any_sync(act, lab);
+        cw_stats_flush(stats, cap_rows, row0 + lab - 1, grp, lane, s * 128 + minx, miny, s * 128 + maxx, maxy, area);
       }
     }
-    __syncwarp();
-    // ---- expansion: one block row (two pixel rows) per iteration, a warp store = one 512-byte row segment ----
-    int* out = labels + ln.px_off + s * 128 + lane * 4;
+  }
+  __syncthreads();
+  // ---- expansion: warp wp writes block rows 8 wp .. 8 wp + 7, a store instruction = one 512-byte row segment ----
+  int* out = labels + ln.px_off + s * 128 + lane * 4;
 #pragma unroll 2
-    for (int br = 0; br < 64; ++br) {
-      const uint2 r2 = sm.rs[br];
-      const uint64_t rs = ((uint64_t)r2.y << 32) | r2.x;
-      const uint4 t4 = sm.pix[2 * br], b4 = sm.pix[2 * br + 1];
-      const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
-      const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
-      const uint32_t te = (uint32_t)(Te >> (2 * lane)) & 3u, to = (uint32_t)(To >> (2 * lane)) & 3u;
-      const uint32_t be = (uint32_t)(Be >> (2 * lane)) & 3u, bo = (uint32_t)(Bo >> (2 * lane)) & 3u;
-      int l0 = 0, l1 = 0;
-      if ((te | to | be | bo) & 1u) l0 = sm.lab[br * 64 + cw_run_start(rs, 2 * lane)];
-      if ((te | to | be | bo) & 2u) l1 = sm.lab[br * 64 + cw_run_start(rs, 2 * lane + 1)];
-      int4 a, b;
-      a.x = (te & 1u) ? l0 : 0; a.y = (to & 1u) ? l0 : 0; a.z = (te & 2u) ? l1 : 0; a.w = (to & 2u) ? l1 : 0;
-      b.x = (be & 1u) ? l0 : 0; b.y = (bo & 1u) ? l0 : 0; b.z = (be & 2u) ? l1 : 0; b.w = (bo & 2u) ? l1 : 0;
-      __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * br) * ln.pitch), a);
-      __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * br + 1) * ln.pitch), b);
-    }
-    __syncwarp();
+  for (int i = 0; i < 8; ++i) {
+    const int b = wp * 8 + i;
+    const uint2 q2 = sm.rs[b];
+    const uint64_t rsb = ((uint64_t)q2.y << 32) | q2.x;
+    const uint4 t4 = sm.pix[2 * b], b4 = sm.pix[2 * b + 1];
+    const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
+    const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
+    const uint32_t te = (uint32_t)(Te >> (2 * lane)) & 3u, to = (uint32_t)(To >> (2 * lane)) & 3u;
+    const uint32_t be = (uint32_t)(Be >> (2 * lane)) & 3u, bo = (uint32_t)(Bo >> (2 * lane)) & 3u;
+    int l0 = 0, l1 = 0;
+    if ((te | to | be | bo) & 1u) l0 = sm.lab[b * 64 + cw_run_start(rsb, 2 * lane)];
+    if ((te | to | be | bo) & 2u) l1 = sm.lab[b * 64 + cw_run_start(rsb, 2 * lane + 1)];
+    int4 a, c;
+    a.x = (te & 1u) ? l0 : 0; a.y = (to & 1u) ? l0 : 0; a.z = (te & 2u) ? l1 : 0; a.w = (to & 2u) ? l1 : 0;
+    c.x = (be & 1u) ? l0 : 0; c.y = (bo & 1u) ? l0 : 0; c.z = (be & 2u) ? l1 : 0; c.w = (bo & 2u) ? l1 : 0;
+    __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * b) * ln.pitch), a);
+    __stcs(reinterpret_cast<int4*>(out + (int64_t)(2 * b + 1) * ln.pitch), c);
   }
 }
 

@@ -1291,29 +1291,29 @@ static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lin
   CclWarpWork w;
   ccl_warp_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
   const int strips = (int)(blk_total / kStripBlocks);
-  const int smem_l = kCw * (int)sizeof(CwLabelSmem), smem_w = kCw * (int)sizeof(CwWriteSmem);
+  const int smem_l = kCw * (int)sizeof(CwLabelSmem);
   static PerDeviceOnce attr_once;
-  static int per_sm_l = 0, per_sm_w = 0, sms = 148;
+  static int per_sm_l = 0, sms = 148;
   if (attr_once.first()) {
     SD_CUDA_CHECK(cudaFuncSetAttribute(ccl_warp_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));
-    SD_CUDA_CHECK(cudaFuncSetAttribute(ccl_warp_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, ccl_warp_label_kernel, 32 * kCw, smem_l);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, ccl_warp_write_kernel, 32 * kCw, smem_w);
     if (per_sm_l < 1) per_sm_l = 1;
-    if (per_sm_w < 1) per_sm_w = 1;
   }
   const int ctas = (strips + kCw - 1) / kCw;
   if (d_stats && cap_rows > 0) SD_CUDA_CHECK(cudaMemsetAsync(d_stats, 0x7f, (size_t)cap_rows * 20, s));
   ccl_warp_label_kernel<<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
   SD_LAUNCH_CHECK("ccl_warp_label_kernel");
+  ccl_seam_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
+  SD_LAUNCH_CHECK("ccl_seam_merge_kernel");
+  ccl_seam_mark_kernel<<<ceil_div((int64_t)strips * 128, 256), 256, 0, s>>>(w, strips);
+  SD_LAUNCH_CHECK("ccl_seam_mark_kernel");
   ccl_line_kernel<<<n_lines, 1024, 0, s>>>(d_lines, n_lines, w, d_num, d_stat_off);
   SD_LAUNCH_CHECK("ccl_line_kernel");
-  ccl_warp_write_kernel<<<std::min(ctas, sms * per_sm_w), 32 * kCw, smem_w, s>>>(d_lines, n_lines, strips, w, d_labels, d_stat_off,
-                                                                               d_stats, cap_rows);
-  SD_LAUNCH_CHECK("ccl_warp_write_kernel");
+  ccl_strip_write2_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels, d_stat_off, d_stats, cap_rows);
+  SD_LAUNCH_CHECK("ccl_strip_write2_kernel");
   if (d_stats && cap_rows > 0) {
     ccl_stats_finish_kernel<<<sms * 2, 256, 0, s>>>(d_stats, d_stat_off, n_lines, cap_rows);
     SD_LAUNCH_CHECK("ccl_stats_finish_kernel");

@@ -48,9 +48,13 @@ def main():
         work = torch.empty(_lib.lib().sd_ccl_workspace_bytes(batch.blk_total, batch.n_lines), dtype=torch.uint8, device=dev)
         cap = max(S.stats_capacity(batch), 2_000_000 if name == "dense" else 0)
         px = 128 * int(sum(m.shape[1] for m in masks))
+        import os
+        os.environ["SD_CCL_V1"] = "1"
+        t1 = ev(lambda: S.ccl_label(batch, planes, work))
+        os.environ["SD_CCL_V1"] = "0"
         t = ev(lambda: S.ccl_label(batch, planes, work))
         ts = ev(lambda: S.ccl_label_stats(batch, planes, cap, work))
-        out[name] = {"px": px, "label_ms": t, "label_frac": 5 * px / t / 1e6 / 6451.5, "label_stats_ms": ts,
+        out[name] = {"px": px, "label_v1_ms": t1, "label_ms": t, "label_frac": 5 * px / t / 1e6 / 6451.5, "label_stats_ms": ts,
                      "label_stats_frac": 5 * px / ts / 1e6 / 6451.5}
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
