@@ -356,6 +356,7 @@ def run_gpu(args):
         t_ext = ev_time(lambda: S.tile_extract_f16(bt, d_rgb_hbm, out=tiles_hbm))
         work = torch.empty(_lib.lib().sd_ccl_workspace_bytes(bt.blk_total, bt.n_lines), dtype=torch.uint8, device="cuda")
         t_ccl = ev_time(lambda: S.ccl_label(bt, planes_hbm, work))
+        t_ccls = ev_time(lambda: S.ccl_label_stats(bt, planes_hbm, S.stats_capacity(bt), work))
         hb = peaks["hbm_gbs"]
         b_ext = 3 * 128 * sum_wt + bt.n_tiles * 128 * 384 * 16
         b_ccl = 5 * px
@@ -363,6 +364,9 @@ def run_gpu(args):
             "sample": f"first {bt.n_lines} lines of the job: {bt.n_tiles} tiles, {px} px",
             "tile_extract_f16": {"ms": t_ext, "GBps": b_ext / t_ext / 1e6, "frac": b_ext / t_ext / 1e6 / hb},
             "ccl_label": {"ms": t_ccl, "GBps": b_ccl / t_ccl / 1e6, "frac": b_ccl / t_ccl / 1e6 / hb},
+            "ccl_label_stats": {"ms": t_ccls, "GBps": b_ccl / t_ccls / 1e6, "frac": b_ccl / t_ccls / 1e6 / hb,
+                                "note": "labels + the cv2 stats rows in one pass (what the pipeline runs); same 5 B/px algorithmic bytes"},
+            "glue": "none: reconstruct_images is fused into the UNet head (tiles OR their thresholded columns into the line planes)",
             "peak_GBps": hb}
         # BASELINE config 5 (CCL / clustering-bound stress): 64 dense 128x16384 masks (~800 k islands) in one launch
         from stroke_derenderer_b200.synth import synth_dense_mask
@@ -375,9 +379,11 @@ def run_gpu(args):
         p5 = torch.from_numpy(h5).to(torch.device("cuda", local))
         w5 = torch.empty(_lib.lib().sd_ccl_workspace_bytes(b5.blk_total, b5.n_lines), dtype=torch.uint8, device="cuda")
         t5 = ev_time(lambda: S.ccl_label(b5, p5, w5))
+        t5s = ev_time(lambda: S.ccl_label_stats(b5, p5, 2_000_000, w5))
         px5 = 128 * 16384 * n5
         extra["hbm_stages"]["ccl_label_config5"] = {"ms": t5, "GBps": 5 * px5 / t5 / 1e6, "frac": 5 * px5 / t5 / 1e6 / hb,
                                                     "sample": f"{n5} dense lines 128x16384, {px5} px"}
+        extra["hbm_stages"]["ccl_label_stats_config5"] = {"ms": t5s, "GBps": 5 * px5 / t5s / 1e6, "frac": 5 * px5 / t5s / 1e6 / hb}
         del p5, w5
 
     cpu = None

@@ -7,9 +7,8 @@
 //      of the strip is two 64-bit words Xe / Xo whose bit k is the left / right pixel of block k.  Lane L owns block
 //      rows 2L and 2L+1: occupancy, horizontal links, run starts and the contacts with the block row above are
 //      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row), unions
-//      are shared-memory atomicMin (min-root: the root of a component is its first block in raster order, which is
-//      what OpenCV's numbering sorts by); paths are flattened only after the union phase (a compressing store can
-//      undo a concurrent union, the round-1 lost-link race).  Outputs per strip: the Xe / Xo words (2 KB), the
+//      are shared-memory compare-and-swaps on roots only (min-root: the root of a component is its first block in
+//      raster order, which is what OpenCV's numbering sorts by), finds halve their paths.  Outputs per strip: the Xe / Xo words (2 KB), the
 //      run-start masks (512 B) and one 16-bit root per run (bit 15 = the root touches a neighbouring strip):
 //      ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that touch no other strip are final
 //      (root bitmap); the others register in the sparse global parent array.
@@ -61,13 +60,21 @@ __device__ __forceinline__ int cw_run_start(uint64_t rs, int k) { return 63 - __
 // Union-find over the runs of one strip, in shared memory.  Parents are 16-bit (node ids are < 4096): 8 KB per strip
 // instead of 16 KB, which is what bounds the number of resident warps.
 typedef unsigned short cw_node_t;
+// find with path halving.  Safe while unions are in flight because links are only ever created by a compare-and-swap
+// on a ROOT (below): a non-root entry is never the target of a union, so re-pointing it at its grandparent (an
+// ancestor for ever, parents only move towards the root) cannot undo a link; roots are never written here.
+// (Round 1 linked with atomicMin on possibly stale roots, where a compressing store could drop a fresh link.)
 __device__ __forceinline__ int cw_find(volatile cw_node_t* p, int a) {
   int q;
-  while ((q = p[a]) != a) a = q;
+  while ((q = p[a]) != a) {
+    const int g = p[q];
+    if (g != q) p[a] = (cw_node_t)g;
+    a = g;
+  }
   return a;
 }
 // min-root union: the larger root is hung under the smaller one with a compare-and-swap that only succeeds while it
-// still IS a root, so a link can never be overwritten.  No path compression while unions are in flight.
+// still IS a root, so a link can never be overwritten.
 __device__ __forceinline__ void cw_union(cw_node_t* p, int a, int b) {
   while (true) {
     a = cw_find(p, a);

@@ -92,7 +92,7 @@ def _tensor(buf: memoryview):
 
 
 def _node(buf: memoryview):
-    inputs, outputs, op, eps = [], [], "", BN_EPS
+    inputs, outputs, op, eps, attrs = [], [], "", BN_EPS, {}
     for fno, wt, val in _fields(buf):
         if fno == 1:
             inputs.append(bytes(val).decode())
@@ -100,16 +100,72 @@ def _node(buf: memoryview):
             outputs.append(bytes(val).decode())
         elif fno == 4:
             op = bytes(val).decode()
-        elif fno == 5:                              # AttributeProto: name (1), f (2)
-            aname, af = "", None
+        elif fno == 5:                              # AttributeProto: name (1), f (2), i (3), s (4), ints (8)
+            aname, aval, ints = "", None, []
             for f2, w2, v2 in _fields(val):
                 if f2 == 1:
                     aname = bytes(v2).decode()
                 elif f2 == 2 and w2 == 5:
-                    af = struct.unpack("<f", bytes(v2))[0]
-            if aname == "epsilon" and af is not None:
-                eps = float(af)
-    return {"op": op, "in": inputs, "out": outputs, "eps": eps}
+                    aval = struct.unpack("<f", bytes(v2))[0]
+                elif f2 == 3 and w2 == 0:
+                    aval = v2
+                elif f2 == 4 and w2 == 2:
+                    aval = bytes(v2).decode(errors="replace")
+                elif f2 == 8:
+                    if w2 == 0:
+                        ints.append(v2)
+                    else:                           # packed
+                        p = 0
+                        while p < len(v2):
+                            d, p = _varint(v2, p)
+                            ints.append(d)
+            attrs[aname] = ints if ints else aval
+            if aname == "epsilon" and isinstance(aval, float):
+                eps = float(aval)
+    return {"op": op, "in": inputs, "out": outputs, "eps": eps, "attrs": attrs}
+
+
+def check_topology(nodes, path: str = "model") -> None:
+    """The engine hard-codes the Attention-UNet data flow: a graph that merely has the right
+    conv shapes but another wiring would load cleanly and binarize wrongly, so refuse it here.  Checked: the graph
+    ENDS in a Sigmoid (evaluate_binarize.py:103 compares the output with bin_thr as a probability; the upstream
+    AttU_Net returns logits unless the export adds the activation), 4 MaxPool, 4 nearest Resize / Upsample, 4 Concat
+    whose FIRST input is the gated skip (a Mul) and whose second is the up-convolution path, 5 Sigmoid (4 psi + output),
+    and every Conv is stride 1, group 1, dilation 1, 'same' padding."""
+    def fail(msg):
+        raise ValueError(f"{path}: not the Attention-UNet binarizer graph this engine implements: {msg}")
+    producer = {o: nd for nd in nodes for o in nd["out"]}
+    compute = [nd for nd in nodes if nd["op"] not in ("Constant", "Identity", "Shape", "Gather", "Unsqueeze", "Cast", "Slice")]
+    if not compute or compute[-1]["op"] != "Sigmoid":
+        fail(f"the graph ends in {compute[-1]['op'] if compute else 'nothing'}, not Sigmoid (the engine thresholds probabilities; "
+             "re-export with the final sigmoid)")
+    count = lambda op: sum(1 for nd in nodes if nd["op"] == op)
+    ups = [nd for nd in nodes if nd["op"] in ("Resize", "Upsample")]
+    for op, want in (("MaxPool", 4), ("Concat", 4), ("Sigmoid", 5), ("Mul", 4)):
+        if count(op) != want:
+            fail(f"{count(op)} {op} nodes, expected {want}")
+    if len(ups) != 4:
+        fail(f"{len(ups)} Resize/Upsample nodes, expected 4")
+    for nd in ups:
+        mode = nd["attrs"].get("mode", "nearest")
+        if mode != "nearest":
+            fail(f"{nd['op']} mode {mode!r}, the engine upsamples with nearest")
+    for nd in nodes:
+        if nd["op"] == "Concat":
+            first = producer.get(nd["in"][0])
+            if len(nd["in"]) != 2 or first is None or first["op"] != "Mul":
+                fail("a Concat whose first input is not the gated skip tensor (x * psi)")
+            if nd["attrs"].get("axis", 1) != 1:
+                fail("a Concat that is not along the channel axis")
+        if nd["op"] == "MaxPool" and (nd["attrs"].get("kernel_shape", [2, 2]) != [2, 2] or nd["attrs"].get("strides", [2, 2]) != [2, 2]):
+            fail("a MaxPool that is not 2x2 / stride 2")
+        if nd["op"] == "Conv":
+            a = nd["attrs"]
+            k = a.get("kernel_shape", [None])[0]
+            if any(v != 1 for v in a.get("strides", [1, 1])) or any(v != 1 for v in a.get("dilations", [1, 1])) or a.get("group", 1) != 1:
+                fail("a Conv with stride / dilation / group other than 1")
+            if k is not None and any(v != k // 2 for v in a.get("pads", [k // 2] * 4)):
+                fail(f"a {k}x{k} Conv whose padding is not {k // 2}")
 
 
 def read_graph(path: str):
@@ -132,9 +188,12 @@ def read_graph(path: str):
     return nodes, inits
 
 
-def load_onnx_state(path: str, img_ch: int = 3, output_ch: int = 1, base: int = 64) -> dict:
-    """Folded conv weights of an exported AttU_Net as a state dict `<conv>.weight` / `<conv>.bias`."""
+def load_onnx_state(path: str, img_ch: int = 3, output_ch: int = 1, base: int = 64, check: bool = True) -> dict:
+    """Folded conv weights of an exported AttU_Net as a state dict `<conv>.weight` / `<conv>.bias`.  `check`: also
+    verify the wiring the engine hard-codes (`check_topology`)."""
     nodes, inits = read_graph(path)
+    if check:
+        check_topology(nodes, path)
     consumers = {}
     for nd in nodes:
         for i in nd["in"]:

@@ -302,12 +302,20 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
     binarized mask and the stroke-estimator partitions out, in input order — `binarize_image` + `main.py:108` +
     `get_partitions` of the reference for every image, as one pipelined job.  A mask is a (128, W', 1) view into one
     fresh array per chunk of lines (`copy=False`: into the reused page-locked staging, valid until the next call)."""
+    t0 = time.perf_counter()
     job = LineSegmentationJob(engine, images, bin_thr=bin_thr, lines_per_chunk=lines_per_chunk, crops=True, prepack=False, seg=seg)
+    t1 = time.perf_counter()
     lut = S.input_lut(S.IMAGENET_MEAN, S.IMAGENET_STD)
     masks, parts = [], []
+    t_collect = [0.0]
 
     def collect(ch, res):
+        tc = time.perf_counter()
         m, p = job.chunk_outputs(ch, res, lut, copy)
         masks.extend(m); parts.extend(p)
+        t_collect[0] += time.perf_counter() - tc
     job._run(True, "device", collect=collect)
+    if os.environ.get("SD_PIPE_DEBUG"):
+        print(f"[segment_lines] job construction {1e3 * (t1 - t0):.1f} ms, run {1e3 * (time.perf_counter() - t1):.1f} ms "
+              f"(of which per-line outputs {1e3 * t_collect[0]:.1f} ms)", file=sys.stderr, flush=True)
     return masks, parts

@@ -184,6 +184,13 @@ def test_onnx_reader_recovers_folded_weights(tmp_path):
     bad.write_bytes(b"\x08\x08")
     with pytest.raises(ValueError):
         load_onnx_state(str(bad))
+    # graphs with the right conv shapes but another wiring load cleanly nowhere: the engine hard-codes the data flow
+    for kw, what in (({"final_sigmoid": False}, "Sigmoid"), ({"resize_mode": "linear"}, "nearest"), ({"swap_concat": True}, "gated skip")):
+        p = tmp_path / "wrong.onnx"
+        _write_onnx(p, state, True, **kw)
+        with pytest.raises(ValueError, match=what):
+            load_onnx_state(str(p))
+        assert len(load_onnx_state(str(p), check=False)) == 2 * len(conv_bn_slots())      # the weights themselves still parse
 
 
 def test_bench_reference_arm_prints_one_json_line():
