@@ -87,12 +87,8 @@ class BinarizationSession:
         return job.binarize_step()
 
     def _segmenter(self, ort):
-        """One Segmenter (streams' staging buffers) per engine, kept across calls."""
-        seg = getattr(ort, "_sd_segmenter", None)
-        if seg is None or seg.bin_thr != self.bin_thr:
-            seg = _seg.Segmenter(ort, bin_thr=self.bin_thr)
-            ort._sd_segmenter = seg
-        return seg
+        """One Segmenter (streams, staging buffers) per engine, kept across calls."""
+        return _seg.Segmenter.for_engine(ort, self.bin_thr)
 
     def binarize_image(self, image, ort):
         """:143-150."""

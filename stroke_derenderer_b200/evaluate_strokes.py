@@ -94,12 +94,13 @@ class StrokeEstimationSession:
                 if keep_device:
                     self.last_device_crops.append(cr["image_input"] if cr is not None else None)
                 imgs_h = cr["image_host"].copy() if cr is not None and "image_host" in cr else None
+                if cr is not None and len(groups):
+                    left, top = groups[:, 1], groups[:, 2]
+                    ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
+                LP = _seg.LazyPartition
                 for k in range(batch.n_lines):
-                    a, b = int(lgs[k]), int(lgs[k + 1])
-                    out.append([_seg.LazyPartition(lut, image=imgs_h[g], translate1=(groups[g, 1], groups[g, 2]),
-                                                   ratio=float(cr["ratio"][g]),
-                                                   translate2=(float(cr["translate2"][g, 0]), float(cr["translate2"][g, 1])))
-                                for g in range(a, b)])
+                    out.append([LP(lut, image=imgs_h[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
+                                for g in range(int(lgs[k]), int(lgs[k + 1]))])
         return out
 
     def load_orts(self, filepaths):

@@ -87,7 +87,7 @@ class LineSegmentationJob:
         self.lines_per_chunk = lines_per_chunk
         self.chunks = []
         with torch.cuda.device(self.device):
-            self.s_copy, self.s_unet, self.s_part = (torch.cuda.Stream(self.device) for _ in range(3))
+            self.s_copy, self.s_unet, self.s_part = self.seg.streams()
             t0 = 0
             for c0 in range(0, len(images), lines_per_chunk):
                 imgs = images[c0:c0 + lines_per_chunk]
@@ -277,13 +277,15 @@ class LineSegmentationJob:
             hp = hp.copy()
             if img_host is not None:
                 img_host = img_host.copy()
-        ratio, t2 = (cr["ratio"], cr["translate2"]) if cr is not None else (None, None)
+        if cr is not None and len(groups):
+            left, top = groups[:, 1], groups[:, 2]
+            ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
+        LP = S.LazyPartition
         for k, ln in enumerate(ch.batch.lines):
             off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
             masks.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
-            a, b = int(lgs[k]), int(lgs[k + 1])
-            parts.append([S.LazyPartition(lut, image=img_host[g], translate1=(groups[g, 1], groups[g, 2]), ratio=float(ratio[g]),
-                                          translate2=(float(t2[g, 0]), float(t2[g, 1]))) for g in range(a, b)])
+            parts.append([LP(lut, image=img_host[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
+                          for g in range(int(lgs[k]), int(lgs[k + 1]))])
         return masks, parts
 
     def line_outputs(self, results, copy: bool = True, mean=None, std=None):
@@ -303,6 +305,8 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
     `get_partitions` of the reference for every image, as one pipelined job.  A mask is a (128, W', 1) view into one
     fresh array per chunk of lines (`copy=False`: into the reused page-locked staging, valid until the next call)."""
     t0 = time.perf_counter()
+    if seg is None:
+        seg = S.Segmenter.for_engine(engine, bin_thr)
     job = LineSegmentationJob(engine, images, bin_thr=bin_thr, lines_per_chunk=lines_per_chunk, crops=True, prepack=False, seg=seg)
     t1 = time.perf_counter()
     lut = S.input_lut(S.IMAGENET_MEAN, S.IMAGENET_STD)

@@ -441,6 +441,25 @@ class Segmenter:
         self.bin_thr = bin_thr
         self.margin = margin
         self.staging = PinnedStaging()
+        self._streams = None
+
+    @classmethod
+    def for_engine(cls, engine: UNetEngine, bin_thr: float = 0.5) -> "Segmenter":
+        """The Segmenter kept with an engine across calls: its pinned staging buffers and its CUDA streams are
+        reused (the caching allocator pools device memory per stream: fresh streams per call would turn every
+        allocation of a call into a cudaMalloc)."""
+        seg = getattr(engine, "_sd_segmenter", None)
+        if seg is None or seg.bin_thr != bin_thr:
+            seg = cls(engine, bin_thr=bin_thr)
+            engine._sd_segmenter = seg
+        return seg
+
+    def streams(self):
+        """(copy, unet, part) streams of the chunk pipeline, created once per Segmenter."""
+        if self._streams is None:
+            with torch.cuda.device(self.device):
+                self._streams = tuple(torch.cuda.Stream(self.device) for _ in range(3))
+        return self._streams
 
     def binarize(self, images, d_rgb: torch.Tensor | None = None, batch: LineBatch | None = None):
         """-> (batch, mask planes u8 {0,255} packed on device)."""
