@@ -199,6 +199,10 @@ int sd_group_canvas(const int32_t* d_labels, const sd_line* d_lines,
 int sd_group_crops(const uint8_t* d_canvas, const int64_t* d_groups, const int32_t* d_rs_dims, int n_groups,
                    int size, uint8_t* d_image_u8, float* d_input_f32, const float* d_lut, void* stream);
 
+/* Stroke-estimator front end, evaluate_strokes.py:72-91 (_encode_postprocess): encoder output d_enc (B, C, h, w) f32
+ * -> d_out (B, 2h * 2w, C) f32, every value repeated on a 2 x 2 grid, channels last, positions flattened. */
+int sd_encode_postprocess(const float* d_enc, int B, int C, int h, int w, float* d_out, void* stream);
+
 /* common.py:85-93 / helper/split.py:127-135 (resize_to_height) for lines whose height is not 128:
  * cv2.resize(img, (dst_w, 128)) with the default INTER_LINEAR, bit-exact (8-bit fixed point, 2x area shortcut),
  * dst_w = int(w * (128 / h)) computed by the caller like the reference does.  Reads (src_h, src_w, 3) u8 at

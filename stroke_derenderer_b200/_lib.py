@@ -73,6 +73,7 @@ EXPORTS = {
                                   C.c_void_p]),
     "sd_group_crops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "sd_encode_postprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_resize_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sd_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "sd_host_unregister": (C.c_int, [C.c_void_p]),

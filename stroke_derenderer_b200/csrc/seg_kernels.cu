@@ -990,12 +990,47 @@ __global__ void __launch_bounds__(256) resize_lines_kernel(const uint8_t* __rest
     }
   }
 }
+// ---------------------------------------------------------------------------
+// K12: stroke-estimator front end, evaluate_strokes.py:72-91 (_encode_postprocess): the encoder output (B, C, h, w)
+//   f32 becomes (B, 2h * 2w, C) f32: every value repeated on a 2 x 2 grid (the reference's stand-in for the encoder's
+//   AdaptiveAvgPool2d), channels last, positions flattened.  Pure data movement: one CTA per (image, 32-channel slab)
+//   reads the slab along its contiguous h*w axis, transposes it through shared memory and writes 128-byte channel
+//   runs for each of the 4 h w output positions.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) encode_postprocess_kernel(const float* __restrict__ enc, int C, int h, int w,
+                                                                 float* __restrict__ out) {
+  extern __shared__ float s_slab[];                 // [32][h*w + 1]
+  const int hw = h * w, b = blockIdx.y, c0 = blockIdx.x * 32;
+  const int nc = min(32, C - c0);
+  const float* src = enc + ((int64_t)b * C + c0) * hw;
+  for (int i = threadIdx.x; i < nc * hw; i += blockDim.x) s_slab[(i / hw) * (hw + 1) + i % hw] = __ldg(src + i);
+  __syncthreads();
+  const int W2 = 2 * w, P = 4 * hw;
+  float* dst = out + (int64_t)b * P * C + c0;
+  for (int i = threadIdx.x; i < P * 32; i += blockDim.x) {
+    const int c = i & 31, pos = i >> 5;
+    if (c >= nc) continue;
+    const int oy = pos / W2, ox = pos - oy * W2;
+    dst[(int64_t)pos * C + c] = s_slab[c * (hw + 1) + (oy >> 1) * w + (ox >> 1)];
+  }
+}
 }  // namespace sd
 
 // ===========================================================================
 // C ABI
 // ===========================================================================
 using namespace sd;
+
+extern "C" int sd_encode_postprocess(const float* d_enc, int B, int C, int h, int w, float* d_out, void* stream) {
+  if (B == 0) return SD_OK;
+  SD_REQUIRE(d_enc && d_out && B > 0 && C > 0 && h > 0 && w > 0, "sd_encode_postprocess: bad argument");
+  SD_REQUIRE(B <= 65535, "sd_encode_postprocess: %d images in one call (max 65535)", B);
+  const int smem = 32 * (h * w + 1) * (int)sizeof(float);
+  SD_REQUIRE(smem <= 48 * 1024, "sd_encode_postprocess: feature map %dx%d too large", h, w);
+  encode_postprocess_kernel<<<dim3((C + 31) / 32, B), 256, smem, (cudaStream_t)stream>>>(d_enc, C, h, w, d_out);
+  SD_LAUNCH_CHECK("encode_postprocess_kernel");
+  return SD_OK;
+}
 
 extern "C" int sd_plan_lines(const int32_t* h_widths, int n_lines, int tile_w, int overlap,
                              sd_line* out, sd_plan* plan) {

@@ -19,6 +19,9 @@ STD = [0.229, 0.224, 0.225]
 PAD, BOS, EOS = 0, 1, 2
 
 
+_host_pool = _seg.host_pool
+
+
 class StrokeEstimationSession:
     def __init__(self, configs_path=None, **params):
         # :35-50
@@ -63,24 +66,43 @@ class StrokeEstimationSession:
         seg = self._segmenter()
         dev = seg.device
         lut = _seg.input_lut(self.mean, self.std)
+        pool = _host_pool()
         out = []
         self.last_device_crops = []
+        pending = []                      # (future of the fresh copy of the crops, chunk tables) of the chunks in flight
+
+        def pack_one(args):
+            m, ln, hn = args
+            off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(m.shape[1])
+            view = hn[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)
+            m = np.asarray(m)
+            if m.dtype == np.bool_:
+                view[:, :w] = m                       # img_bin.astype(np.uint8) of :193
+            else:
+                np.not_equal(m, 0, out=view[:, :w], casting="unsafe")
+            view[:, w:] = 0                           # pad columns of the plane must be zero (CCL strips)
+
+        def finish(item):
+            fut, groups, lgs, cr, n_lines = item
+            imgs_h = fut.result() if fut is not None else None
+            if cr is not None and len(groups):
+                left, top = groups[:, 1], groups[:, 2]
+                ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
+            LP = _seg.LazyPartition
+            for k in range(n_lines):
+                out.append([LP(lut, image=imgs_h[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
+                            for g in range(int(lgs[k]), int(lgs[k + 1]))])
+
         with torch.cuda.device(dev):
             for c0 in range(0, len(imgs_bin), lines_per_chunk):
                 masks = imgs_bin[c0:c0 + lines_per_chunk]
-                key = ("chunk", (c0 // lines_per_chunk) & 1)           # two staging sets: pack k+1 while k is in flight
+                key = ("chunk", (c0 // lines_per_chunk) & 1)           # two staging sets: chunk k+1 is packed while the
+                if len(pending) == 2:                                  # host copy of chunk k-1 still reads the other set
+                    finish(pending.pop(0))
                 batch = _seg.plan_batch([m.shape[1] for m in masks], dev)
                 h = seg.staging.get_tensor((key, "masks"), batch.px_total)
                 hn = h.numpy()
-                for m, ln in zip(masks, batch.lines):
-                    off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(m.shape[1])
-                    view = hn[off:off + _seg.TILE_H * pitch].reshape(_seg.TILE_H, pitch)
-                    m = np.asarray(m)
-                    if m.dtype == np.bool_:
-                        view[:, :w] = m                   # img_bin.astype(np.uint8) of :193
-                    else:
-                        np.not_equal(m, 0, out=view[:, :w], casting="unsafe")
-                    view[:, w:] = 0                       # pad columns of the plane must be zero (CCL strips)
+                list(pool.map(pack_one, [(m, ln, hn) for m, ln in zip(masks, batch.lines)]))   # numpy copies release the GIL
                 planes = h.to(dev, non_blocking=True)
                 res = seg.partition(batch, planes, canvases="device", key=key, crops=True, crops_to_host=True,
                                     crop_lut=lut if keep_device else None)
@@ -90,21 +112,80 @@ class StrokeEstimationSession:
                     img = res["crops"]["image"]
                     res["crops"]["image_host"] = _seg.copy_d2h(seg.staging.get((key, "crops"), img.numel()), img, dev).reshape(tuple(img.shape))
                 torch.cuda.current_stream(dev).synchronize()
-                cr, groups, lgs = res["crops"], res["groups"], res["line_group_start"]
+                cr = res["crops"]
                 if keep_device:
                     self.last_device_crops.append(cr["image_input"] if cr is not None else None)
-                imgs_h = cr["image_host"].copy() if cr is not None and "image_host" in cr else None
-                if cr is not None and len(groups):
-                    left, top = groups[:, 1], groups[:, 2]
-                    ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
-                LP = _seg.LazyPartition
-                for k in range(batch.n_lines):
-                    out.append([LP(lut, image=imgs_h[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
-                                for g in range(int(lgs[k]), int(lgs[k + 1]))])
+                fut = pool.submit(np.copy, cr["image_host"]) if cr is not None and "image_host" in cr else None
+                pending.append((fut, res["groups"], res["line_group_start"], cr, batch.n_lines))
+            while pending:
+                finish(pending.pop(0))
         return out
 
+    # ---- stroke-estimator front end (evaluate_strokes.py:150-160, 250-262) --------------------
     def load_orts(self, filepaths):
-        raise NotImplementedError("stroke-estimator graphs are outside the B200 segmentation path (SURVEY.md 2)")
+        """:150-160.  The stroke-estimator graphs (encoder, projection, decoder_*) live on the same Drive link as the
+        binarizer and, unlike the binarizer, not even their topology is named in the reference, so this framework
+        cannot execute them: every value of `filepaths` must already be a model HANDLE, an object with
+        `.run(output_names, {"input": ndarray}) -> [ndarray]` (the onnxruntime signature the reference uses) and
+        optionally `.run_device(output_names, {"input": cuda tensor}) -> [cuda tensor]` to keep the batch in HBM.
+        A path raises: there is no CPU fallback and no ONNX executor here."""
+        orts = {}
+        for k, v in filepaths.items():
+            if not hasattr(v, "run"):
+                raise NotImplementedError(f"'{k}': {v!r} is not a model handle; the stroke-estimator graphs are not part of the "
+                                          "reference tree and cannot be executed by this framework (SURVEY.md 2)")
+            orts[k] = v
+        return orts
+
+    @staticmethod
+    def _run_handle(handle, out_names, x):
+        """One model call with the batch kept on the GPU when the handle can take it."""
+        if hasattr(handle, "run_device"):
+            return handle.run_device(out_names, {"input": x})[0]
+        y = handle.run(out_names, {"input": x.cpu().numpy() if isinstance(x, torch.Tensor) else x})[0]
+        return torch.from_numpy(np.ascontiguousarray(y)).to(x.device) if isinstance(x, torch.Tensor) else y
+
+    def _encode_postprocess(self, enc):
+        """:72-91 on the GPU (sd_encode_postprocess): (B, C, E/2, E/2) -> (B, E*E, C) f32, values repeated on a 2x2
+        grid.  numpy in -> numpy out, cuda tensor in -> cuda tensor out."""
+        from . import _lib
+        is_np = not isinstance(enc, torch.Tensor)
+        dev = torch.device("cuda", self.device)
+        t = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32)).to(dev) if is_np else enc.to(torch.float32).contiguous()
+        B, C, h, w = t.shape
+        E = self.enc_image_size
+        if (2 * h, 2 * w) != (E, E):
+            raise ValueError(f"encoder output {h}x{w} does not fill the {E}x{E} grid of _encode_postprocess")
+        out = torch.empty((B, E * E, C), dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().sd_encode_postprocess(t.data_ptr(), B, C, h, w, out.data_ptr(),
+                                                        torch.cuda.current_stream(t.device).cuda_stream), "sd_encode_postprocess")
+        return out.cpu().numpy() if is_np else out
+
+    def encode_partitions_batch(self, imgs_bin, orts, max_batch: int = 512):
+        """The front half of `estimate_strokes` (:250-262) for MANY lines at once: partitions of every line (device
+        crops, never copied to the host as f32) -> encoder in batches of up to `max_batch` crops that cross line
+        boundaries -> _encode_postprocess -> optional projection.  The reference runs this per line image with
+        whatever batch that line happens to have (:171-181).
+        -> (partitions per line, enc per line: cuda tensor (n_parts, P, E) f32)."""
+        parts = self.get_partitions_batch(imgs_bin, keep_device=True)
+        crops = [c for c in self.last_device_crops if c is not None and c.shape[0]]
+        encs = []
+        if crops:
+            allc = torch.cat(crops, 0) if len(crops) > 1 else crops[0]
+            for s0 in range(0, allc.shape[0], max_batch):
+                enc = self._run_handle(orts["encoder"], ["output"], allc[s0:s0 + max_batch])
+                enc = self._encode_postprocess(enc)
+                if "projection" in orts:
+                    enc = self._run_handle(orts["projection"], ["output"], enc)
+                encs.append(enc)
+        enc_all = torch.cat(encs, 0) if encs else None
+        out, g = [], 0
+        for pl in parts:
+            out.append(enc_all[g:g + len(pl)] if enc_all is not None else torch.zeros((0, 0, 0)))
+            g += len(pl)
+        return parts, out
 
     def process_image(self, img_bin, orts, max_length=None):
-        raise NotImplementedError("stroke estimation is outside the B200 segmentation path (SURVEY.md 2)")
+        raise NotImplementedError("the LSTM-attention stroke decoder (evaluate_strokes.py:262-303) is a second model outside the "
+                                  "B200 segmentation path (SURVEY.md 2); its front end is encode_partitions_batch")

@@ -273,10 +273,11 @@ class LineSegmentationJob:
         cr = res["crops"]
         img_host = cr["image_host"] if cr is not None and "image_host" in cr else None
         groups, lgs = res["groups"], res["line_group_start"]
-        if copy:
-            hp = hp.copy()
+        if copy:                          # fresh arrays (two host threads; numpy copies release the GIL)
+            f1 = S.host_pool().submit(np.copy, hp)
             if img_host is not None:
                 img_host = img_host.copy()
+            hp = f1.result()
         if cr is not None and len(groups):
             left, top = groups[:, 1], groups[:, 2]
             ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()

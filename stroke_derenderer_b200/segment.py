@@ -84,13 +84,21 @@ def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True, out: torch.Ten
                                                   pin_memory=pinned and torch.cuda.is_available())
     assert buf.numel() >= int(batch.plan.img_bytes)
     nb = buf.numpy()
-    for img, ln in zip(images, batch.lines):
+
+    def put(args):
+        img, ln = args
         if img.shape[0] != TILE_H:
-            continue
+            return
         a = np.ascontiguousarray(img, dtype=np.uint8)
         assert a.shape == (TILE_H, int(ln["width"]), 3), (a.shape, int(ln["width"]))
         off = int(ln["img_off"])
         nb[off:off + a.size] = a.reshape(-1)
+    work = list(zip(images, batch.lines))
+    if int(batch.plan.img_bytes) >= (8 << 20):          # numpy copies release the GIL: a few threads beat one core's memcpy
+        list(host_pool().map(put, work))
+    else:
+        for wk in work:
+            put(wk)
     return buf
 
 
@@ -335,6 +343,18 @@ def group_crops(device, canvas: torch.Tensor, d_groups: torch.Tensor, groups: np
                                              d_lut.data_ptr() if d_lut is not None else None,
                                              torch.cuda.current_stream(device).cuda_stream), "sd_group_crops")
     return {"image": image, "image_input": inp, "ratio": ratio, "translate2": t2, "rs_dims": rs}
+
+
+_POOL = None
+
+
+def host_pool():
+    """A few host threads for the big numpy copies of the batched calls (packing lines, fresh copies of results)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="sd-host")
+    return _POOL
 
 
 class PinnedStaging:

@@ -428,3 +428,49 @@ def test_ccl_union_race_regression(cuda_device):
         assert bool((num == n_ref).all()), int((num != n_ref).sum().item())
         got = labels.view(2000, 128, 128)
         assert bool((got == torch.from_numpy(ref).to(got.device).to(torch.int32)[None]).all())
+
+
+def test_stroke_front_end_encode_postprocess_and_batching(cuda_device):
+    """_encode_postprocess (evaluate_strokes.py:72-91) on the GPU, bit-exact against the
+    reference's numpy expression, and the batched front end: the device-resident crops of MANY lines go through an
+    encoder handle in cross-line batches.  The encoder graph itself is not in the reference (Drive file, topology not
+    even named), so the handle here is a small seeded torch module: the plumbing is what is checked."""
+    from stroke_derenderer_b200.evaluate_strokes import StrokeEstimationSession
+    se = StrokeEstimationSession()
+    rng = np.random.default_rng(5)
+    for B, C in ((1, 8), (5, 100), (33, 512)):
+        enc = rng.standard_normal((B, C, 7, 7)).astype(np.float32)
+        ref = np.zeros((B, C, 14, 14), np.float32)                 # the reference's expression, verbatim semantics
+        ref[:, :, ::2, ::2] = enc; ref[:, :, 1::2, 1::2] = enc; ref[:, :, ::2, 1::2] = enc; ref[:, :, 1::2, ::2] = enc
+        ref = np.reshape(np.transpose(ref, (0, 2, 3, 1)), (B, -1, C)).astype(np.float32)
+        assert np.array_equal(se._encode_postprocess(enc), ref)
+        assert torch.equal(se._encode_postprocess(torch.from_numpy(enc).cuda()).cpu(), torch.from_numpy(ref))
+
+    class Encoder:                       # stand-in handle with both call forms; (B,3,224,224) -> (B,16,7,7)
+        def __init__(self):
+            torch.manual_seed(3)
+            self.net = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 7, 32, 3), torch.nn.ReLU()).cuda().eval()
+            self.batches = []
+
+        @torch.no_grad()
+        def run_device(self, names, feeds):
+            self.batches.append(int(feeds["input"].shape[0]))
+            return [self.net(feeds["input"])]
+
+        def run(self, names, feeds):
+            return [self.run_device(names, {"input": torch.from_numpy(feeds["input"]).cuda()})[0].cpu().numpy()]
+
+    masks = [ink_mask(synth_line(w, seed=500 + i)) for i, w in enumerate([900, 2000, 1300, 64])]
+    enc_h = Encoder()
+    orts = se.load_orts({"encoder": enc_h})
+    parts, encs = se.encode_partitions_batch(masks, orts, max_batch=16)
+    n = sum(len(p) for p in parts)
+    assert n > 16 and sum(enc_h.batches) == n and max(enc_h.batches) == 16          # batches cross line boundaries
+    for p, e in zip(parts, encs):
+        assert e.shape[0] == len(p)
+        if len(p):                       # per line == the reference order of operations on that line's own crops
+            x = np.stack([q["image_input"] for q in p]).astype(np.float32)
+            want = se._encode_postprocess(enc_h.run(["output"], {"input": x})[0])
+            assert np.allclose(e.cpu().numpy(), want, rtol=1e-4, atol=1e-5) and e.shape[1:] == (196, 16)
+    with pytest.raises(NotImplementedError):
+        se.load_orts({"encoder": "models/encoder.onnx"})

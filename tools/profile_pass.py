@@ -56,6 +56,8 @@ def main():
     if args.what in ("all", "unet"):
         eng = UNetEngine(state, device=0, max_tiles=nt)
         masks = torch.empty((nt, 128, 384), dtype=torch.uint8, device=dev)
+        if batch.n_tiles < nt:
+            raise SystemExit(f"--lines {args.lines} give {batch.n_tiles} tiles, fewer than --tiles {nt}")
         out["unet_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5))
         out["unet_sustained_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5), reps=60)   # power-capped steady state
         for small in (37, 64):
@@ -83,20 +85,22 @@ def main():
                 planes_h[int(ln["px_off"]):int(ln["px_off"]) + 128 * int(ln["pitch"])] = m.reshape(-1)
             planes = torch.from_numpy(planes_h).to(dev)
         else:
-            # text-like masks: the ink of the synthetic lines, run through the real tile -> glue path
-            mask_tiles = (tiles[..., 0] < 0.5).to(torch.uint8) * 255
-            planes = S.glue_u8(batch, mask_tiles.contiguous())
+            # text-like masks: the ink of the synthetic lines (there is no glue pass any more: the UNet head writes the planes)
+            planes_h = np.zeros(batch.px_total, np.uint8)
+            for im, ln in zip(images, batch.lines):
+                off, pitch = int(ln["px_off"]), int(ln["pitch"])
+                planes_h[off:off + 128 * pitch].reshape(128, pitch)[:, :im.shape[1]] = (im[:, :, 0] < 128) * 255
+            planes = torch.from_numpy(planes_h).to(dev)
             out["tile_extract_f16_ms"] = ev(lambda: S.tile_extract_f16(batch, d_rgb, out=tiles))
-            out["glue_u8_ms"] = ev(lambda: S.glue_u8(batch, mask_tiles, out=planes))
         seg = S.Segmenter(None, device=dev)
         work = torch.empty(_lib.lib().sd_ccl_workspace_bytes(batch.blk_total, batch.n_lines), dtype=torch.uint8, device=dev)
         out["ccl_ms"] = ev(lambda: S.ccl_label(batch, planes, work))
+        out["ccl_label_stats_ms"] = ev(lambda: S.ccl_label_stats(batch, planes, max(S.stats_capacity(batch), 2_000_000 if args.what == "dense" else 0), work))
         seg.partition(batch, planes, canvases="device")
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         if args.what != "dense":
             S.tile_extract_f16(batch, d_rgb, out=tiles)
-            S.glue_u8(batch, mask_tiles, out=planes)
         res = seg.partition(batch, planes, canvases="device", crops=True)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
