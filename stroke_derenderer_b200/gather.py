@@ -37,7 +37,7 @@ def _up(v: int, a: int) -> int:
 
 
 def region_capacity(n_tiles: int, n_lines: int, px_total: int, n_chunks: int, crop_size: int = 224,
-                    groups_per_tile: float = 6.0, islands_per_tile: float = 40.0) -> int:
+                    groups_per_tile: float = 4.5, islands_per_tile: float = 40.0) -> int:
     """Bytes a rank's region needs for one step: exact for the planes, generous bounds for what depends on the
     data (islands, groups; measured on the synthetic lines: ~6 islands and ~2.7 groups per tile).  A step that
     outgrows its region raises, it never writes past it."""
