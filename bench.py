@@ -189,34 +189,22 @@ def run_gpu(args):
     job = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops)
     # the end-to-end job starts from the plain numpy images (packing inside the step) and gathers on the host:
     # every rank's D2H copies land in its page-locked region of one /dev/shm arena, rank 0 reads all lines in input order
-    job_e2e = LineSegmentationJob(engine, images, lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops, prepack=False)
-    caps = torch.tensor([job_e2e.arena_bytes() if r == rank else 0 for r in range(world)], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(caps, op=dist.ReduceOp.SUM)
-    caps = [int(v) for v in caps.tolist()]
-    arena_name = f"sd_b200_gather_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}"
-    arena = G.ResultArena(arena_name, caps, rank, create=True) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    if arena is None:
-        arena = G.ResultArena(arena_name, caps, rank, create=False)
-    arena.register()
-    writer = G.RegionWriter(arena.region(rank), max(len(job_e2e.chunks), 1))
+    from stroke_derenderer_b200.pipeline import ShardedSegmentation
+    sharded = ShardedSegmentation(engine, images, widths, rank=rank, world=world, barrier=dist.barrier if world > 1 else None,
+                                  lines_per_chunk=args.lines_per_chunk, crops=not args.no_crops)
+    job_e2e, caps = sharded.job, sharded.caps
     gather_ms = []
 
     def e2e_step():
-        res = job_e2e.host_step(writer)                  # ends with a stream synchronize: this rank's bytes are in the arena
-        if world > 1:
-            dist.barrier()
+        t0 = time.perf_counter()
+        res, got = sharded.step()
         if rank == 0:                                    # the caller now holds every line, in input order
-            t0 = time.perf_counter()
-            got = G.GatheredResults(arena, shards, widths, args.lines_per_chunk, step=writer.step)
+            t1 = time.perf_counter()
             probe = (0, n_total // 2, n_total - 1)
             e2e_step.check = [(int(got.mask(i).shape[1]), got.num(i), int(got.crops(i).shape[0])) for i in probe]
-            gather_ms.append(1e3 * (time.perf_counter() - t0))
+            gather_ms.append(1e3 * (time.perf_counter() - t1))
             del got
-        if world > 1:
-            dist.barrier()                               # readers are done before the next step reuses the arena
+        sharded.release()                                # readers are done before the next step reuses the arena
         return res
 
     def barrier():
@@ -467,7 +455,7 @@ def run_gpu(args):
         out.update(extra)
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     engine.close()
-    arena.close()
+    sharded.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -78,8 +78,63 @@ def main(imgs, bs, ort_bs, se, orts_se, output_folder, strokes=True):
             print(f"{filename}: {len(out)} crops, saved to {path}")
 
 
+def main_sharded(img_filepaths, models_folder, output_folder, strokes=True):
+    """The same job over ALL GPUs of the box: `torchrun --nnodes=1 --nproc-per-node N main.py -models DIR ...`.
+    One process per GPU, lines dealt to ranks by tile count, every rank's results land in its region of one shared-memory
+    arena (no collective on the data path; the process group only provides the barrier), rank 0 writes every output
+    file in input order — what the reference's single process does (main.py:91-136)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from stroke_derenderer_b200 import segment as _seg
+    from stroke_derenderer_b200.pipeline import ShardedSegmentation
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0")) % max(torch.cuda.device_count(), 1)
+    dist.init_process_group("gloo")
+    paths = sorted(img_filepaths)
+    # sizes of all lines: every rank decodes a slice of the folder, the (h, w) pairs are exchanged as small objects
+    mine_hw = {i: load_image(paths[i]).shape[:2] for i in range(rank, len(paths), world)}
+    all_hw = [None] * world
+    dist.all_gather_object(all_hw, mine_hw)
+    hw = {k: v for d in all_hw for k, v in d.items()}
+    widths = [_seg.resized_width_hw(int(hw[i][0]), int(hw[i][1])) for i in range(len(paths))]
+    cfg_b = Path(models_folder) / "configs_binarizer.json"
+    bs = BinarizationSession(configs_path=str(cfg_b) if cfg_b.exists() else None, device=local)
+    weights = Path(models_folder) / "binarizer.onnx"
+    if not weights.exists():
+        weights = Path(models_folder) / "binarizer.npz"
+    ort_bs = bs.init_onnx_inference(str(weights))
+    job = ShardedSegmentation(ort_bs, [load_image(paths[i]) for i in ShardedSegmentation.shard_of(widths, rank, world)], widths,
+                              rank=rank, world=world, barrier=dist.barrier, lines_per_chunk=bs.lines_per_chunk, crops=strokes)
+    try:
+        _, got = job.step()
+        if rank == 0:
+            Path(output_folder).mkdir(parents=True, exist_ok=True)
+            for i, p in enumerate(paths):
+                stem = Path(p).stem
+                img_bin = got.mask(i) > (255 * bs.bin_thr)                  # main.py:108
+                save_image(normalize_image(img_bin.astype(np.uint8)), str(Path(output_folder) / f"{stem}_BINARIZED.png"), grayscale=True)
+                if strokes:
+                    g = got.groups(i)
+                    _, ratio, t2 = _seg.crop_geometry(g) if len(g) else (None, [], [])
+                    out = [{"translate1": [int(g[k, 1]), int(g[k, 2])], "ratio": float(ratio[k]),
+                            "translate2": [float(t2[k, 0]), float(t2[k, 1])]} for k in range(len(g))]
+                    save_json(out, str(Path(output_folder) / f"{stem}_PARTITIONS.json"))
+            print(f"{len(paths)} images binarized" + (" and partitioned" if strokes else "") + f" on {world} GPU process(es); results in {output_folder}")
+            del got
+        job.release()
+    finally:
+        job.close()
+        ort_bs.close()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    import os
     vargs = parse_args()
     paths = [str(x) for x in Path(vargs.input).glob("*.png")]
-    sessions = initialize_sessions(vargs.models)
-    main(load_images(paths), *sessions, vargs.output, strokes=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        main_sharded(paths, vargs.models, vargs.output, strokes=True)
+    else:
+        sessions = initialize_sessions(vargs.models)
+        main(load_images(paths), *sessions, vargs.output, strokes=True)

@@ -324,3 +324,65 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
         print(f"[segment_lines] job construction {1e3 * (t1 - t0):.1f} ms, run {1e3 * (time.perf_counter() - t1):.1f} ms "
               f"(of which per-line outputs {1e3 * t_collect[0]:.1f} ms)", file=sys.stderr, flush=True)
     return masks, parts
+
+
+class ShardedSegmentation:
+    """One job over all GPUs of a box, the way the reference's single process sees it (main.py:91-136: one list of
+    images in, results in input order out): one PROCESS per GPU (torchrun ranks), whole lines dealt to ranks by tile
+    count (`shard_lines`), no data-path collective.  Every rank runs its shard through `LineSegmentationJob.host_step`
+    with its D2H copies landing in its page-locked region of one `/dev/shm` arena; after a barrier the caller (rank 0)
+    holds every line of every rank in input order (`gather.GatheredResults`).
+
+    widths: the resized widths of ALL lines (every rank knows them); images: THIS rank's lines, in the order of
+    `shards[rank]`; barrier: a callable that synchronises the ranks (torch.distributed.barrier), None for one rank."""
+
+    def __init__(self, engine: UNetEngine, images, widths, rank: int = 0, world: int = 1, barrier=None, name: str | None = None,
+                 lines_per_chunk: int = 32, crops: bool = True, all_caps=None):
+        self.rank, self.world, self.barrier = rank, world, barrier
+        self.widths = [int(w) for w in widths]
+        self.shards = shard_lines(self.widths, world)
+        if len(images) != len(self.shards[rank]):
+            raise ValueError(f"rank {rank}: got {len(images)} lines, its shard has {len(self.shards[rank])}")
+        self.lines_per_chunk = lines_per_chunk
+        self.job = LineSegmentationJob(engine, images, lines_per_chunk=lines_per_chunk, crops=crops, prepack=False)
+        # every rank can size every region: the capacity depends on the shard's widths only
+        self.caps = all_caps if all_caps is not None else [self._capacity(s) for s in self.shards]
+        self.name = name or f"sd_b200_gather_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}"
+        self.arena = G.ResultArena(self.name, self.caps, rank, create=True) if rank == 0 else None
+        self._sync()
+        if self.arena is None:
+            self.arena = G.ResultArena(self.name, self.caps, rank, create=False)
+        self.arena.register()
+        self.writer = G.RegionWriter(self.arena.region(rank), max(len(self.job.chunks), 1))
+
+    @staticmethod
+    def shard_of(widths, rank: int, world: int):
+        """Global indices of the lines of `rank` (sorted), before the job exists."""
+        return shard_lines([int(w) for w in widths], world)[rank]
+
+    def _capacity(self, idx) -> int:
+        w = [self.widths[i] for i in idx]
+        tiles = sum(n_tiles_for_width(x) for x in w)
+        px = sum(TILE_H * ((x + 127) // 128 * 128) for x in w)
+        return G.region_capacity(tiles, len(w), px, max((len(w) + self.lines_per_chunk - 1) // self.lines_per_chunk, 1))
+
+    def _sync(self):
+        if self.world > 1 and self.barrier is not None:
+            self.barrier()
+
+    def step(self):
+        """Runs this rank's shard; returns (this rank's chunk results, GatheredResults on rank 0 / None elsewhere).
+        The gathered views stay valid until the next `step` (call `release()` when done reading)."""
+        res = self.job.host_step(self.writer)            # ends with a stream synchronize: this rank's bytes are in the arena
+        self._sync()
+        got = None
+        if self.rank == 0:
+            got = G.GatheredResults(self.arena, self.shards, self.widths, self.lines_per_chunk, step=self.writer.step)
+        return res, got
+
+    def release(self):
+        """Readers are done: the next step may reuse the arena."""
+        self._sync()
+
+    def close(self):
+        self.arena.close()

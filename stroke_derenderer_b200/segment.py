@@ -70,11 +70,14 @@ def plan_batch(widths, device, tile_w=TILE_W, overlap=64) -> LineBatch:
     return LineBatch(torch.device(device), lines, plan, d_lines, [int(w) for w in widths])
 
 
-def resized_width(img, height: int = TILE_H) -> int:
+def resized_width_hw(h: int, w: int, height: int = TILE_H) -> int:
     """Line width after resize_to_height (common.py:89-91): int(w * (height / h)); w itself at h == height,
     where cv2.resize is a copy."""
-    h, w = img.shape[0], img.shape[1]
     return int(w) if h == height else int(w * (height / h))
+
+
+def resized_width(img, height: int = TILE_H) -> int:
+    return resized_width_hw(img.shape[0], img.shape[1], height)
 
 
 def pack_lines_rgb(images, batch: LineBatch, pinned: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:

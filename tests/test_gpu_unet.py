@@ -302,3 +302,44 @@ def test_main_cli_dropin(cuda_device, parity_state, tmp_path):
                 assert p["translate1"] == [int(w["translate1"][0]), int(w["translate1"][1])] and p["ratio"] == float(w["ratio"])
     finally:
         sessions[1].close()
+
+
+def test_main_cli_sharded_two_processes(cuda_device, parity_state, tmp_path):
+    """The multi-GPU form of the CLI: `torchrun --nproc-per-node 2 main.py ...` (two rank processes; on a one-GPU box both
+    use cuda:0).  Lines are dealt to the ranks, results come back through the shared-memory gather arena, rank 0 writes
+    the files: they must equal what the single-process CLI writes."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    import cv2
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root))
+    import main as cli
+    from onnx_writer import write_onnx as _write_onnx
+    models, inp, out1, out2 = tmp_path / "models", tmp_path / "in", tmp_path / "out1", tmp_path / "out2"
+    models.mkdir(); inp.mkdir()
+    _write_onnx(models / "binarizer.onnx", parity_state, folded=True)
+    (models / "configs_binarizer.json").write_text(json.dumps({"bin_thr": 0.5, "lines_per_chunk": 2, "max_tiles": 16}))
+    widths = [900, 400, 1700, 2600, 640, 3100, 1234]
+    for i, w in enumerate(widths):
+        cv2.imwrite(str(inp / f"line{i:02d}.png"), cv2.cvtColor(synth_line(w, 600 + i), cv2.COLOR_RGB2BGR))
+    sessions = cli.initialize_sessions(str(models))
+    try:
+        cli.main(cli.load_images(sorted(str(p) for p in inp.glob("*.png"))), *sessions, str(out1), strokes=True)
+    finally:
+        sessions[1].close()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(root / "main.py"), "-models", str(models), "-input", str(inp), "--output", str(out2)],
+                       capture_output=True, text=True, timeout=900, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-3000:]
+    names = sorted(p.name for p in out1.iterdir())
+    assert names == sorted(p.name for p in out2.iterdir()) and len(names) == 2 * len(widths)
+    for n in names:
+        if n.endswith(".png"):
+            assert np.array_equal(cv2.imread(str(out1 / n), cv2.IMREAD_UNCHANGED), cv2.imread(str(out2 / n), cv2.IMREAD_UNCHANGED)), n
+        else:
+            assert json.loads((out1 / n).read_text()) == json.loads((out2 / n).read_text()), n
