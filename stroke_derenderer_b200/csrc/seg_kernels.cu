@@ -1,10 +1,11 @@
 // Bandwidth-bound stages of the segmentation path: tile extraction (K1), glue +
-// threshold (K6), connected-component labelling with OpenCV-identical numbering
-// (K7), island stats (K8), group canvases (K9), plus the host-side planners.
+// threshold (K6, legacy API: the product path glues in the UNet head), connected-component labelling with
+// OpenCV-identical numbering + island stats (K7 / K8, ccl_warp.cuh), group canvases (K9), 224x224 crops (K10),
+// general-height resize (K11), the stroke front end's encode post-process (K12), plus the host-side planners.
 //
 // Data layout in HBM
 //   lines_rgb : packed (128, W, 3) u8 images at sd_line.img_off
-//   planes    : packed (128, pitch) planes at sd_line.px_off, pitch = round_up(W,16);
+//   planes    : packed (128, pitch) planes at sd_line.px_off, pitch = round_up(W,128);
 //               mask planes are u8, label planes int32 (same element offsets).
 //               Every row therefore starts 16-byte aligned and a thread moves
 //               16 pixels with one 128-bit access.
@@ -244,465 +245,12 @@ __global__ void __launch_bounds__(64) glue_kernel(
 }
 
 // ---------------------------------------------------------------------------
-// K7: connected-component labelling with OpenCV's numbering, strip-resident.
-//
-// A line (128 x pitch, pitch % 128 == 0) is cut into strips of 128 x 128 px = 64 x 64 blocks of
-// 2x2 px.  Five launches, 6 B/px of traffic against the 5 B/px algorithmic minimum:
-//   1. ccl_strip_label_kernel  (CTA = strip): mask -> 1 bit/px in smem.  A thread owns 16 blocks of one
-//      block row as 32-bit masks; horizontal runs of linked blocks are found with bit arithmetic, so
-//      the union-find (shared memory, min-root unions, path compression) has one node per RUN and one
-//      union per (run, upper run) contact instead of one per block.  Per block a 16-bit record
-//      (local root << 4 | 2x2 occupancy) -> HBM (0.5 B/px).  Local roots that do not touch a
-//      neighbouring strip are final: their bits go to the root bitmap (plain stores, every strip owns
-//      its words).  Boundary-touching local roots register in a sparse global parent array and the
-//      strip's two boundary block columns (root index + pixel bits) are emitted for the merge.
-//   2. ccl_boundary_merge_kernel (thread = boundary block row): unions across strip boundaries on the
-//      sparse global parents (8-connectivity between the two pixel columns).
-//   3. ccl_boundary_mark_kernel: boundary roots that are still roots -> bitmap.
-//   4. ccl_line_scan_kernel (CTA = line): exclusive scan of the bitmap popcounts: label(root g) =
-//      1 + #roots of the line with index < g = OpenCV's label, because a component's root is its
-//      first 2x2 block in raster order.
-//   5. ccl_strip_write_kernel (CTA = strip): records -> final int32 labels, 512 B per warp store.
-// Block indices are global: line.blk_off + br * bw + bc.
+// K7 / K8 fused: connected-component labelling with OpenCV's numbering and the cv2 stats rows live
+// in ccl_warp.cuh (warp-per-strip run-level union-find; the strip-per-CTA kernels of round 1 are gone).
+// A line (128 x pitch, pitch % 128 == 0) is cut into strips of 128 x 128 px = 64 x 64 blocks of 2 x 2 px; block
+// indices are global: line.blk_off + br * bw + bc.
 // ---------------------------------------------------------------------------
 constexpr int kStripBlocks = 4096;
-constexpr uint32_t kEven = 0x55555555u;
-
-struct CclWork {
-  int* parent;          // [blk_total]   sparse: boundary-touching local roots only
-  uint16_t* rec;        // [blk_total]   (local root index << 4) | occupancy bits (p00, p01, p10, p11)
-  uint32_t* bitmap;     // [blk_total/32] bit = block is the root (first block) of a component
-  int* prefix;          // [blk_total/32] exclusive count of root bits before this word, per line
-  int* bnd_root;        // [strips][2][64] global index of the local root of each boundary block, -1 if none
-  uint32_t* bnd_bits;   // [strips][2][4]  pixel column 0 / 127 of the strip, 128 rows
-  void* strip_tab;      // [strips] StripInfo
-};
-
-__device__ __forceinline__ uint32_t nzflags(uint32_t w) {   // 0x80 in every non-zero byte
-  return (w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t nz16(uint4 v) {   // bit k = byte k non-zero
-  const uint32_t lo = __dp4a(nzflags(v.x), 0x08040201u, __dp4a(nzflags(v.y), 0x80402010u, 0u));   // 128 * bits 0..7
-  const uint32_t hi = __dp4a(nzflags(v.z), 0x08040201u, __dp4a(nzflags(v.w), 0x80402010u, 0u));
-  return (lo | (hi << 8)) >> 7;
-}
-
-// warp-cooperative line lookup: #lines whose block offset is <= off, minus one (lines are sorted)
-__device__ __forceinline__ int find_line_warp(const sd_line* __restrict__ L, int n, int64_t off, int lane) {
-  int cnt = 0;
-  for (int i = lane; i < n; i += 32) cnt += (L[i].blk_off <= off) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  return cnt - 1;
-}
-
-// global union-find on the sparse parents (min-root).  .cg loads: other CTAs' threads re-parent
-// nodes concurrently; a stale value would still be an ancestor, fresh ones shorten the walk.
-__device__ __forceinline__ int uf_find(const int* __restrict__ parent, int a) {
-  int p = __ldcg(parent + a);
-  while (p != a) { a = p; p = __ldcg(parent + a); }
-  return a;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { int t = a; a = b; b = t; }       // a > b: hang a under b
-    int old = atomicMin(&parent[a], b);
-    if (old == a) return;
-    a = old;                                      // somebody re-parented a meanwhile; retry
-  }
-}
-
-// shared-memory union-find over run starts (min-root: parents are smaller than their children, a union
-// completes only when its atomicMin hit a true root).  NO path compression while unions are in flight: a
-// compressing plain store can race with the atomicMin of a union that targets the same node through a stale
-// root and silently drop that link (seen as a split component in ~25 % of runs on some strips).  Paths are
-// compressed afterwards, once every root is final (suf_find_flatten).
-__device__ __forceinline__ int suf_find(volatile int* p, int a) {
-  int q;
-  while ((q = p[a]) != a) a = q;
-  return a;
-}
-__device__ __forceinline__ int suf_find_flatten(volatile int* p, int a) {   // only after the union phase
-  int r = a, q;
-  while ((q = p[r]) != r) r = q;
-  while (a > r) { q = p[a]; p[a] = r; a = q; }
-  return r;
-}
-__device__ __forceinline__ void suf_union(int* p, int a, int b) {
-  while (true) {
-    a = suf_find(p, a);
-    b = suf_find(p, b);
-    if (a == b) return;
-    if (a < b) { int t = a; a = b; b = t; }
-    int old = atomicMin(&p[a], b);
-    if (old == a) return;
-    a = old;
-  }
-}
-
-// index (0..15) of the run start that owns block k: highest run-start bit at or below bit 2k
-__device__ __forceinline__ int run_start(uint32_t rs2, int k) {
-  return (31 - __clz(rs2 & ((2u << (2 * k)) - 1u))) >> 1;
-}
-
-// one per strip, built on the device from the line table (no per-CTA search, one 32-byte load)
-struct __align__(16) StripInfo {
-  int64_t px0;          // element offset of the strip's top-left pixel in the packed planes
-  int32_t pitch, bw;
-  int32_t blk_base;     // line.blk_off + s * 64: global index of the strip's block (0, 0)
-  int32_t s, ns, line;
-};
-
-__global__ void __launch_bounds__(128) ccl_strip_table_kernel(const sd_line* __restrict__ L, StripInfo* __restrict__ tab) {
-  const sd_line ln = L[blockIdx.x];
-  const int ns = ln.bw >> 6;
-  const int64_t first = ln.blk_off >> 12;
-  for (int s = threadIdx.x; s < ns; s += blockDim.x) {
-    StripInfo t;
-    t.px0 = ln.px_off + s * 128; t.pitch = ln.pitch; t.bw = ln.bw;
-    t.blk_base = (int)ln.blk_off + s * 64; t.s = s; t.ns = ns; t.line = blockIdx.x;
-    tab[first + s] = t;
-  }
-}
-
-__device__ __forceinline__ StripInfo load_strip(const StripInfo* __restrict__ tab, int i) {
-  const uint4* p = reinterpret_cast<const uint4*>(tab + i);
-  const uint4 a = __ldg(p), b = __ldg(p + 1);
-  StripInfo t;
-  t.px0 = (int64_t)(((uint64_t)a.y << 32) | a.x); t.pitch = (int)a.z; t.bw = (int)a.w;
-  t.blk_base = (int)b.x; t.s = (int)b.y; t.ns = (int)b.z; t.line = (int)b.w;
-  return t;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-
-// pair k (bits 2k, 2k+1) of x -> bits 4k, 4k+1
-__device__ __forceinline__ uint64_t spread_pairs(uint32_t x) {
-  uint64_t v = x;
-  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
-  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
-  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
-  v = (v | (v << 2)) & 0x3333333333333333ull;
-  return v;
-}
-
-// Persistent: a CTA walks strips blockIdx.x, += gridDim.x; the next strip's mask bytes stream into a
-// staging buffer with cp.async while the current strip is labelled.
-__global__ void __launch_bounds__(256) ccl_strip_label_kernel(
-    const uint8_t* __restrict__ mask, const StripInfo* __restrict__ tab, int n_strips, CclWork w) {
-  __shared__ __align__(16) uint8_t s_stage[128 * 128];   // raw mask bytes of the strip being converted
-  __shared__ uint32_t s_bits[131][4];                 // [2 + r] = pixel row r; rows -2, -1 are empty
-  __shared__ int s_parent[kStripBlocks];              // only run starts are live
-  __shared__ uint32_t s_rs[64][4];                    // run-start masks (bit 2k = block k of the thread starts a run)
-  __shared__ uint32_t s_touch[kStripBlocks / 32];     // local roots that touch a neighbouring strip
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  int strip = blockIdx.x;
-  if (strip >= n_strips) return;
-  auto fetch = [&](const StripInfo& si) {             // a warp instruction moves 4 rows x 128 B
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int row = it * 32 + wp * 4 + (lane >> 3);
-      cp_async16(s_stage + row * 128 + (lane & 7) * 16, mask + si.px0 + (int64_t)row * si.pitch + (lane & 7) * 16);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  StripInfo cur = load_strip(tab, strip);
-  fetch(cur);
-  int nxt = strip + gridDim.x;
-  StripInfo ninfo = cur;
-  if (nxt < n_strips) ninfo = load_strip(tab, nxt);
-  if (tid < 8) s_bits[tid >> 2][tid & 3] = 0u;
-  const int br = tid >> 2, q = tid & 3;
-  const int base = br * 64 + q * 16;
-
-  while (true) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int row = it * 32 + wp * 4 + (lane >> 3);
-      const uint4 v = *reinterpret_cast<const uint4*>(s_stage + row * 128 + (lane & 7) * 16);
-      const uint32_t nz = nz16(v);
-      const uint32_t other = __shfl_xor_sync(0xffffffffu, nz, 1);
-      if (!(lane & 1)) s_bits[row + 2][(lane & 7) >> 1] = nz | (other << 16);
-    }
-    if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
-    __syncthreads();
-    const bool has_next = nxt < n_strips;
-    if (has_next) fetch(ninfo);                       // staging is free again
-    const int nn = nxt + gridDim.x;
-    StripInfo nninfo = ninfo;
-    if (nn < n_strips) nninfo = load_strip(tab, nn);
-
-    // thread = 16 horizontally adjacent blocks of one block row = one 32-bit word of each pixel row.
-    // Windows: bit (1 + c) = pixel column c of the word, bit 0 = the pixel left of it, bit 33 = right of it.
-    auto window = [&](int i) -> uint64_t {
-      uint64_t v = (uint64_t)s_bits[i][q] << 1;
-      if (q > 0) v |= s_bits[i][q - 1] >> 31;
-      if (q < 3) v |= (uint64_t)(s_bits[i][q + 1] & 1u) << 33;
-      return v;
-    };
-    const uint64_t UUw = window(2 * br), Uw = window(2 * br + 1), Tw = window(2 * br + 2), Bw = window(2 * br + 3);
-    const uint64_t Pw = Tw | Bw, PUw = UUw | Uw;
-    // even-bit domain: bit 2k <-> block k of this thread
-    const uint32_t P1 = (uint32_t)(Pw >> 1);
-    const uint32_t occ2 = (P1 | (P1 >> 1)) & kEven;                      // block k has a pixel
-    const uint32_t hl2 = (uint32_t)(Pw & (Pw >> 1)) & kEven;             // block k touches block k-1 (8-conn)
-    const uint32_t hlU2 = (uint32_t)(PUw & (PUw >> 1)) & kEven;          // same for the block row above
-    const uint32_t rs2 = occ2 & ~(hl2 & ~1u);                            // run starts inside the thread
-    s_rs[br][q] = rs2;
-    for (uint32_t t = rs2; t; t &= t - 1) {
-      const int k = (__ffs(t) - 1) >> 1;
-      s_parent[base + k] = base + k;
-    }
-    // contacts with the block row above (Uw == 0 for br == 0)
-    uint32_t vu, vl, vr;
-    {
-      const uint32_t T0 = (uint32_t)(Tw >> 1) & kEven, T1 = (uint32_t)(Tw >> 2) & kEven;
-      const uint32_t U0 = (uint32_t)(Uw >> 1) & kEven, U1 = (uint32_t)(Uw >> 2) & kEven;
-      const uint32_t UL = (uint32_t)Uw & kEven, UR = (uint32_t)(Uw >> 3) & kEven;
-      const uint32_t vu0 = (T0 | T1) & (U0 | U1);     // block k - upper block k
-      vl = T0 & UL;                                   // block k - upper block k-1
-      vr = T1 & UR;                                   // block k - upper block k+1
-      // drop contacts that join the same (run, upper run) pair as a neighbouring contact
-      vl &= ~(vu0 & hlU2) & ~((vu0 << 2) & hl2);
-      vr &= ~(vu0 & (hlU2 >> 2)) & ~((vu0 >> 2) & (hl2 >> 2));
-      vu = vu0 & ~((vu0 << 2) & hl2 & hlU2);
-    }
-    __syncthreads();
-
-    // One loop over all contacts of the thread (a single copy of the union code, so the lanes of a warp
-    // run it together): bit 2k = up, bit 2k+1 = up-left, bit 32+2k = up-right of block k.
-    if (hl2 & 1u)                                     // run continues from the thread on the left
-      suf_union(s_parent, base, base - 16 + ((31 - __clz(s_rs[br][q - 1])) >> 1));
-    for (uint64_t t = (uint64_t)(vu | (vl << 1)) | ((uint64_t)vr << 32); t; t &= t - 1) {
-      const int b = __ffsll((long long)t) - 1;
-      const int k = (b & 31) >> 1;
-      const int kp = k + (b >= 32 ? 1 : -(b & 1));
-      int qq = q, kk = kp;
-      if (kp < 0) { qq = q - 1; kk = 15; } else if (kp > 15) { qq = q + 1; kk = 0; }
-      const int up = run_start(s_rs[br - 1][qq], kk);
-      suf_union(s_parent, base + run_start(rs2, k), base - 64 + (qq - q) * 16 + up);
-    }
-    __syncthreads();
-    // flatten: afterwards s_parent[run start] is the run's root
-    for (uint32_t t = rs2; t; t &= t - 1) suf_find_flatten(s_parent, base + ((__ffs(t) - 1) >> 1));
-
-    // records: every block of a run carries the run's root
-    uint32_t recw[8];
-    int r_first = 0, r_last = 0;
-    {
-      const uint64_t nib = spread_pairs((uint32_t)(Tw >> 1)) | (spread_pairs((uint32_t)(Bw >> 1)) << 2);   // nibble k = 2x2 occupancy
-      volatile int* vp = s_parent;
-      int root = 0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        if ((rs2 >> (2 * k)) & 1u) root = vp[base + k];
-        const uint32_t occ4 = (uint32_t)(nib >> (4 * k)) & 15u;
-        const uint32_t rc = occ4 ? (((uint32_t)root << 4) | occ4) : 0u;
-        if (k == 0) r_first = root;
-        if (k == 15) r_last = root;
-        if (k & 1) recw[k >> 1] |= rc << 16; else recw[k >> 1] = rc;
-      }
-    }
-    const int blk_off = cur.blk_base - cur.s * 64;    // the line's block offset
-    {
-      uint4* rp = reinterpret_cast<uint4*>(w.rec + cur.blk_base + (int64_t)br * cur.bw + q * 16);
-      rp[0] = make_uint4(recw[0], recw[1], recw[2], recw[3]);
-      rp[1] = make_uint4(recw[4], recw[5], recw[6], recw[7]);
-    }
-    const int gbase = cur.blk_base;                   // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
-    if (q == 0) {
-      const bool on = cur.s > 0 && (occ2 & 1u);
-      if (on) atomicOr(&s_touch[r_first >> 5], 1u << (r_first & 31));
-      w.bnd_root[((int64_t)strip * 2 + 0) * 64 + br] = on ? gbase + (r_first >> 6) * cur.bw + (r_first & 63) : -1;
-    }
-    if (q == 3) {
-      const bool on = cur.s < cur.ns - 1 && ((occ2 >> 30) & 1u);
-      if (on) atomicOr(&s_touch[r_last >> 5], 1u << (r_last & 31));
-      w.bnd_root[((int64_t)strip * 2 + 1) * 64 + br] = on ? gbase + (r_last >> 6) * cur.bw + (r_last & 63) : -1;
-    }
-    if (tid < 128) {
-      const uint32_t m0 = __ballot_sync(0xffffffffu, s_bits[tid + 2][0] & 1u);
-      const uint32_t m1 = __ballot_sync(0xffffffffu, s_bits[tid + 2][3] >> 31);
-      if (lane == 0) {
-        w.bnd_bits[((int64_t)strip * 2 + 0) * 4 + wp] = m0;
-        w.bnd_bits[((int64_t)strip * 2 + 1) * 4 + wp] = m1;
-      }
-    }
-    __syncthreads();
-
-    // roots: interior ones are final -> bitmap; boundary-touching ones register in the global parents
-    uint32_t rootbits = 0;
-    {
-      volatile int* vp = s_parent;
-      for (uint32_t t = rs2; t; t &= t - 1) {
-        const int k = (__ffs(t) - 1) >> 1;
-        const int idx = base + k;
-        if (vp[idx] == idx) {
-          if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) {
-            const int g = gbase + br * cur.bw + q * 16 + k;
-            w.parent[g] = g;
-          } else {
-            rootbits |= 1u << k;
-          }
-        }
-      }
-    }
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, rootbits, 1);
-    if (!(q & 1)) w.bitmap[(blk_off >> 5) + (int64_t)br * (cur.bw >> 5) + cur.s * 2 + (q >> 1)] = rootbits | (other << 16);
-    if (!has_next) break;
-    cur = ninfo; ninfo = nninfo; strip = nxt; nxt = nn;
-  }
-}
-
-__device__ __forceinline__ uint32_t col_bit(const uint32_t* __restrict__ p, int r) { return (p[r >> 5] >> (r & 31)) & 1u; }
-
-// thread = one block row of one strip boundary: pixel column 127 of strip sg-1 against pixel column 0 of strip sg
-__global__ void __launch_bounds__(256) ccl_boundary_merge_kernel(CclWork w, int n_strips) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_strips * 64) return;
-  const int sg = i >> 6, br = i & 63;
-  if (sg == 0) return;
-  const int a = w.bnd_root[((int64_t)(sg - 1) * 2 + 1) * 64 + br];
-  if (a < 0) return;                                  // empty, or strip sg-1 is the last strip of its line
-  const int* Rr = w.bnd_root + ((int64_t)sg * 2 + 0) * 64;
-  const uint32_t* Lb = w.bnd_bits + ((int64_t)(sg - 1) * 2 + 1) * 4;
-  const uint32_t* Rb = w.bnd_bits + ((int64_t)sg * 2 + 0) * 4;
-  const uint32_t a0 = col_bit(Lb, 2 * br), a1 = col_bit(Lb, 2 * br + 1);
-  const uint32_t c0 = col_bit(Rb, 2 * br), c1 = col_bit(Rb, 2 * br + 1);
-  if ((a0 | a1) & (c0 | c1)) uf_union(w.parent, a, Rr[br]);
-  if (br > 0 && a0 && col_bit(Rb, 2 * br - 1)) uf_union(w.parent, a, Rr[br - 1]);
-  if (br < 63 && a1 && col_bit(Rb, 2 * br + 2)) uf_union(w.parent, a, Rr[br + 1]);
-}
-
-// boundary-touching local roots that are still roots after the merge are component roots
-__global__ void __launch_bounds__(256) ccl_boundary_mark_kernel(CclWork w, int n_strips) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_strips * 128) return;
-  const int k = w.bnd_root[i];
-  if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
-}
-
-// exclusive scan of the root counts per bitmap word of one line (64 * bw / 32 words, a multiple of 128)
-__global__ void __launch_bounds__(1024) ccl_line_scan_kernel(
-    const sd_line* __restrict__ L, CclWork w, int* __restrict__ num_out) {
-  const int l = blockIdx.x, tid = threadIdx.x;
-  const sd_line ln = L[l];
-  const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
-  int* prefix = w.prefix + (ln.blk_off >> 5);
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
-  const int words = 2 * ln.bw;
-  for (int c = 0; c < words; c += blockDim.x * 4) {
-    const int i = c + tid * 4;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (i < words) v = __ldcg(reinterpret_cast<const uint4*>(bitmap + i));
-    const int n0 = __popc(v.x), n1 = __popc(v.y), n2 = __popc(v.z), n3 = __popc(v.w);
-    const int tot = n0 + n1 + n2 + n3;
-    int inc = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((tid & 31) >= o) inc += t;
-    }
-    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
-    __syncthreads();
-    int wv = (tid < 32) ? s_warp[tid] : 0;            // warp 0 scans the 32 warp totals
-    if (tid < 32) {
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, wv, o);
-        if (tid >= o) wv += t;
-      }
-    }
-    const int carry = s_carry;
-    __syncthreads();
-    if (tid < 32) s_warp[tid] = wv;                   // inclusive warp totals
-    __syncthreads();
-    const int woff = (tid >> 5) ? s_warp[(tid >> 5) - 1] : 0;
-    const int ex = carry + woff + inc - tot;
-    if (i < words) *reinterpret_cast<int4*>(prefix + i) = make_int4(ex, ex + n0, ex + n0 + n1, ex + n0 + n1 + n2);
-    if (tid == blockDim.x - 1) s_carry = carry + woff + inc;
-    __syncthreads();
-  }
-  if (tid == 0) num_out[l] = s_carry + 1;             // cv2 counts the background label
-}
-
-__global__ void __launch_bounds__(256) ccl_strip_write_kernel(
-    const sd_line* __restrict__ L, int n_lines, CclWork w, int* __restrict__ labels) {
-  __shared__ __align__(16) uint16_t s_rec[kStripBlocks];
-  __shared__ int s_lab[kStripBlocks];
-  __shared__ uint32_t s_touch[kStripBlocks / 32];
-  __shared__ int s_l;
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  const int64_t blk0 = (int64_t)blockIdx.x * kStripBlocks;
-  if (wp == 0) {
-    const int l = find_line_warp(L, n_lines, blk0, lane);
-    if (lane == 0) s_l = l;
-  }
-  if (tid < kStripBlocks / 32) s_touch[tid] = 0u;
-  __syncthreads();
-  const sd_line ln = L[s_l];
-  const int ns = ln.bw >> 6;
-  const int s = (int)((blk0 - ln.blk_off) >> 12);
-  const int br = tid >> 2, q = tid & 3;
-  const int base = br * 64 + q * 16;
-  uint4 ra, rb;
-  {
-    const uint4* rp = reinterpret_cast<const uint4*>(w.rec + ln.blk_off + (int64_t)br * ln.bw + s * 64 + q * 16);
-    ra = __ldcs(rp); rb = __ldcs(rp + 1);
-    reinterpret_cast<uint4*>(s_rec + base)[0] = ra;
-    reinterpret_cast<uint4*>(s_rec + base)[1] = rb;
-  }
-  __syncthreads();
-  if (tid < 64) {
-    const uint32_t rc = s_rec[tid * 64];
-    if (s > 0 && (rc & 15u)) atomicOr(&s_touch[rc >> 9], 1u << ((rc >> 4) & 31));
-  } else if (tid < 128) {
-    const uint32_t rc = s_rec[(tid - 64) * 64 + 63];
-    if (s < ns - 1 && (rc & 15u)) atomicOr(&s_touch[rc >> 9], 1u << ((rc >> 4) & 31));
-  }
-  __syncthreads();
-  {
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    const int gbase = (int)ln.blk_off + s * 64;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const uint32_t rc = (rw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-      const int idx = base + k;
-      if ((rc & 15u) && (int)(rc >> 4) == idx) {
-        int g = gbase + br * ln.bw + q * 16 + k;
-        if ((s_touch[idx >> 5] >> (idx & 31)) & 1u) g = uf_find(w.parent, g);
-        s_lab[idx] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
-      }
-    }
-  }
-  __syncthreads();
-  int* out = labels + ln.px_off + s * 128 + lane * 4;
-  const uint32_t* rec2 = reinterpret_cast<const uint32_t*>(s_rec);
-#pragma unroll 4
-  for (int it = 0; it < 16; ++it) {                   // a warp instruction writes one 512-B row segment
-    const int row = wp * 16 + it;
-    const uint32_t two = rec2[(row >> 1) * 32 + lane];
-    const uint32_t rc0 = two & 0xFFFFu, rc1 = two >> 16;
-    const int l0 = (rc0 & 15u) ? s_lab[rc0 >> 4] : 0, l1 = (rc1 & 15u) ? s_lab[rc1 >> 4] : 0;
-    const int sh = (row & 1) * 2;
-    int4 o;
-    o.x = ((rc0 >> sh) & 1u) ? l0 : 0; o.y = ((rc0 >> (sh + 1)) & 1u) ? l0 : 0;
-    o.z = ((rc1 >> sh) & 1u) ? l1 : 0; o.w = ((rc1 >> (sh + 1)) & 1u) ? l1 : 0;
-    __stcs(reinterpret_cast<int4*>(out + (int64_t)row * ln.pitch), o);
-  }
-}
-
 }  // namespace sd
 #include "ccl_warp.cuh"
 namespace sd {
@@ -1260,42 +808,7 @@ extern "C" int sd_glue_threshold_f16(const void* d_prob, int n_tiles, const sd_l
 
 namespace sd {
 static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-// carves the CCL workspace; returns the bytes used
-static size_t ccl_carve(void* base, int64_t blk_total, CclWork* w) {
-  const size_t strips = (size_t)(blk_total / kStripBlocks);
-  size_t off = 0;
-  char* p = reinterpret_cast<char*>(base);
-  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += up256(bytes); return r; };
-  int* parent = reinterpret_cast<int*>(take((size_t)blk_total * 4));
-  uint16_t* rec = reinterpret_cast<uint16_t*>(take((size_t)blk_total * 2));
-  uint32_t* bitmap = reinterpret_cast<uint32_t*>(take((size_t)blk_total / 32 * 4));
-  int* prefix = reinterpret_cast<int*>(take((size_t)blk_total / 32 * 4));
-  int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
-  uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
-  void* strip_tab = take(strips * 32);
-  if (w) { w->strip_tab = strip_tab; w->parent = parent; w->rec = rec; w->bitmap = bitmap; w->prefix = prefix; w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; }
-  return off;
-}
-}  // namespace sd
-
-namespace sd {
-// persistent label kernel: as many CTAs as fit on the device at once
-static int ccl_label_grid() {
-  static int grid = 0;
-  if (!grid) {
-    int dev = 0, sms = 148, per_sm = 4;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_strip_label_kernel, 256, 0);
-    grid = sms * (per_sm > 0 ? per_sm : 1);
-    if (const char* g = getenv("SD_CCL_GRID")) grid = std::max(atoi(g), 1);   // debug: e.g. a huge value = one strip per CTA
-  }
-  return grid;
-}
-}  // namespace sd
-
-namespace sd {
-// second-generation workspace (ccl_warp.cuh)
+// CCL workspace (ccl_warp.cuh)
 static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
   const size_t strips = (size_t)(blk_total / kStripBlocks);
   size_t off = 0;
@@ -1313,11 +826,6 @@ static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
   if (w) { w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots;
            w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; w->ticket = ticket; }
   return off;
-}
-
-static int ccl_env(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
 }
 
 // label (+ stats) with the warp-per-strip kernels
@@ -1359,7 +867,7 @@ static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lin
 
 extern "C" size_t sd_ccl_workspace_bytes(int64_t blk_total, int n_lines) {
   (void)n_lines;
-  return std::max(ccl_carve(nullptr, blk_total, nullptr), ccl_warp_carve(nullptr, blk_total, nullptr)) + 256;
+  return ccl_warp_carve(nullptr, blk_total, nullptr) + 256;
 }
 
 extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,
@@ -1369,25 +877,7 @@ extern "C" int sd_ccl_label(const uint8_t* d_mask, const sd_line* d_lines, int n
              "sd_ccl_label: bad totals");
   SD_REQUIRE(((uintptr_t)d_mask & 15) == 0 && ((uintptr_t)d_labels & 15) == 0, "sd_ccl_label: planes must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  if (ccl_env("SD_CCL_V1", 0) == 0)
-    return ccl_warp_run(d_mask, d_lines, n_lines, blk_total, d_labels, d_num, nullptr, nullptr, 0, d_work, s);
-  CclWork w;
-  ccl_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
-  const int strips = (int)(blk_total / kStripBlocks);
-  ccl_strip_table_kernel<<<n_lines, 128, 0, s>>>(d_lines, reinterpret_cast<StripInfo*>(w.strip_tab));
-  SD_LAUNCH_CHECK("ccl_strip_table_kernel");
-  ccl_strip_label_kernel<<<std::min(strips, ccl_label_grid()), 256, 0, s>>>(
-      d_mask, reinterpret_cast<const StripInfo*>(w.strip_tab), strips, w);
-  SD_LAUNCH_CHECK("ccl_strip_label_kernel");
-  ccl_boundary_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
-  SD_LAUNCH_CHECK("ccl_boundary_merge_kernel");
-  ccl_boundary_mark_kernel<<<ceil_div((int64_t)strips * 128, 256), 256, 0, s>>>(w, strips);
-  SD_LAUNCH_CHECK("ccl_boundary_mark_kernel");
-  ccl_line_scan_kernel<<<n_lines, 1024, 0, s>>>(d_lines, w, d_num);
-  SD_LAUNCH_CHECK("ccl_line_scan_kernel");
-  ccl_strip_write_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels);
-  SD_LAUNCH_CHECK("ccl_strip_write_kernel");
-  return SD_OK;
+  return ccl_warp_run(d_mask, d_lines, n_lines, blk_total, d_labels, d_num, nullptr, nullptr, 0, d_work, s);
 }
 
 extern "C" int sd_ccl_label_stats(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t px_total,

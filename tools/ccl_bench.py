@@ -1,5 +1,5 @@
 """CCL timing / profiling target: the 128-line text sample of bench.py's hbm_stages and 64 dense config-5 lines.
-Without a profiler: CUDA-event times of sd_ccl_label and sd_ccl_label_stats.  Under ncu only the region between
+Without a profiler: CUDA-event times of sd_ccl_label and sd_ccl_label_stats (round 1's kernels, removed since, took 0.227 / 0.259 ms on the same two samples).  Under ncu only the region between
 cudaProfilerStart/Stop is captured (one call per workload):
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv python tools/ccl_bench.py
 """
@@ -48,13 +48,9 @@ def main():
         work = torch.empty(_lib.lib().sd_ccl_workspace_bytes(batch.blk_total, batch.n_lines), dtype=torch.uint8, device=dev)
         cap = max(S.stats_capacity(batch), 2_000_000 if name == "dense" else 0)
         px = 128 * int(sum(m.shape[1] for m in masks))
-        import os
-        os.environ["SD_CCL_V1"] = "1"
-        t1 = ev(lambda: S.ccl_label(batch, planes, work))
-        os.environ["SD_CCL_V1"] = "0"
         t = ev(lambda: S.ccl_label(batch, planes, work))
         ts = ev(lambda: S.ccl_label_stats(batch, planes, cap, work))
-        out[name] = {"px": px, "label_v1_ms": t1, "label_ms": t, "label_frac": 5 * px / t / 1e6 / 6451.5, "label_stats_ms": ts,
+        out[name] = {"px": px, "label_ms": t, "label_frac": 5 * px / t / 1e6 / 6451.5, "label_stats_ms": ts,
                      "label_stats_frac": 5 * px / ts / 1e6 / 6451.5}
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
