@@ -382,7 +382,7 @@ def run_gpu(args):
                "sample": desc + "; reference Python algorithm + torch-CPU fp32 stand-in for onnxruntime-CPU (absent offline)"}
 
     api = fused_api = parity = None
-    if rank == 0 and not args.no_api:
+    if rank == 0 and world == 1 and not args.no_api:     # like cpu_baseline: a single-GPU figure, measured at N = 1 only
         # The reference-signature calls on plain (unpinned) numpy lists, rank 0's lines on its GPU:
         #   masks = BinarizationSession.binarize_images(images, ort)      evaluate_binarize.py:130-140
         #   img_bin = mask[:, :, 0] > 255 * bin_thr                       main.py:108

@@ -282,11 +282,12 @@ class LineSegmentationJob:
             left, top = groups[:, 1], groups[:, 2]
             ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
         LP = S.LazyPartition
+        have_crops = img_host is not None and len(groups) > 0
         for k, ln in enumerate(ch.batch.lines):
             off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
             masks.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
             parts.append([LP(lut, image=img_host[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
-                          for g in range(int(lgs[k]), int(lgs[k + 1]))])
+                          for g in range(int(lgs[k]), int(lgs[k + 1]))] if have_crops else [])
         return masks, parts
 
     def line_outputs(self, results, copy: bool = True, mean=None, std=None):
