@@ -397,6 +397,12 @@ class LazyPartition(dict):
         super().__init__(**kw)
         self._lut = lut
 
+    def __contains__(self, key):
+        return key == "image_input" or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
     def __missing__(self, key):
         if key != "image_input":
             raise KeyError(key)
