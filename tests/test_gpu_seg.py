@@ -474,3 +474,30 @@ def test_stroke_front_end_encode_postprocess_and_batching(cuda_device):
             assert np.allclose(e.cpu().numpy(), want, rtol=1e-4, atol=1e-5) and e.shape[1:] == (196, 16)
     with pytest.raises(NotImplementedError):
         se.load_orts({"encoder": "models/encoder.onnx"})
+
+
+def test_stroke_encoder_handle_vs_torch_fp32(cuda_device):
+    """The library-path encoder handle (stride-32 ResNet trunk, recalled topology, seeded weights; cuDNN fp16
+    channels-last) against the same module in torch-CPU fp32, and through the batched front end.  UNPINNED: the
+    reference's encoder.onnx is a Drive file whose topology the tree does not name."""
+    from stroke_derenderer_b200.evaluate_strokes import StrokeEstimationSession
+    from stroke_derenderer_b200.stroke_encoder import EncoderHandle, seeded_trunk
+    ref_net = seeded_trunk(18, seed=7)
+    handle = EncoderHandle(seeded_trunk(18, seed=7), device=0, max_batch=8)
+    se = StrokeEstimationSession()
+    masks = [ink_mask(synth_line(w, seed=700 + i)) for i, w in enumerate([800, 1500])]
+    parts, encs = se.encode_partitions_batch(masks, se.load_orts({"encoder": handle}), max_batch=8)
+    n = sum(len(p) for p in parts)
+    assert n >= 8
+    x = np.stack([q["image_input"] for p in parts for q in p]).astype(np.float32)
+    with torch.no_grad():
+        want = ref_net(torch.from_numpy(x)).numpy()
+    got_raw = handle.run(["output"], {"input": x})[0]
+    assert got_raw.shape == want.shape == (n, 512, 7, 7)
+    rel = float(np.linalg.norm(got_raw - want) / np.linalg.norm(want))
+    print(f"[encoder handle] rel-L2 err vs torch fp32 {rel:.5f}")
+    assert rel < 1e-2
+    got = torch.cat([e for e in encs if e.shape[0]], 0).cpu().numpy()
+    want_pp = se._encode_postprocess(want)
+    assert got.shape == want_pp.shape == (n, 196, 512)
+    assert float(np.linalg.norm(got - want_pp) / np.linalg.norm(want_pp)) < 1e-2
