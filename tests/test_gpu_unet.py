@@ -343,3 +343,50 @@ def test_main_cli_sharded_two_processes(cuda_device, parity_state, tmp_path):
             assert np.array_equal(cv2.imread(str(out1 / n), cv2.IMREAD_UNCHANGED), cv2.imread(str(out2 / n), cv2.IMREAD_UNCHANGED)), n
         else:
             assert json.loads((out1 / n).read_text()) == json.loads((out2 / n).read_text()), n
+
+
+def test_edge_case_lines_through_the_public_calls(cuda_device, parity_state):
+    """Degenerate inputs through the pipelined public calls: no images, a line with no ink (no islands, no groups, no
+    crops), a 1-px-wide line, a line of another height, and a chunk that consists of empty lines only — through
+    binarize_images, segment_lines and the gather arena."""
+    import os
+    from oracle import segmentation_ref as O
+    from stroke_derenderer_b200 import gather as G
+    from stroke_derenderer_b200.evaluate_binarize import BinarizationSession
+    from stroke_derenderer_b200.pipeline import LineSegmentationJob, segment_lines
+    bs = BinarizationSession(max_tiles=16, lines_per_chunk=2)
+    e = bs.init_onnx_inference(parity_state)
+    try:
+        assert bs.binarize_images([], e) == []
+        white = np.full((128, 700, 3), 255, np.uint8)
+        lines = [white, white.copy(), synth_line(900, 811), np.full((128, 1, 3), 255, np.uint8), synth_line(500, 812, height=96), white[:, :40].copy()]
+        masks, parts = segment_lines(e, lines, lines_per_chunk=2)
+        assert len(masks) == len(parts) == len(lines)
+        ort = O.TorchOrtSession(parity_state)
+        ref_bs = O.BinarizationSessionRef()
+        for i, (m, p) in enumerate(zip(masks, parts)):
+            ref = ref_bs.binarize_image(lines[i], ort)
+            assert m.shape == ref.shape, (i, m.shape, ref.shape)
+            assert float((m == ref).mean()) >= 0.998, i
+            want = O.get_partitions((m[:, :, 0] > 127).astype(np.uint8))
+            assert len(p) == len(want), i
+            for a, b in zip(p, want):
+                assert np.array_equal(a["image"], b["image"]) and a["ratio"] == b["ratio"]
+        assert len(parts[2]) > 0
+        # the same lines through the gather arena
+        job = LineSegmentationJob(e, lines, lines_per_chunk=2, prepack=False)
+        widths = [m.shape[1] for m in masks]
+        arena = G.ResultArena(f"sd_test_edge_{os.getpid()}", [job.arena_bytes()], rank=0, create=True)
+        try:
+            arena.register()
+            wr = G.RegionWriter(arena.region(0), len(job.chunks))
+            job.host_step(wr)
+            got = G.GatheredResults(arena, [list(range(len(lines)))], widths, 2, step=1)
+            for i in range(len(lines)):
+                assert np.array_equal(got.mask(i), masks[i][:, :, 0]) and got.crops(i).shape[0] == len(parts[i]) == len(got.groups(i))
+                assert got.stats(i).shape[0] == got.num(i) - 1
+            del got
+        finally:
+            arena.close()
+    finally:
+        e.close()
