@@ -58,18 +58,29 @@ class StrokeEstimationSession:
     def get_partitions_batch(self, imgs_bin, lines_per_chunk: int = 64, keep_device: bool = False):
         """Many lines in one pipelined device pass: per chunk of lines one H2D of the packed masks, CCL, stats,
         clustering, canvases and the 224x224 crops (sd_group_crops: cv2.normalize / cv2.resize / pad bit for bit),
-        one D2H of the u8 crops.  -> per line the list of partition dicts of :213-219; `image_input` is built on
-        first access (segment.LazyPartition), or stays on the GPU for the stroke-estimator front end
-        (`keep_device=True` adds `self.last_device_crops`: per chunk the (g, 3, size, size) f32 tensor)."""
+        one D2H of the u8 crops straight into the page-locked arrays that are returned (no second host copy).
+        Two host lanes (a thread + a CUDA stream each) take alternate chunks, so packing / H2D / kernels / D2H of
+        chunk k+1 run while the caller's thread builds the partition dicts of chunk k.
+        -> per line the list of partition dicts of :213-219; `image_input` is built on first access
+        (segment.LazyPartition), or stays on the GPU for the stroke-estimator front end (`keep_device=True` adds
+        `self.last_device_crops`: per chunk the (g, 3, size, size) f32 tensor)."""
         if self.img_size % 2 or self.img_size > 256:
             raise ValueError(f"B200 crop kernel supports even image sizes up to 256, got {self.img_size} (no CPU fallback)")
         seg = self._segmenter()
         dev = seg.device
         lut = _seg.input_lut(self.mean, self.std)
         pool = _host_pool()
-        out = []
-        self.last_device_crops = []
-        pending = []                      # (future of the fresh copy of the crops, chunk tables) of the chunks in flight
+        fresh = _seg.FreshPinned()
+        n_chunks = (len(imgs_bin) + lines_per_chunk - 1) // lines_per_chunk
+        self.last_device_crops = [None] * n_chunks
+        if not n_chunks:
+            return []
+        n_lanes = min(2, n_chunks)
+        streams = seg.lane_streams(n_lanes)
+        with torch.cuda.device(dev):
+            caller_stream = torch.cuda.current_stream(dev)
+        from concurrent.futures import Future
+        done = [Future() for _ in range(n_chunks)]
 
         def pack_one(args):
             m, ln, hn = args
@@ -82,43 +93,54 @@ class StrokeEstimationSession:
                 np.not_equal(m, 0, out=view[:, :w], casting="unsafe")
             view[:, w:] = 0                           # pad columns of the plane must be zero (CCL strips)
 
-        def finish(item):
-            fut, groups, lgs, cr, n_lines = item
-            imgs_h = fut.result() if fut is not None else None
-            if cr is not None and len(groups):
-                left, top = groups[:, 1], groups[:, 2]
-                ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
-            LP = _seg.LazyPartition
-            for k in range(n_lines):
-                out.append([LP(lut, image=imgs_h[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
-                            for g in range(int(lgs[k]), int(lgs[k + 1]))])
+        def run_chunk(ci, lane):
+            masks = imgs_bin[ci * lines_per_chunk:(ci + 1) * lines_per_chunk]
+            key = ("lane", lane)                      # one staging set per lane: its chunks run one after the other
+            batch = _seg.plan_batch([m.shape[1] for m in masks], dev)
+            h = seg.staging.get_tensor((key, "masks"), batch.px_total)
+            hn = h.numpy()
+            list(pool.map(pack_one, [(m, ln, hn) for m, ln in zip(masks, batch.lines)]))   # numpy copies release the GIL
+            planes = h.to(dev, non_blocking=True)
+            res = seg.partition(batch, planes, canvases="device", key=key, zero_copy=True, crops=True, crops_to_host=True,
+                                crop_lut=lut if keep_device else None, staging=fresh)
+            if self.img_size != _seg.IMG_SIZE and len(res["groups"]):
+                res["crops"] = _seg.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"], size=self.img_size,
+                                                lut=lut if keep_device else None)
+                img = res["crops"]["image"]
+                res["crops"]["image_host"] = _seg.copy_d2h(fresh.get(None, img.numel()), img, dev).reshape(tuple(img.shape))
+            torch.cuda.current_stream(dev).synchronize()
+            cr = res["crops"]
+            if keep_device and cr is not None and cr["image_input"] is not None:
+                cr["image_input"].record_stream(caller_stream)     # allocated on the lane's stream, read on the caller's
+                self.last_device_crops[ci] = cr["image_input"]
+            return (cr["image_host"] if cr is not None and "image_host" in cr else None, res["groups"], cr,
+                    res["line_group_start"], batch.n_lines)
+
+        def run_lane(lane):
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(streams[lane]):
+                    for ci in range(lane, n_chunks, n_lanes):
+                        done[ci].set_result(run_chunk(ci, lane))
+            except BaseException as e:                # the caller's thread re-raises it from the first unfinished chunk
+                for f in done:
+                    if not f.done():
+                        f.set_exception(e)
 
         with torch.cuda.device(dev):
-            for c0 in range(0, len(imgs_bin), lines_per_chunk):
-                masks = imgs_bin[c0:c0 + lines_per_chunk]
-                key = ("chunk", (c0 // lines_per_chunk) & 1)           # two staging sets: chunk k+1 is packed while the
-                if len(pending) == 2:                                  # host copy of chunk k-1 still reads the other set
-                    finish(pending.pop(0))
-                batch = _seg.plan_batch([m.shape[1] for m in masks], dev)
-                h = seg.staging.get_tensor((key, "masks"), batch.px_total)
-                hn = h.numpy()
-                list(pool.map(pack_one, [(m, ln, hn) for m, ln in zip(masks, batch.lines)]))   # numpy copies release the GIL
-                planes = h.to(dev, non_blocking=True)
-                res = seg.partition(batch, planes, canvases="device", key=key, crops=True, crops_to_host=True,
-                                    crop_lut=lut if keep_device else None)
-                if self.img_size != _seg.IMG_SIZE and len(res["groups"]):
-                    res["crops"] = _seg.group_crops(dev, res["canvas"], res["_keep"][0], res["groups"], size=self.img_size,
-                                                    lut=lut if keep_device else None)
-                    img = res["crops"]["image"]
-                    res["crops"]["image_host"] = _seg.copy_d2h(seg.staging.get((key, "crops"), img.numel()), img, dev).reshape(tuple(img.shape))
-                torch.cuda.current_stream(dev).synchronize()
-                cr = res["crops"]
-                if keep_device:
-                    self.last_device_crops.append(cr["image_input"] if cr is not None else None)
-                fut = pool.submit(np.copy, cr["image_host"]) if cr is not None and "image_host" in cr else None
-                pending.append((fut, res["groups"], res["line_group_start"], cr, batch.n_lines))
-            while pending:
-                finish(pending.pop(0))
+            cur = torch.cuda.current_stream(dev)
+            for st in streams:
+                st.wait_stream(cur)
+            lanes = [_seg.lane_pool().submit(run_lane, k) for k in range(n_lanes)]
+            out = []
+            try:
+                for f in done:
+                    imgs_h, groups, cr, lgs, n_lines = f.result()
+                    out.extend(_seg.build_partitions(lut, imgs_h, groups, cr, lgs, n_lines))
+            finally:
+                for ln in lanes:
+                    ln.result()
+                for st in streams:
+                    cur.wait_stream(st)
         return out
 
     # ---- stroke-estimator front end (evaluate_strokes.py:150-160, 250-262) --------------------

@@ -119,7 +119,7 @@ class LineSegmentationJob:
         self.n_lines = sum(c.batch.n_lines for c in self.chunks)
         self.px_total = sum(c.batch.px_total for c in self.chunks)
 
-    def _run(self, from_host: bool, canvases: str, writer: G.RegionWriter | None = None, collect=None):
+    def _run(self, from_host: bool, canvases: str, writer: G.RegionWriter | None = None, collect=None, fresh: bool = False):
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             for st in (self.s_copy, self.s_unet, self.s_part):
@@ -160,7 +160,8 @@ class LineSegmentationJob:
             results = []
             dbg = os.environ.get("SD_PIPE_DEBUG")
             t_dbg = [time.perf_counter()]
-            st = writer if writer is not None else self.staging
+            # fresh: results land in new page-locked arrays the caller keeps (no copy out of a reused staging buffer)
+            st = writer if writer is not None else (S.FreshPinned() if fresh else self.staging)
             with torch.cuda.stream(self.s_part):
                 for ch, ev in zip(self.chunks, ready):
                     self.s_part.wait_event(ev)
@@ -198,9 +199,10 @@ class LineSegmentationJob:
 
     def binarize_step(self):
         """Only the binarization half, from the caller's numpy images: -> [ (128, W', 1) u8 {0,255} ] in line order
-        (evaluate_binarize.py:130-140).  One packed D2H per chunk; the per-line arrays are fresh copies, made while
-        the GPU is still on later chunks."""
+        (evaluate_binarize.py:130-140).  One packed D2H per chunk, straight into a fresh page-locked array
+        (`segment.FreshPinned`): a line's mask is a view into it, no second host copy."""
         out = []
+        fresh = S.FreshPinned()
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             for st in (self.s_copy, self.s_unet, self.s_part):
@@ -228,13 +230,12 @@ class LineSegmentationJob:
                         done += n
                     while glued < len(self.chunks) and self.chunks[glued].t1 <= done:
                         g = self.chunks[glued]
-                        hosts[glued] = S.copy_d2h(self.staging.get((("chunk", g.index), "planes"), g.batch.px_total), g.planes, self.device)
+                        hosts[glued] = S.copy_d2h(fresh.get(None, g.batch.px_total), g.planes, self.device)
                         ev = torch.cuda.Event(); ev.record(self.s_unet)
                         evs[glued] = ev
                         glued += 1
             for ch, ev, hp in zip(self.chunks, evs, hosts):
                 ev.synchronize()
-                hp = hp.copy()                        # one fresh array per chunk; a line's mask is a view into it
                 for ln in ch.batch.lines:
                     off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
                     out.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
@@ -268,26 +269,19 @@ class LineSegmentationJob:
         `BinarizationSession.binarize_images` (evaluate_binarize.py:130-140) and
         `StrokeEstimationSession.get_partitions` (evaluate_strokes.py:186-224) return.  `image_input` of a
         partition is materialised on first access (`segment.LazyPartition`)."""
-        masks, parts = [], []
         hp = res["planes_host"]
         cr = res["crops"]
         img_host = cr["image_host"] if cr is not None and "image_host" in cr else None
-        groups, lgs = res["groups"], res["line_group_start"]
         if copy:                          # fresh arrays (two host threads; numpy copies release the GIL)
             f1 = S.host_pool().submit(np.copy, hp)
             if img_host is not None:
                 img_host = img_host.copy()
             hp = f1.result()
-        if cr is not None and len(groups):
-            left, top = groups[:, 1], groups[:, 2]
-            ratio, t2x, t2y = cr["ratio"].tolist(), cr["translate2"][:, 0].tolist(), cr["translate2"][:, 1].tolist()
-        LP = S.LazyPartition
-        have_crops = img_host is not None and len(groups) > 0
-        for k, ln in enumerate(ch.batch.lines):
+        masks = []
+        for ln in ch.batch.lines:
             off, pitch, w = int(ln["px_off"]), int(ln["pitch"]), int(ln["width"])
             masks.append(hp[off:off + TILE_H * pitch].reshape(TILE_H, pitch)[:, :w, None])
-            parts.append([LP(lut, image=img_host[g], translate1=(left[g], top[g]), ratio=ratio[g], translate2=(t2x[g], t2y[g]))
-                          for g in range(int(lgs[k]), int(lgs[k + 1]))] if have_crops else [])
+        parts = S.build_partitions(lut, img_host, res["groups"], cr, res["line_group_start"], ch.batch.n_lines)
         return masks, parts
 
     def line_outputs(self, results, copy: bool = True, mean=None, std=None):
@@ -305,7 +299,8 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
     """The fused public call on one GPU: a list of (h, w, 3) u8 line images (plain numpy) in, per line the
     binarized mask and the stroke-estimator partitions out, in input order — `binarize_image` + `main.py:108` +
     `get_partitions` of the reference for every image, as one pipelined job.  A mask is a (128, W', 1) view into one
-    fresh array per chunk of lines (`copy=False`: into the reused page-locked staging, valid until the next call)."""
+    fresh page-locked array per chunk of lines, a partition's `image` a view into the chunk's crop array: the D2H copies
+    land directly in what is returned (`copy=False`: in the reused staging instead, valid until the next call)."""
     t0 = time.perf_counter()
     if seg is None:
         seg = S.Segmenter.for_engine(engine, bin_thr)
@@ -317,10 +312,10 @@ def segment_lines(engine: UNetEngine, images, bin_thr: float = 0.5, lines_per_ch
 
     def collect(ch, res):
         tc = time.perf_counter()
-        m, p = job.chunk_outputs(ch, res, lut, copy)
+        m, p = job.chunk_outputs(ch, res, lut, copy=False)
         masks.extend(m); parts.extend(p)
         t_collect[0] += time.perf_counter() - tc
-    job._run(True, "device", collect=collect)
+    job._run(True, "device", collect=collect, fresh=copy)
     if os.environ.get("SD_PIPE_DEBUG"):
         print(f"[segment_lines] job construction {1e3 * (t1 - t0):.1f} ms, run {1e3 * (time.perf_counter() - t1):.1f} ms "
               f"(of which per-line outputs {1e3 * t_collect[0]:.1f} ms)", file=sys.stderr, flush=True)

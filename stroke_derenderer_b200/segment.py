@@ -360,6 +360,18 @@ def host_pool():
     return _POOL
 
 
+_LANES = None
+
+
+def lane_pool():
+    """Threads of the host lanes of the batched calls (a lane = a thread + a CUDA stream that takes every other chunk)."""
+    global _LANES
+    if _LANES is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _LANES = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sd-lane")
+    return _LANES
+
+
 class PinnedStaging:
     """Grow-only pinned host staging buffers, one per purpose (`key`), owned by ONE Segmenter / job (two
     Segmenters driven from different threads, one per GPU, never share a buffer).  `get` returns a uint8 numpy
@@ -374,6 +386,19 @@ class PinnedStaging:
             buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
             self._bufs[key] = buf
         return buf[:nbytes]
+
+    def get(self, key, nbytes: int) -> np.ndarray:
+        return self.get_tensor(key, nbytes).numpy()
+
+
+class FreshPinned:
+    """Staging for RESULTS the caller keeps: every `get` hands out a new page-locked buffer, so device-to-host copies
+    land directly in the arrays that are returned (no second host copy).  The numpy view keeps its tensor alive; when
+    the last view of a result dies the block goes back to torch's caching host allocator, and the next call gets it
+    without a cudaHostAlloc (first calls pay the page-locking once)."""
+
+    def get_tensor(self, key, nbytes: int) -> torch.Tensor:
+        return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())[:nbytes]
 
     def get(self, key, nbytes: int) -> np.ndarray:
         return self.get_tensor(key, nbytes).numpy()
@@ -411,6 +436,35 @@ class LazyPartition(dict):
         v = self._lut[:, norm]
         self[key] = v
         return v
+
+
+_LP_CLASSES = {}
+
+
+def lazy_partition_class(lut: np.ndarray):
+    """A LazyPartition subclass with the table bound at class level: instances are then built by dict's own C
+    constructor (`cls(image=..., translate1=..., ...)`), ~3x cheaper than a Python __init__ per partition."""
+    key = lut.tobytes()
+    cls = _LP_CLASSES.get(key)
+    if cls is None:
+        cls = type("LazyPartition", (LazyPartition,), {"_lut": lut, "__init__": dict.__init__})
+        if len(_LP_CLASSES) > 16:
+            _LP_CLASSES.clear()
+        _LP_CLASSES[key] = cls
+    return cls
+
+
+def build_partitions(lut, image_host, groups, crops, lgs, n_lines):
+    """Per line the list of partition dicts of evaluate_strokes.py:213-219 for one chunk: `image` is a (size, size) view
+    into `image_host`, translate1 = (left, top) as numpy int64 like the reference's, ratio / translate2 Python floats."""
+    if image_host is None or not len(groups):
+        return [[] for _ in range(n_lines)]
+    LP = lazy_partition_class(lut)
+    t1 = zip(groups[:, 1], groups[:, 2])
+    t2 = zip(crops["translate2"][:, 0].tolist(), crops["translate2"][:, 1].tolist())
+    flat = [LP(image=im, translate1=a, ratio=r, translate2=b) for im, a, r, b in zip(image_host, t1, crops["ratio"].tolist(), t2)]
+    b = lgs.tolist()
+    return [flat[b[k]:b[k + 1]] for k in range(n_lines)]
 
 
 class PartitionResult(dict):
@@ -489,6 +543,13 @@ class Segmenter:
             with torch.cuda.device(self.device):
                 self._streams = tuple(torch.cuda.Stream(self.device) for _ in range(3))
         return self._streams
+
+    def lane_streams(self, n: int):
+        """CUDA streams of the host lanes (`lane_pool`), created once per Segmenter."""
+        if getattr(self, "_lane_streams", None) is None or len(self._lane_streams) < n:
+            with torch.cuda.device(self.device):
+                self._lane_streams = tuple(torch.cuda.Stream(self.device) for _ in range(n))
+        return self._lane_streams[:n]
 
     def binarize(self, images, d_rgb: torch.Tensor | None = None, batch: LineBatch | None = None):
         """-> (batch, mask planes u8 {0,255} packed on device)."""
