@@ -6,16 +6,18 @@
 //      with coalesced 16-byte loads; every load becomes 8 "even column" + 8 "odd column" bits (dp4a), so pixel row r
 //      of the strip is two 64-bit words Xe / Xo whose bit k is the left / right pixel of block k.  Lane L owns block
 //      rows 2L and 2L+1: occupancy, horizontal links, run starts and the contacts with the block row above are
-//      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row), unions
-//      are shared-memory compare-and-swaps on roots only (min-root: the root of a component is its first block in
-//      raster order, which is what OpenCV's numbering sorts by), finds halve their paths.  Outputs per strip: the Xe / Xo words (2 KB), the
+//      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row).  Every run
+//      first takes ONE contact with the row above as its parent (plain stores), pointer jumping flattens the resulting
+//      forest (depth halves per round, no divergence), and only the contacts that are left — where two trees meet —
+//      are real unions: shared-memory compare-and-swaps on roots only (min-root: the root of a component is its first
+//      block in raster order, which is what OpenCV's numbering sorts by), finds halve their paths.  Outputs per strip: the Xe / Xo words (2 KB), the
 //      run-start masks (512 B) and one 16-bit root per run (bit 15 = the root touches a neighbouring strip):
 //      ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that touch no other strip are final
 //      (root bitmap); the others register in the sparse global parent array.
-//   2. ccl_seam_merge_kernel / ccl_seam_mark_kernel (thread = seam block row): unions across the strip seams on the
-//      sparse global parents; seam roots that survive are marked in the bitmap.  ccl_line_kernel (CTA = line):
-//      exclusive scan of the root bitmap (label = 1 + #roots before the root), island count; the last CTA to
-//      finish also scans the counts of all lines into the stats row offsets.
+//   2. ccl_seam_merge_kernel (thread = seam block row): 8-connectivity across strip seams on the sparse global parents.
+//      ccl_line_kernel (CTA = line): seam roots that survived the merges enter the root bitmap; exclusive scan of the
+//      bitmap (label = 1 + #roots before the root), island count; the last CTA to finish also scans the counts of all
+//      lines into the stats row offsets.
 //   3. ccl_strip_write2_kernel (CTA = strip, 256 threads): run roots -> final labels (shared-memory table), int32
 //      labels out as 512-byte row segments, and, fused, the cv2 stats: every run's extent / area is reduced over the
 //      lanes that hold runs of the same label (match_any + redux) before one set of global atomics per group.
@@ -87,16 +89,41 @@ __device__ __forceinline__ void cw_union(cw_node_t* p, int a, int b) {
   }
 }
 
-// contacts of a block row (top pixel row Te / To, links hl, run starts rs) with the pixel row above it (Ue / Uo; links
-// hlU and run starts rsU of that block row): one union per distinct (run, upper run) pair
-__device__ __forceinline__ void cw_contacts(cw_node_t* parent, int base, int baseU, uint64_t Te, uint64_t To, uint64_t Ue, uint64_t Uo,
-                                            uint64_t hl, uint64_t hlU, uint64_t rs, uint64_t rsU) {
+// Contacts of a block row (top pixel row Te / To, links hl, run starts rs) with the pixel row above it (Ue / Uo; links
+// hlU of that block row): bit k of vu / vl / vr = block k touches upper block k / k-1 / k+1, thinned so that a
+// (run, upper run) pair that touches along several adjacent blocks is reported once.
+struct CwContacts { uint64_t vu, vl, vr; };
+__device__ __forceinline__ CwContacts cw_contact_masks(uint64_t Te, uint64_t To, uint64_t Ue, uint64_t Uo, uint64_t hl, uint64_t hlU) {
   const uint64_t vu0 = (Te | To) & (Ue | Uo);                 // block k - upper block k
   uint64_t vl = Te & (Uo << 1);                               // block k - upper block k-1 (diagonal)
   uint64_t vr = To & (Ue >> 1);                               // block k - upper block k+1 (diagonal)
   vl &= ~(vu0 & hlU) & ~((vu0 << 1) & hl);
   vr &= ~(vu0 & (hlU >> 1)) & ~((vu0 >> 1) & (hl >> 1));
-  uint64_t vu = vu0 & ~((vu0 << 1) & hl & hlU);
+  CwContacts c;
+  c.vu = vu0 & ~((vu0 << 1) & hl & hlU);
+  c.vl = vl; c.vr = vr;
+  return c;
+}
+// Phase A: every run of the row takes its FIRST contact with the row above as its parent (a plain store: the entry
+// belongs to this lane alone, and a link always points to a smaller node id, so the forest is acyclic and a tree's root is
+// its smallest node = the component's first block in raster order).  The contact is removed from the masks; what is left
+// in them are the places where two trees meet (the bottom of a "V"), a small minority on handwriting.
+__device__ __forceinline__ void cw_link_first(cw_node_t* parent, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts& c) {
+  for (uint64_t t = rs; t; t &= t - 1) {
+    const int k = __ffsll((long long)t) - 1;
+    const uint64_t above = t & (t - 1);                                              // run starts to the right of k
+    const uint64_t ext = (above ? ((above & (~above + 1ull)) - 1ull) : ~0ull) & ~((1ull << k) - 1ull);   // blocks k .. next start - 1
+    const uint64_t cu = c.vu & ext, cl = c.vl & ext, cr = c.vr & ext;
+    int node = base + k;
+    if (cu) { const int j = __ffsll((long long)cu) - 1; c.vu &= ~(1ull << j); node = baseU + cw_run_start(rsU, j); }
+    else if (cl) { const int j = __ffsll((long long)cl) - 1; c.vl &= ~(1ull << j); node = baseU + cw_run_start(rsU, j - 1); }
+    else if (cr) { const int j = __ffsll((long long)cr) - 1; c.vr &= ~(1ull << j); node = baseU + cw_run_start(rsU, j + 1); }
+    parent[base + k] = (cw_node_t)node;
+  }
+}
+// Phase C: the contacts phase A left over, as real unions (compare-and-swap on roots) over the flattened trees
+__device__ __forceinline__ void cw_union_rest(cw_node_t* parent, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts c) {
+  uint64_t vu = c.vu, vl = c.vl, vr = c.vr;
   while (vu | vl | vr) {
     int k, dk;
     if (vu) { k = __ffsll((long long)vu) - 1; vu &= vu - 1; dk = 0; }
@@ -119,6 +146,39 @@ __device__ __forceinline__ int cw_find_line(const sd_line* __restrict__ L, int n
 #pragma unroll
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   return cnt - 1;
+}
+
+__device__ __forceinline__ int cw_uf_find(const int* __restrict__ parent, int a) {
+  int p = __ldcg(parent + a);
+  while (p != a) { a = p; p = __ldcg(parent + a); }
+  return a;
+}
+__device__ __forceinline__ void cw_uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = cw_uf_find(parent, a);
+    b = cw_uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+__device__ __forceinline__ uint32_t cw_col_bit(const uint32_t* __restrict__ p, int row) { return (__ldcg(p + (row & 3)) >> (row >> 2)) & 1u; }
+
+// One block row of one strip seam: 8-connectivity between pixel column 127 of strip sg-1 and pixel column 0 of strip sg
+// on the sparse global parents (bnd_root of the right side of a line's last strip is -1, so lines never merge).
+__device__ __forceinline__ void cw_seam_row(const CclWarpWork& w, int64_t sg, int br) {
+  const int a = __ldcg(w.bnd_root + (sg - 1) * 128 + 64 + br);
+  if (a < 0) return;
+  const int* Rr = w.bnd_root + sg * 128;
+  const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
+  const uint32_t* Rb = w.bnd_bits + sg * 8;
+  const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
+  const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
+  if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, __ldcg(Rr + br));
+  if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, __ldcg(Rr + br - 1));
+  if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, __ldcg(Rr + br + 1));
 }
 
 __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t* __restrict__ mask, const sd_line* __restrict__ L,
@@ -171,14 +231,37 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     w.rs[(int64_t)strip * 64 + 2 * lane] = make_uint2((uint32_t)rsa, (uint32_t)(rsa >> 32));
     w.rs[(int64_t)strip * 64 + 2 * lane + 1] = make_uint2((uint32_t)rsb, (uint32_t)(rsb >> 32));
     const int na = 2 * lane * 64, nb = na + 64;                           // node bases of the two block rows
-    for (uint64_t t = rsa; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[na + k] = (cw_node_t)(na + k); }
-    for (uint64_t t = rsb; t; t &= t - 1) { const int k = __ffsll((long long)t) - 1; sm.parent[nb + k] = (cw_node_t)(nb + k); }
     // the block row above row a belongs to lane L-1 (its row b)
     const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
     const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
+    CwContacts ca = cw_contact_masks(Tea, Toa, Ue, Uo, hla, hlU);
+    CwContacts cb = cw_contact_masks(Teb, Tob, Bea, Boa, hlb, hla);
+    // phase A: first contact of every run -> its parent (stores only)
+    cw_link_first(sm.parent, na, na - 64, rsa, rsU, ca);
+    cw_link_first(sm.parent, nb, na, rsb, rsa, cb);
+    // phase B: pointer jumping flattens the forest (a vertical stroke is a chain of up to 64 runs: depth halves per round)
+    {
+      volatile cw_node_t* vp = sm.parent;
+#pragma unroll 1
+      for (int round = 0; round < 6; ++round) {
+        __syncwarp();
+        bool changed = false;
+        uint64_t ta = rsa, tb = rsb;
+        while (ta | tb) {
+          int xa = -1, xb = -1, pa = 0, pb = 0;
+          if (ta) { xa = na + __ffsll((long long)ta) - 1; ta &= ta - 1; pa = vp[xa]; }
+          if (tb) { xb = nb + __ffsll((long long)tb) - 1; tb &= tb - 1; pb = vp[xb]; }
+          const int ga = xa >= 0 ? vp[pa] : 0, gb = xb >= 0 ? vp[pb] : 0;
+          if (xa >= 0 && ga != pa) { vp[xa] = (cw_node_t)ga; changed = true; }
+          if (xb >= 0 && gb != pb) { vp[xb] = (cw_node_t)gb; changed = true; }
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;
+      }
+    }
     __syncwarp();
-    cw_contacts(sm.parent, na, na - 64, Tea, Toa, Ue, Uo, hla, hlU, rsa, rsU);
-    cw_contacts(sm.parent, nb, na, Teb, Tob, Bea, Boa, hlb, hla, rsb, rsa);
+    // phase C: the remaining contacts join trees
+    cw_union_rest(sm.parent, na, na - 64, rsa, rsU, ca);
+    cw_union_rest(sm.parent, nb, na, rsb, rsa, cb);
     __syncwarp();
     // ---- seam blocks: their roots touch a neighbouring strip ----
     const int gbase = (int)ln.blk_off + s * 64;                          // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
@@ -245,54 +328,18 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
   }
 }
 
-__device__ __forceinline__ int cw_uf_find(const int* __restrict__ parent, int a) {
-  int p = __ldcg(parent + a);
-  while (p != a) { a = p; p = __ldcg(parent + a); }
-  return a;
-}
-__device__ __forceinline__ void cw_uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = cw_uf_find(parent, a);
-    b = cw_uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }
-    const int old = atomicMin(&parent[a], b);
-    if (old == a) return;
-    a = old;
-  }
-}
-__device__ __forceinline__ uint32_t cw_col_bit(const uint32_t* __restrict__ p, int row) { return (p[row & 3] >> (row >> 2)) & 1u; }
-
-// thread = one block row of one strip seam: 8-connectivity between pixel column 127 of strip sg-1 and pixel column 0
-// of strip sg (bnd_root of the right side of a line's last strip is -1, so lines never merge)
+// thread = one block row of one strip seam.  (Measured alternative, rejected: the strip that finishes second at a seam
+// merges it inside the label kernel — the serial global pointer chases on every warp's critical path cost +36 us on
+// 66 Mpx against the 15 us of this kernel.)
 __global__ void __launch_bounds__(256) ccl_seam_merge_kernel(CclWarpWork w, int n_strips) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_strips * 64) return;
-  const int64_t sg = i >> 6;
-  const int br = i & 63;
-  if (sg == 0) return;
-  const int a = w.bnd_root[(sg - 1) * 128 + 64 + br];
-  if (a < 0) return;
-  const int* Rr = w.bnd_root + sg * 128;
-  const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
-  const uint32_t* Rb = w.bnd_bits + sg * 8;
-  const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
-  const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
-  if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, Rr[br]);
-  if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, Rr[br - 1]);
-  if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, Rr[br + 1]);
+  if (i >= n_strips * 64 || (i >> 6) == 0) return;
+  cw_seam_row(w, i >> 6, i & 63);
 }
 
-// seam roots that are still roots after the merge are component roots
-__global__ void __launch_bounds__(256) ccl_seam_mark_kernel(CclWarpWork w, int n_strips) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_strips * 128) return;
-  const int k = w.bnd_root[i];
-  if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
-}
-
-// CTA = line: exclusive scan of the root bitmap (label = 1 + #roots before the root), island count; the last CTA to
-// finish turns the counts of all lines into stats row offsets (stat_off[l] = sum over lines < l of (num - 1)).
+// CTA = line: seam roots that are still roots after the merges are component roots (root bitmap); then the exclusive
+// scan of the bitmap (label = 1 + #roots before the root), island count; the last CTA to finish turns the counts of all
+// lines into stats row offsets (stat_off[l] = sum over lines < l of (num - 1)).
 __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restrict__ L, int n_lines, CclWarpWork w,
                                                         int* __restrict__ num_out, int64_t* __restrict__ stat_off) {
   const int l = blockIdx.x, tid = threadIdx.x;
@@ -303,6 +350,14 @@ __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restric
   __shared__ int s_carry;
   __shared__ int s_last;
   if (tid == 0) s_carry = 0;
+  {
+    const int64_t first = (ln.blk_off >> 12) * 128;                       // bnd_root entries of this line's strips
+    const int n_bnd = (ln.bw >> 6) * 128;
+    for (int i = tid; i < n_bnd; i += blockDim.x) {
+      const int k = __ldcg(w.bnd_root + first + i);
+      if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
+    }
+  }
   __syncthreads();
   const int words = 2 * ln.bw;
   for (int c = 0; c < words; c += blockDim.x * 4) {

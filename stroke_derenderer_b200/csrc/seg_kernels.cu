@@ -847,14 +847,19 @@ static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lin
   }
   const int ctas = (strips + kCw - 1) / kCw;
   if (d_stats && cap_rows > 0) SD_CUDA_CHECK(cudaMemsetAsync(d_stats, 0x7f, (size_t)cap_rows * 20, s));
+  // SD_CCL_STAGE=k (debug / profiling): stop after the k-th kernel of the chain, so that CUDA-event times of the call
+  // for k = 1..4 give every kernel's steady-state share (tools/ccl_bench.py --stages)
+  const char* stage_env = getenv("SD_CCL_STAGE");
+  const int stage = stage_env ? atoi(stage_env) : 99;
   ccl_warp_label_kernel<<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
   SD_LAUNCH_CHECK("ccl_warp_label_kernel");
+  if (stage < 2) return SD_OK;
   ccl_seam_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
   SD_LAUNCH_CHECK("ccl_seam_merge_kernel");
-  ccl_seam_mark_kernel<<<ceil_div((int64_t)strips * 128, 256), 256, 0, s>>>(w, strips);
-  SD_LAUNCH_CHECK("ccl_seam_mark_kernel");
+  if (stage < 3) return SD_OK;
   ccl_line_kernel<<<n_lines, 1024, 0, s>>>(d_lines, n_lines, w, d_num, d_stat_off);
   SD_LAUNCH_CHECK("ccl_line_kernel");
+  if (stage < 4) return SD_OK;
   ccl_strip_write2_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels, d_stat_off, d_stats, cap_rows);
   SD_LAUNCH_CHECK("ccl_strip_write2_kernel");
   if (d_stats && cap_rows > 0) {

@@ -55,11 +55,11 @@ class StrokeEstimationSession:
             seg = self._seg_obj = _seg.Segmenter(None, margin=self.margin, device=dev)
         return seg
 
-    def get_partitions_batch(self, imgs_bin, lines_per_chunk: int = 64, keep_device: bool = False):
+    def get_partitions_batch(self, imgs_bin, lines_per_chunk: int = 64, keep_device: bool = False, lanes: int = 3):
         """Many lines in one pipelined device pass: per chunk of lines one H2D of the packed masks, CCL, stats,
         clustering, canvases and the 224x224 crops (sd_group_crops: cv2.normalize / cv2.resize / pad bit for bit),
         one D2H of the u8 crops straight into the page-locked arrays that are returned (no second host copy).
-        Two host lanes (a thread + a CUDA stream each) take alternate chunks, so packing / H2D / kernels / D2H of
+        A few host lanes (a thread + a CUDA stream each) take the chunks in turn, so packing / H2D / kernels / D2H of
         chunk k+1 run while the caller's thread builds the partition dicts of chunk k.
         -> per line the list of partition dicts of :213-219; `image_input` is built on first access
         (segment.LazyPartition), or stays on the GPU for the stroke-estimator front end (`keep_device=True` adds
@@ -75,7 +75,7 @@ class StrokeEstimationSession:
         self.last_device_crops = [None] * n_chunks
         if not n_chunks:
             return []
-        n_lanes = min(2, n_chunks)
+        n_lanes = max(1, min(lanes, n_chunks, 4))
         streams = seg.lane_streams(n_lanes)
         with torch.cuda.device(dev):
             caller_stream = torch.cuda.current_stream(dev)

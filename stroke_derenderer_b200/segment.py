@@ -368,7 +368,7 @@ def lane_pool():
     global _LANES
     if _LANES is None:
         from concurrent.futures import ThreadPoolExecutor
-        _LANES = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sd-lane")
+        _LANES = ThreadPoolExecutor(max_workers=4, thread_name_prefix="sd-lane")
     return _LANES
 
 
