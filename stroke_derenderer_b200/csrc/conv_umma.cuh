@@ -1316,7 +1316,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
 // the kernel is bound by the 16 KB output store per tile, not by the tensor pipe.
 //   warp 0: MMA issuer | warps 1-4: im2col producers | warps 5-8: epilogue (TMEM -> bias/ReLU -> TMA store)
 // ---------------------------------------------------------------------------------------------
-constexpr int kC1Stages = 4;
+#ifndef SD_C1_CTAS
+#define SD_C1_CTAS 2
+#endif
+constexpr int kC1CtasPerSm = SD_C1_CTAS;               // 2 CTAs x 4 stages (108 KB each); 3 CTAs x 2 stages measured slower (0.53 vs 0.48 ms per 256 tiles)
+constexpr int kC1Stages = kC1CtasPerSm == 3 ? 2 : 4;
 constexpr int kC1K = 80;
 constexpr int kC1GroupBytes = (kC1K / 8) * 128;        // 1280: one 8-row group across K
 constexpr int kC1ABytes = 16 * kC1GroupBytes;          // 20480
@@ -1338,7 +1342,7 @@ __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t 
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(kC1Threads, 2) conv_first_umma_kernel(const __grid_constant__ ConvFirstParams p) {
+__global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kernel(const __grid_constant__ ConvFirstParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));

@@ -846,7 +846,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
     first.run = [e, cp](int B, cudaStream_t s) mutable -> int {
       cp.B = B; cp.in = reinterpret_cast<const uint4*>(e->in_tiles);
       const int n_work = B * e->H * (e->W / 128);
-      const int grid = n_work < 2 * e->num_sms ? n_work : 2 * e->num_sms;
+      const int grid = n_work < kC1CtasPerSm * e->num_sms ? n_work : kC1CtasPerSm * e->num_sms;
       conv_first_umma_kernel<<<grid, kC1Threads, kC1SmemBytes, s>>>(cp);
       SD_LAUNCH_CHECK("conv_first_umma_kernel");
       return SD_OK;

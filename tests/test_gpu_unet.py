@@ -233,6 +233,12 @@ def test_api_calls_from_numpy_and_gather_arena(cuda_device, parity_state):
             assert np.array_equal(m[:, :, 0], ref["batch"].plane(ref["planes"], i).cpu().numpy()), i
         se = StrokeEstimationSession()
         parts = se.get_partitions_batch([m[:, :, 0] > 127 for m in masks], lines_per_chunk=3)
+        # the host lanes (threads + streams taking the chunks in turn) only change the schedule, never the result or its order
+        parts1 = se.get_partitions_batch([m[:, :, 0] > 127 for m in masks], lines_per_chunk=2, lanes=1)
+        assert [len(a) for a in parts] == [len(a) for a in parts1]
+        for a, b in zip(parts, parts1):
+            for pa, pb in zip(a, b):
+                assert np.array_equal(pa["image"], pb["image"]) and pa["translate1"] == pb["translate1"] and pa["ratio"] == pb["ratio"]
         m2, p2 = segment_lines(e, lines, lines_per_chunk=4)
         assert all(np.array_equal(a, b) for a, b in zip(masks, m2))
         from oracle import segmentation_ref as O
