@@ -59,6 +59,12 @@ __device__ __forceinline__ uint64_t cw_shfl_up64(uint64_t v, int lane) {
 // block column of the run start that owns block k: highest run-start bit at or below k
 __device__ __forceinline__ int cw_run_start(uint64_t rs, int k) { return 63 - __clzll((long long)(rs & ((2ull << k) - 1ull))); }
 
+// Programmatic dependent launch: the kernels of the chain are launched with programmatic stream serialization, so the
+// launch latency and prologue of kernel k+1 overlap the tail of kernel k.  Every kernel lets its dependents launch right
+// away and waits for the COMPLETION (and memory flush) of its predecessor before it touches any data.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Union-find over the runs of one strip, in shared memory.  Parents are 16-bit (node ids are < 4096): 8 KB per strip
 // instead of 16 KB, which is what bounds the number of resident warps.
 typedef unsigned short cw_node_t;
@@ -108,7 +114,7 @@ __device__ __forceinline__ CwContacts cw_contact_masks(uint64_t Te, uint64_t To,
 // belongs to this lane alone, and a link always points to a smaller node id, so the forest is acyclic and a tree's root is
 // its smallest node = the component's first block in raster order).  The contact is removed from the masks; what is left
 // in them are the places where two trees meet (the bottom of a "V"), a small minority on handwriting.
-__device__ __forceinline__ void cw_link_first(cw_node_t* parent, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts& c) {
+__device__ __forceinline__ void cw_link_first(cw_node_t* parent, uint16_t*& list, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts& c) {
   for (uint64_t t = rs; t; t &= t - 1) {
     const int k = __ffsll((long long)t) - 1;
     const uint64_t above = t & (t - 1);                                              // run starts to the right of k
@@ -119,6 +125,7 @@ __device__ __forceinline__ void cw_link_first(cw_node_t* parent, int base, int b
     else if (cl) { const int j = __ffsll((long long)cl) - 1; c.vl &= ~(1ull << j); node = baseU + cw_run_start(rsU, j - 1); }
     else if (cr) { const int j = __ffsll((long long)cr) - 1; c.vr &= ~(1ull << j); node = baseU + cw_run_start(rsU, j + 1); }
     parent[base + k] = (cw_node_t)node;
+    *list++ = (uint16_t)(base + k);                          // compact run list, block-row major: the balanced phases walk it
   }
 }
 // Phase C: the contacts phase A left over, as real unions (compare-and-swap on roots) over the flattened trees
@@ -135,7 +142,8 @@ __device__ __forceinline__ void cw_union_rest(cw_node_t* parent, int base, int b
 
 struct __align__(16) CwLabelSmem {
   cw_node_t parent[kStripBlocks];  // node = block row * 64 + first block of the run
-  uint8_t e[128][8], o[128][8];    // Xe / Xo of every pixel row, one byte per 16-pixel load
+  uint8_t e[128][8], o[128][8];    // Xe / Xo of every pixel row, one byte per 16-pixel load; once they are in registers the
+                                   // first 512 B hold the root bits of the strip (bit = block is an interior component root)
   uint32_t touch[kStripBlocks / 32];
 };
 
@@ -164,21 +172,26 @@ __device__ __forceinline__ void cw_uf_union(int* parent, int a, int b) {
     a = old;
   }
 }
-__device__ __forceinline__ uint32_t cw_col_bit(const uint32_t* __restrict__ p, int row) { return (__ldcg(p + (row & 3)) >> (row >> 2)) & 1u; }
+__device__ __forceinline__ uint32_t cw_col_bit(uint4 p, int row) {
+  const uint32_t w = (row & 2) ? ((row & 1) ? p.w : p.z) : ((row & 1) ? p.y : p.x);
+  return (w >> (row >> 2)) & 1u;
+}
 
 // One block row of one strip seam: 8-connectivity between pixel column 127 of strip sg-1 and pixel column 0 of strip sg
-// on the sparse global parents (bnd_root of the right side of a line's last strip is -1, so lines never merge).
+// on the sparse global parents (bnd_root of the right side of a line's last strip is -1, so lines never merge).  All
+// inputs are fetched up front (one round trip to L2) before the unions walk the parents.
 __device__ __forceinline__ void cw_seam_row(const CclWarpWork& w, int64_t sg, int br) {
   const int a = __ldcg(w.bnd_root + (sg - 1) * 128 + 64 + br);
-  if (a < 0) return;
   const int* Rr = w.bnd_root + sg * 128;
-  const uint32_t* Lb = w.bnd_bits + (sg - 1) * 8 + 4;
-  const uint32_t* Rb = w.bnd_bits + sg * 8;
+  const int b0 = __ldcg(Rr + br), bm = br > 0 ? __ldcg(Rr + br - 1) : -1, bp = br < 63 ? __ldcg(Rr + br + 1) : -1;
+  const uint4 Lb = __ldcg(reinterpret_cast<const uint4*>(w.bnd_bits + (sg - 1) * 8 + 4));
+  const uint4 Rb = __ldcg(reinterpret_cast<const uint4*>(w.bnd_bits + sg * 8));
+  if (a < 0) return;
   const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
   const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
-  if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, __ldcg(Rr + br));
-  if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, __ldcg(Rr + br - 1));
-  if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, __ldcg(Rr + br + 1));
+  if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, b0);
+  if (br > 0 && a0 && cw_col_bit(Rb, 2 * br - 1)) cw_uf_union(w.parent, a, bm);
+  if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, bp);
 }
 
 __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t* __restrict__ mask, const sd_line* __restrict__ L,
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
   extern __shared__ __align__(16) uint8_t cw_smem[];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   CwLabelSmem& sm = reinterpret_cast<CwLabelSmem*>(cw_smem)[wp];
+  pdl_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0) *w.ticket = 0u;
   for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
     const int64_t blk0 = (int64_t)strip * kStripBlocks;
@@ -236,24 +250,35 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
     CwContacts ca = cw_contact_masks(Tea, Toa, Ue, Uo, hla, hlU);
     CwContacts cb = cw_contact_masks(Teb, Tob, Bea, Boa, hlb, hla);
-    // phase A: first contact of every run -> its parent (stores only)
-    cw_link_first(sm.parent, na, na - 64, rsa, rsU, ca);
-    cw_link_first(sm.parent, nb, na, rsb, rsa, cb);
-    // phase B: pointer jumping flattens the forest (a vertical stroke is a chain of up to 64 runs: depth halves per round)
+    // run ordinals: the runs of the strip in block-row-major order (the order of the root entries the write kernel reads)
+    const int cnt = __popcll(rsa) + __popcll(rsb);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const int n_runs = __shfl_sync(0xffffffffu, inc, 31);
+    uint16_t* const list = w.roots + (int64_t)strip * kStripBlocks;     // node ids now, root entries at the end (same slots)
+    uint32_t* const rootw = reinterpret_cast<uint32_t*>(&sm.e[0][0]);
+    __syncwarp();                                                          // every lane has its Xe / Xo words in registers
+    rootw[lane] = 0u; rootw[lane + 32] = 0u; rootw[lane + 64] = 0u; rootw[lane + 96] = 0u;
+    // phase A: first contact of every run -> its parent (stores only); the run joins the list
+    {
+      uint16_t* lp = list + (inc - cnt);
+      cw_link_first(sm.parent, lp, na, na - 64, rsa, rsU, ca);
+      cw_link_first(sm.parent, lp, nb, na, rsb, rsa, cb);
+    }
+    // phase B: pointer jumping flattens the forest (a vertical stroke is a chain of up to 64 runs: depth halves per
+    // round).  Lane-balanced over the run list: text fills a few block rows with many runs and leaves the rest empty.
     {
       volatile cw_node_t* vp = sm.parent;
 #pragma unroll 1
       for (int round = 0; round < 6; ++round) {
         __syncwarp();
         bool changed = false;
-        uint64_t ta = rsa, tb = rsb;
-        while (ta | tb) {
-          int xa = -1, xb = -1, pa = 0, pb = 0;
-          if (ta) { xa = na + __ffsll((long long)ta) - 1; ta &= ta - 1; pa = vp[xa]; }
-          if (tb) { xb = nb + __ffsll((long long)tb) - 1; tb &= tb - 1; pb = vp[xb]; }
-          const int ga = xa >= 0 ? vp[pa] : 0, gb = xb >= 0 ? vp[pb] : 0;
-          if (xa >= 0 && ga != pa) { vp[xa] = (cw_node_t)ga; changed = true; }
-          if (xb >= 0 && gb != pb) { vp[xb] = (cw_node_t)gb; changed = true; }
+        for (int j = lane; j < n_runs; j += 32) {
+          const int x = list[j];
+          const int pa = vp[x];
+          const int ga = vp[pa];
+          if (ga != pa) { vp[x] = (cw_node_t)ga; changed = true; }
         }
         if (!__any_sync(0xffffffffu, changed)) break;
       }
@@ -297,32 +322,24 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
       }
     }
     __syncwarp();
-    // ---- one root entry per run (block-row major); interior roots -> bitmap, seam roots -> global parents ----
+    // ---- one root entry per run (block-row major, lane-balanced over the list); interior roots -> root bits, seam roots
+    //      -> global parents ----
     {
-      const int cnt = __popcll(rsa) + __popcll(rsb);
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      uint16_t* out = w.roots + (int64_t)strip * kStripBlocks + (inc - cnt);
       volatile cw_node_t* vp = sm.parent;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nbase = h ? nb : na, row = 2 * lane + h;
-        uint64_t rootbits = 0ull;
-        for (uint64_t t = h ? rsb : rsa; t; t &= t - 1) {
-          const int k = __ffsll((long long)t) - 1;
-          const int r = cw_find(vp, nbase + k);                          // every union is done: roots are final
-          vp[nbase + k] = (cw_node_t)r;                                  // shortens the walks of the runs that follow
-          const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
-          *out++ = (uint16_t)(r | (tch << 15));
-          if (r == nbase + k) {
-            if (tch) { const int g = gbase + row * ln.bw + k; w.parent[g] = g; }
-            else rootbits |= 1ull << k;
-          }
+      for (int j = lane; j < n_runs; j += 32) {
+        const int x = list[j];
+        const int r = cw_find(vp, x);                                      // every union is done: roots are final
+        const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
+        list[j] = (uint16_t)(r | (tch << 15));
+        if (r == x) {
+          if (tch) { const int g = gbase + (x >> 6) * ln.bw + (x & 63); w.parent[g] = g; }
+          else atomicOr(&rootw[x >> 5], 1u << (x & 31));
         }
-        *reinterpret_cast<uint2*>(w.bitmap + (ln.blk_off >> 5) + (int64_t)row * (ln.bw >> 5) + s * 2) =
-            make_uint2((uint32_t)rootbits, (uint32_t)(rootbits >> 32));
       }
+      __syncwarp();
+      uint32_t* bm = w.bitmap + (ln.blk_off >> 5) + (int64_t)(2 * lane) * (ln.bw >> 5) + s * 2;
+      *reinterpret_cast<uint2*>(bm) = make_uint2(rootw[4 * lane], rootw[4 * lane + 1]);
+      *reinterpret_cast<uint2*>(bm + (ln.bw >> 5)) = make_uint2(rootw[4 * lane + 2], rootw[4 * lane + 3]);
     }
     __syncwarp();                                                          // shared memory is reused by the next strip
   }
@@ -332,6 +349,8 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
 // merges it inside the label kernel — the serial global pointer chases on every warp's critical path cost +36 us on
 // 66 Mpx against the 15 us of this kernel.)
 __global__ void __launch_bounds__(256) ccl_seam_merge_kernel(CclWarpWork w, int n_strips) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_strips * 64 || (i >> 6) == 0) return;
   cw_seam_row(w, i >> 6, i & 63);
@@ -344,6 +363,8 @@ __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restric
                                                         int* __restrict__ num_out, int64_t* __restrict__ stat_off) {
   const int l = blockIdx.x, tid = threadIdx.x;
   const sd_line ln = L[l];
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
   int* prefix = w.prefix + (ln.blk_off >> 5);
   __shared__ int s_warp[32];
@@ -450,6 +471,8 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
   __shared__ CwWriteSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int strip = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t blk0 = (int64_t)strip * kStripBlocks;
   if (wp == 0) {
     const int li = cw_find_line(L, n_lines, blk0, lane);
@@ -550,6 +573,7 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
 // stats rows -> cv2 layout (x, y, w, h, area); grid-stride over the rows actually used
 __global__ void __launch_bounds__(256) ccl_stats_finish_kernel(int32_t* __restrict__ st, const int64_t* __restrict__ stat_off, int n_lines,
                                                                int64_t cap_rows) {
+  pdl_wait();
   int64_t rows = stat_off[n_lines];
   if (rows > cap_rows) rows = cap_rows;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {

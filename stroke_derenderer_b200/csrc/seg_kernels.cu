@@ -828,6 +828,18 @@ static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
   return off;
 }
 
+// launch with programmatic stream serialization (the kernel calls pdl_wait() before it touches its predecessor's output)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // label (+ stats) with the warp-per-strip kernels
 static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t blk_total, int32_t* d_labels,
                         int32_t* d_num, int64_t* d_stat_off, int32_t* d_stats, int64_t cap_rows, void* d_work, cudaStream_t s) {
@@ -854,16 +866,16 @@ static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lin
   ccl_warp_label_kernel<<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
   SD_LAUNCH_CHECK("ccl_warp_label_kernel");
   if (stage < 2) return SD_OK;
-  ccl_seam_merge_kernel<<<ceil_div((int64_t)strips * 64, 256), 256, 0, s>>>(w, strips);
+  launch_pdl(ccl_seam_merge_kernel, dim3((unsigned)ceil_div((int64_t)strips * 64, 256)), dim3(256), 0, s, w, strips);
   SD_LAUNCH_CHECK("ccl_seam_merge_kernel");
   if (stage < 3) return SD_OK;
-  ccl_line_kernel<<<n_lines, 1024, 0, s>>>(d_lines, n_lines, w, d_num, d_stat_off);
+  launch_pdl(ccl_line_kernel, dim3(n_lines), dim3(1024), 0, s, d_lines, n_lines, w, d_num, d_stat_off);
   SD_LAUNCH_CHECK("ccl_line_kernel");
   if (stage < 4) return SD_OK;
-  ccl_strip_write2_kernel<<<strips, 256, 0, s>>>(d_lines, n_lines, w, d_labels, d_stat_off, d_stats, cap_rows);
+  launch_pdl(ccl_strip_write2_kernel, dim3(strips), dim3(256), 0, s, d_lines, n_lines, w, d_labels, (const int64_t*)d_stat_off, d_stats, cap_rows);
   SD_LAUNCH_CHECK("ccl_strip_write2_kernel");
   if (d_stats && cap_rows > 0) {
-    ccl_stats_finish_kernel<<<sms * 2, 256, 0, s>>>(d_stats, d_stat_off, n_lines, cap_rows);
+    launch_pdl(ccl_stats_finish_kernel, dim3(sms * 2), dim3(256), 0, s, d_stats, (const int64_t*)d_stat_off, n_lines, cap_rows);
     SD_LAUNCH_CHECK("ccl_stats_finish_kernel");
   }
   return SD_OK;
