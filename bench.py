@@ -356,6 +356,20 @@ def run_gpu(args):
                                 "note": "labels + the cv2 stats rows in one pass (what the pipeline runs); same 5 B/px algorithmic bytes"},
             "glue": "none: reconstruct_images is fused into the UNet head (tiles OR their thresholded columns into the line planes)",
             "peak_GBps": hb}
+        # the same chain over ALL lines of the job (config 3: 512 lines): the fixed costs of the four launches and the
+        # partial second wave of the warp-per-strip label kernel weigh less
+        if len(images) > n_hbm:
+            bt_all = S.plan_batch([im.shape[1] for im in images], torch.device("cuda", local))
+            planes_all = (torch.from_numpy(np.concatenate([np.pad(ink_mask(im) * 255, ((0, 0), (0, int(ln["pitch"]) - im.shape[1]))).reshape(-1)
+                                                           for im, ln in zip(images, bt_all.lines)])).to(torch.device("cuda", local)))
+            work_all = torch.empty(_lib.lib().sd_ccl_workspace_bytes(bt_all.blk_total, bt_all.n_lines), dtype=torch.uint8, device="cuda")
+            t_all = ev_time(lambda: S.ccl_label(bt_all, planes_all, work_all))
+            t_alls = ev_time(lambda: S.ccl_label_stats(bt_all, planes_all, S.stats_capacity(bt_all), work_all))
+            px_all = 128 * int(sum(bt_all.widths))
+            extra["hbm_stages"]["ccl_label_whole_job"] = {"ms": t_all, "GBps": 5 * px_all / t_all / 1e6, "frac": 5 * px_all / t_all / 1e6 / hb,
+                                                          "sample": f"all {bt_all.n_lines} lines of the job, {px_all} px"}
+            extra["hbm_stages"]["ccl_label_stats_whole_job"] = {"ms": t_alls, "GBps": 5 * px_all / t_alls / 1e6, "frac": 5 * px_all / t_alls / 1e6 / hb}
+            del planes_all, work_all
         # BASELINE config 5 (CCL / clustering-bound stress): 64 dense 128x16384 masks (~800 k islands) in one launch
         from stroke_derenderer_b200.synth import synth_dense_mask
         n5 = 64

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--what", default="all", choices=["all", "unet", "seg", "dense"])
     ap.add_argument("--tiles", type=int, default=128)
     ap.add_argument("--lines", type=int, default=64)
+    ap.add_argument("--sustain-reps", type=int, default=60, help="back-to-back UNet passes of the power-capped steady-state timing")
     args = ap.parse_args()
     _lib.require_cuda()
     dev = torch.device("cuda", 0)
@@ -59,7 +60,7 @@ def main():
         if batch.n_tiles < nt:
             raise SystemExit(f"--lines {args.lines} give {batch.n_tiles} tiles, fewer than --tiles {nt}")
         out["unet_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5))
-        out["unet_sustained_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5), reps=60)   # power-capped steady state
+        out["unet_sustained_ms"] = ev(lambda: eng.forward_into(tiles[:nt], masks, 0.5), reps=args.sustain_reps)   # power-capped steady state
         for small in (37, 64):
             if small < nt:
                 out[f"unet_ms_{small}tiles"] = ev(lambda: eng.forward_into(tiles[:small], masks, 0.5), reps=5)
