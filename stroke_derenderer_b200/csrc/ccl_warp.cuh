@@ -6,14 +6,17 @@
 //      with coalesced 16-byte loads; every load becomes 8 "even column" + 8 "odd column" bits (dp4a), so pixel row r
 //      of the strip is two 64-bit words Xe / Xo whose bit k is the left / right pixel of block k.  Lane L owns block
 //      rows 2L and 2L+1: occupancy, horizontal links, run starts and the contacts with the block row above are
-//      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row).  Every run
-//      first takes ONE contact with the row above as its parent (plain stores), pointer jumping flattens the resulting
-//      forest (depth halves per round, no divergence), and only the contacts that are left — where two trees meet —
-//      are real unions: shared-memory compare-and-swaps on roots only (min-root: the root of a component is its first
-//      block in raster order, which is what OpenCV's numbering sorts by), finds halve their paths.  Outputs per strip: the Xe / Xo words (2 KB), the
-//      run-start masks (512 B) and one 16-bit root per run (bit 15 = the root touches a neighbouring strip):
-//      ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that touch no other strip are final
-//      (root bitmap); the others register in the sparse global parent array.
+//      plain 64-bit logic.  Union-find nodes are RUNS (maximal chains of linked blocks of one block row), numbered
+//      by their ORDINAL in block-row-major order (= raster order of their first blocks, so the smallest ordinal of a
+//      component is its first block in raster order, which is what OpenCV's numbering sorts by).  Every run first
+//      takes ONE contact with the row above as its parent (plain stores), pointer jumping — lane-balanced over the
+//      ordinals — flattens the resulting forest (depth halves per round), and only the contacts that are left, where
+//      two trees meet, are real unions: shared-memory compare-and-swaps on roots only, finds halve their paths.
+//      Parents are 16-bit and dense (4 KB for up to 2048 runs: 32 resident warps per SM; a strip with more runs —
+//      salt-and-pepper noise — keeps its parents in a global scratch array, same code).  Outputs per strip: the
+//      Xe / Xo words (2 KB), the run-start masks (512 B) and one 16-bit root ordinal per run (bit 15 = the root
+//      touches a neighbouring strip): ~0.2 B/px instead of the 0.5 B/px per-block records of round 1.  Roots that
+//      touch no other strip are final (root bitmap); the others register in the sparse global parent array.
 //   2. ccl_seam_merge_kernel (thread = seam block row): 8-connectivity across strip seams on the sparse global parents.
 //      ccl_line_kernel (CTA = line): seam roots that survived the merges enter the root bitmap; exclusive scan of the
 //      bitmap (label = 1 + #roots before the root), island count; the last CTA to finish also scans the counts of all
@@ -37,7 +40,8 @@ struct CclWarpWork {
   int* prefix;          // [blk_total / 32]  exclusive count of root bits before this word, per line
   uint4* pix;           // [strips][128]     {Xe.lo, Xe.hi, Xo.lo, Xo.hi} of every pixel row of the strip
   uint2* rs;            // [strips][64]      run-start mask of every block row
-  uint16_t* roots;      // [strips][4096]    one entry per run, block-row major: local root block | touch << 15
+  uint16_t* roots;      // [strips][4096]    one entry per run, block-row major: ordinal of its root run | touch << 15
+  uint16_t* parent_fb;  // [strips][4096]    local parents of a strip with more than kMaxSmemRuns runs (rare: noise)
   int* bnd_root;        // [strips][2][64]   global index of the root of each seam block (left / right column), -1 if none
   uint32_t* bnd_bits;   // [strips][2][4]    seam pixel columns: bit L of word r = pixel row 4L + r
   unsigned int* ticket; // [1]               lines finished (the last line CTA builds the stats offsets)
@@ -65,9 +69,13 @@ __device__ __forceinline__ int cw_run_start(uint64_t rs, int k) { return 63 - __
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Union-find over the runs of one strip, in shared memory.  Parents are 16-bit (node ids are < 4096): 8 KB per strip
-// instead of 16 KB, which is what bounds the number of resident warps.
+// Union-find over the runs of one strip.  Parents are 16-bit and indexed by run ordinal: 4 KB of shared memory per strip
+// for up to kMaxSmemRuns runs, which is what bounds the number of resident warps (the worst case, 4096 runs, is served
+// from global memory through the same generic pointer).
 typedef unsigned short cw_node_t;
+constexpr int kMaxSmemRuns = 2048;
+// ordinal (within its block row, 0-based) of the run that owns block k: run starts at or below k, minus one
+__device__ __forceinline__ int cw_run_index(uint64_t rs, int k) { return __popcll(rs & ((2ull << k) - 1ull)) - 1; }
 // find with path halving.  Safe while unions are in flight because links are only ever created by a compare-and-swap
 // on a ROOT (below): a non-root entry is never the target of a union, so re-pointing it at its grandparent (an
 // ancestor for ever, parents only move towards the root) cannot undo a link; roots are never written here.
@@ -110,41 +118,55 @@ __device__ __forceinline__ CwContacts cw_contact_masks(uint64_t Te, uint64_t To,
   c.vl = vl; c.vr = vr;
   return c;
 }
-// Phase A: every run of the row takes its FIRST contact with the row above as its parent (a plain store: the entry
-// belongs to this lane alone, and a link always points to a smaller node id, so the forest is acyclic and a tree's root is
-// its smallest node = the component's first block in raster order).  The contact is removed from the masks; what is left
-// in them are the places where two trees meet (the bottom of a "V"), a small minority on handwriting.
-__device__ __forceinline__ void cw_link_first(cw_node_t* parent, uint16_t*& list, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts& c) {
-  for (uint64_t t = rs; t; t &= t - 1) {
+// Phase A: every run of the row (ordinals off, off + 1, ...) takes its FIRST contact with the row above (whose runs
+// start at ordinal offU) as its parent: a plain store, the entry belongs to this lane alone, and a link always points to
+// a smaller ordinal, so the forest is acyclic and a tree's root is its smallest run = the component's first block in
+// raster order.  The contact is removed from the masks; what is left in them are the places where two trees meet (the
+// bottom of a "V"), a small minority on handwriting.
+__device__ __forceinline__ void cw_link_first(cw_node_t* parent, int off, int offU, uint64_t rs, uint64_t rsU, CwContacts& c) {
+  for (uint64_t t = rs; t; t &= t - 1, ++off) {
     const int k = __ffsll((long long)t) - 1;
     const uint64_t above = t & (t - 1);                                              // run starts to the right of k
     const uint64_t ext = (above ? ((above & (~above + 1ull)) - 1ull) : ~0ull) & ~((1ull << k) - 1ull);   // blocks k .. next start - 1
     const uint64_t cu = c.vu & ext, cl = c.vl & ext, cr = c.vr & ext;
-    int node = base + k;
-    if (cu) { const int j = __ffsll((long long)cu) - 1; c.vu &= ~(1ull << j); node = baseU + cw_run_start(rsU, j); }
-    else if (cl) { const int j = __ffsll((long long)cl) - 1; c.vl &= ~(1ull << j); node = baseU + cw_run_start(rsU, j - 1); }
-    else if (cr) { const int j = __ffsll((long long)cr) - 1; c.vr &= ~(1ull << j); node = baseU + cw_run_start(rsU, j + 1); }
-    parent[base + k] = (cw_node_t)node;
-    *list++ = (uint16_t)(base + k);                          // compact run list, block-row major: the balanced phases walk it
+    int node = off;
+    if (cu) { const int j = __ffsll((long long)cu) - 1; c.vu &= ~(1ull << j); node = offU + cw_run_index(rsU, j); }
+    else if (cl) { const int j = __ffsll((long long)cl) - 1; c.vl &= ~(1ull << j); node = offU + cw_run_index(rsU, j - 1); }
+    else if (cr) { const int j = __ffsll((long long)cr) - 1; c.vr &= ~(1ull << j); node = offU + cw_run_index(rsU, j + 1); }
+    parent[off] = (cw_node_t)node;
   }
 }
 // Phase C: the contacts phase A left over, as real unions (compare-and-swap on roots) over the flattened trees
-__device__ __forceinline__ void cw_union_rest(cw_node_t* parent, int base, int baseU, uint64_t rs, uint64_t rsU, CwContacts c) {
+__device__ __forceinline__ void cw_union_rest(cw_node_t* parent, int off, int offU, uint64_t rs, uint64_t rsU, CwContacts c) {
   uint64_t vu = c.vu, vl = c.vl, vr = c.vr;
   while (vu | vl | vr) {
     int k, dk;
     if (vu) { k = __ffsll((long long)vu) - 1; vu &= vu - 1; dk = 0; }
     else if (vl) { k = __ffsll((long long)vl) - 1; vl &= vl - 1; dk = -1; }
     else { k = __ffsll((long long)vr) - 1; vr &= vr - 1; dk = 1; }
-    cw_union(parent, base + cw_run_start(rs, k), baseU + cw_run_start(rsU, k + dk));
+    cw_union(parent, off + cw_run_index(rs, k), offU + cw_run_index(rsU, k + dk));
   }
+}
+// position (block row * 64 + block column) of the run with ordinal r: row by bisection of the row offsets, column = the
+// (r - rowoff[row])-th run start of that row.  Only used for the few roots that touch a strip seam.
+__device__ __forceinline__ int cw_run_position(const uint16_t* rowoff, const uint64_t* rs, int r) {
+  int lo = 0;
+#pragma unroll
+  for (int step = 32; step; step >>= 1) if (lo + step < 64 && rowoff[lo + step] <= r) lo += step;   // last row with rowoff <= r
+  // rows without runs share the offset of the next row: step back is impossible (we took the LAST such row, which owns run r)
+  uint64_t m = rs[lo];
+  for (int n = r - rowoff[lo]; n > 0; --n) m &= m - 1;
+  return lo * 64 + __ffsll((long long)m) - 1;
 }
 
 struct __align__(16) CwLabelSmem {
-  cw_node_t parent[kStripBlocks];  // node = block row * 64 + first block of the run
-  uint8_t e[128][8], o[128][8];    // Xe / Xo of every pixel row, one byte per 16-pixel load; once they are in registers the
-                                   // first 512 B hold the root bits of the strip (bit = block is an interior component root)
-  uint32_t touch[kStripBlocks / 32];
+  union {
+    cw_node_t parent[kMaxSmemRuns];             // by run ordinal
+    struct { uint8_t e[128][8], o[128][8]; } x; // Xe / Xo of every pixel row, one byte per 16-pixel load (until they are in registers)
+  };
+  uint64_t rs[64];                              // run starts of every block row
+  uint32_t touch[kStripBlocks / 32];            // by run ordinal: the root touches a neighbouring strip
+  uint16_t rowoff[64];                          // first ordinal of every block row
 };
 
 // warp-cooperative: #lines whose block offset is <= off, minus one (lines are sorted by offset)
@@ -220,15 +242,15 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
         const int row = (b * 8 + i) * 4 + (lane >> 3);
         uint32_t e, o;
         cw_bits16(v[i], e, o);
-        sm.e[row][lane & 7] = (uint8_t)e;
-        sm.o[row][lane & 7] = (uint8_t)o;
+        sm.x.e[row][lane & 7] = (uint8_t)e;
+        sm.x.o[row][lane & 7] = (uint8_t)o;
       }
     }
     sm.touch[lane] = 0u; sm.touch[lane + 32] = 0u; sm.touch[lane + 64] = 0u; sm.touch[lane + 96] = 0u;
     __syncwarp();
     // ---- lane L: block rows a = 2L (pixel rows 4L, 4L+1) and b = 2L+1 (4L+2, 4L+3) ----
-    const uint64_t* E = reinterpret_cast<const uint64_t*>(&sm.e[4 * lane][0]);
-    const uint64_t* O = reinterpret_cast<const uint64_t*>(&sm.o[4 * lane][0]);
+    const uint64_t* E = reinterpret_cast<const uint64_t*>(&sm.x.e[4 * lane][0]);
+    const uint64_t* O = reinterpret_cast<const uint64_t*>(&sm.x.o[4 * lane][0]);
     const uint64_t Tea = E[0], Bea = E[1], Teb = E[2], Beb = E[3];
     const uint64_t Toa = O[0], Boa = O[1], Tob = O[2], Bob = O[3];
     {
@@ -244,69 +266,68 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     const uint64_t rsa = occa & ~hla, rsb = occb & ~hlb;                  // run starts
     w.rs[(int64_t)strip * 64 + 2 * lane] = make_uint2((uint32_t)rsa, (uint32_t)(rsa >> 32));
     w.rs[(int64_t)strip * 64 + 2 * lane + 1] = make_uint2((uint32_t)rsb, (uint32_t)(rsb >> 32));
-    const int na = 2 * lane * 64, nb = na + 64;                           // node bases of the two block rows
-    // the block row above row a belongs to lane L-1 (its row b)
-    const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
-    const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
-    CwContacts ca = cw_contact_masks(Tea, Toa, Ue, Uo, hla, hlU);
-    CwContacts cb = cw_contact_masks(Teb, Tob, Bea, Boa, hlb, hla);
-    // run ordinals: the runs of the strip in block-row-major order (the order of the root entries the write kernel reads)
-    const int cnt = __popcll(rsa) + __popcll(rsb);
+    // run ordinals: the runs of the strip in block-row-major order (= the order of the root entries the write kernel reads)
+    const int cnt_a = __popcll(rsa), cnt = cnt_a + __popcll(rsb);
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     const int n_runs = __shfl_sync(0xffffffffu, inc, 31);
-    uint16_t* const list = w.roots + (int64_t)strip * kStripBlocks;     // node ids now, root entries at the end (same slots)
-    uint32_t* const rootw = reinterpret_cast<uint32_t*>(&sm.e[0][0]);
-    __syncwarp();                                                          // every lane has its Xe / Xo words in registers
-    rootw[lane] = 0u; rootw[lane + 32] = 0u; rootw[lane + 64] = 0u; rootw[lane + 96] = 0u;
-    // phase A: first contact of every run -> its parent (stores only); the run joins the list
-    {
-      uint16_t* lp = list + (inc - cnt);
-      cw_link_first(sm.parent, lp, na, na - 64, rsa, rsU, ca);
-      cw_link_first(sm.parent, lp, nb, na, rsb, rsa, cb);
-    }
+    const int oa = inc - cnt, ob = oa + cnt_a;                            // first ordinals of the two block rows
+    // the block row above row a belongs to lane L-1 (its row b)
+    const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
+    const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
+    const int oU = __shfl_up_sync(0xffffffffu, ob, 1);
+    CwContacts ca = cw_contact_masks(Tea, Toa, Ue, Uo, hla, hlU);
+    CwContacts cb = cw_contact_masks(Teb, Tob, Bea, Boa, hlb, hla);
+    __syncwarp();                                                          // every lane has its Xe / Xo words: the parents may overwrite them
+    sm.rs[2 * lane] = rsa; sm.rs[2 * lane + 1] = rsb;
+    sm.rowoff[2 * lane] = (uint16_t)oa; sm.rowoff[2 * lane + 1] = (uint16_t)ob;
+    cw_node_t* const par = n_runs <= kMaxSmemRuns ? sm.parent : w.parent_fb + (int64_t)strip * kStripBlocks;
+    // phase A: first contact of every run -> its parent (stores only)
+    cw_link_first(par, oa, oU, rsa, rsU, ca);
+    cw_link_first(par, ob, oa, rsb, rsa, cb);
     // phase B: pointer jumping flattens the forest (a vertical stroke is a chain of up to 64 runs: depth halves per
-    // round).  Lane-balanced over the run list: text fills a few block rows with many runs and leaves the rest empty.
+    // round).  Lane-balanced over the ordinals: text fills a few block rows with many runs and leaves the rest empty.
     {
-      volatile cw_node_t* vp = sm.parent;
+      volatile cw_node_t* vp = par;
 #pragma unroll 1
       for (int round = 0; round < 6; ++round) {
         __syncwarp();
         bool changed = false;
         for (int j = lane; j < n_runs; j += 32) {
-          const int x = list[j];
-          const int pa = vp[x];
+          const int pa = vp[j];
           const int ga = vp[pa];
-          if (ga != pa) { vp[x] = (cw_node_t)ga; changed = true; }
+          if (ga != pa) { vp[j] = (cw_node_t)ga; changed = true; }
         }
         if (!__any_sync(0xffffffffu, changed)) break;
       }
     }
     __syncwarp();
     // phase C: the remaining contacts join trees
-    cw_union_rest(sm.parent, na, na - 64, rsa, rsU, ca);
-    cw_union_rest(sm.parent, nb, na, rsb, rsa, cb);
+    cw_union_rest(par, oa, oU, rsa, rsU, ca);
+    cw_union_rest(par, ob, oa, rsb, rsa, cb);
     __syncwarp();
     // ---- seam blocks: their roots touch a neighbouring strip ----
     const int gbase = (int)ln.blk_off + s * 64;                          // global index of local block i: gbase + (i >> 6) * bw + (i & 63)
     {
-      volatile cw_node_t* vp = sm.parent;
+      volatile cw_node_t* vp = par;
       int* br = w.bnd_root + (int64_t)strip * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint64_t occ = h ? occb : occa, rs = h ? rsb : rsa;
-        const int nbase = h ? nb : na, row = 2 * lane + h;
+        const int off = h ? ob : oa, row = 2 * lane + h;
         int left = -1, right = -1;
         if (s > 0 && (occ & 1ull)) {
-          const int r = cw_find(vp, nbase);                              // block 0 has no left neighbour: it starts its run
+          const int r = cw_find(vp, off);                                // block 0 has no left neighbour: it starts the row's first run
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
-          left = gbase + (r >> 6) * ln.bw + (r & 63);
+          const int pos = cw_run_position(sm.rowoff, sm.rs, r);
+          left = gbase + (pos >> 6) * ln.bw + (pos & 63);
         }
         if (s < ns - 1 && (occ >> 63)) {
-          const int r = cw_find(vp, nbase + cw_run_start(rs, 63));
+          const int r = cw_find(vp, off + cw_run_index(rs, 63));
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
-          right = gbase + (r >> 6) * ln.bw + (r & 63);
+          const int pos = cw_run_position(sm.rowoff, sm.rs, r);
+          right = gbase + (pos >> 6) * ln.bw + (pos & 63);
         }
         br[row] = left; br[64 + row] = right;
       }
@@ -322,24 +343,30 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
       }
     }
     __syncwarp();
-    // ---- one root entry per run (block-row major, lane-balanced over the list); interior roots -> root bits, seam roots
-    //      -> global parents ----
+    // ---- one root entry per run (lane-balanced over the ordinals) ----
     {
-      volatile cw_node_t* vp = sm.parent;
+      volatile cw_node_t* vp = par;
+      uint16_t* out = w.roots + (int64_t)strip * kStripBlocks;
       for (int j = lane; j < n_runs; j += 32) {
-        const int x = list[j];
-        const int r = cw_find(vp, x);                                      // every union is done: roots are final
+        const int r = cw_find(vp, j);                                      // every union is done: roots are final
         const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
-        list[j] = (uint16_t)(r | (tch << 15));
-        if (r == x) {
-          if (tch) { const int g = gbase + (x >> 6) * ln.bw + (x & 63); w.parent[g] = g; }
-          else atomicOr(&rootw[x >> 5], 1u << (x & 31));
-        }
+        out[j] = (uint16_t)(r | (tch << 15));
       }
-      __syncwarp();
-      uint32_t* bm = w.bitmap + (ln.blk_off >> 5) + (int64_t)(2 * lane) * (ln.bw >> 5) + s * 2;
-      *reinterpret_cast<uint2*>(bm) = make_uint2(rootw[4 * lane], rootw[4 * lane + 1]);
-      *reinterpret_cast<uint2*>(bm + (ln.bw >> 5)) = make_uint2(rootw[4 * lane + 2], rootw[4 * lane + 3]);
+      // ---- the roots themselves (row-owned: the position is known): interior roots -> bitmap, seam roots -> global parents
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 2 * lane + h;
+        int o = h ? ob : oa;
+        uint64_t rootbits = 0ull;
+        for (uint64_t t = h ? rsb : rsa; t; t &= t - 1, ++o) {
+          if (vp[o] != o) continue;
+          const int k = __ffsll((long long)t) - 1;
+          if ((sm.touch[o >> 5] >> (o & 31)) & 1u) { const int g = gbase + row * ln.bw + k; w.parent[g] = g; }
+          else rootbits |= 1ull << k;
+        }
+        *reinterpret_cast<uint2*>(w.bitmap + (ln.blk_off >> 5) + (int64_t)row * (ln.bw >> 5) + s * 2) =
+            make_uint2((uint32_t)rootbits, (uint32_t)(rootbits >> 32));
+      }
     }
     __syncwarp();                                                          // shared memory is reused by the next strip
   }
@@ -441,7 +468,7 @@ __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restric
 }
 
 struct __align__(16) CwWriteSmem {
-  int lab[kStripBlocks];           // node (block row * 64 + first block of the run) -> final label
+  int lab[kStripBlocks];           // run ordinal -> final label
   uint4 pix[128];
   uint2 rs[64];
   int rowoff[64];                  // first run ordinal of every block row
@@ -497,18 +524,19 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
   const uint2 r2 = sm.rs[br];
   const uint64_t rs = ((uint64_t)r2.y << 32) | r2.x;
   const uint64_t mine = rs & (0xFFFFull << (16 * q));                    // run starts inside this thread's 16 blocks
-  const uint16_t* rt = w.roots + (int64_t)strip * kStripBlocks + sm.rowoff[br] + __popcll(rs & ((1ull << (16 * q)) - 1ull));
-  const int nbase = br * 64;
-  // pass 1: runs that are roots compute their final label
+  const int ord0 = sm.rowoff[br] + __popcll(rs & ((1ull << (16 * q)) - 1ull));     // ordinal of this thread's first run
+  const uint16_t* rt = w.roots + (int64_t)strip * kStripBlocks + ord0;
+  // pass 1: runs that are roots (their entry is their own ordinal) compute their final label from their position
   {
     const uint16_t* p = rt;
-    for (uint64_t t = mine; t; t &= t - 1) {
-      const int k = __ffsll((long long)t) - 1;
+    int ord = ord0;
+    for (uint64_t t = mine; t; t &= t - 1, ++ord) {
       const uint32_t rr = __ldg(p++);
-      if ((int)(rr & 0x7fffu) == nbase + k) {
+      if ((int)(rr & 0x7fffu) == ord) {
+        const int k = __ffsll((long long)t) - 1;
         int g = gbase + br * ln.bw + k;
         if (rr >> 15) g = cw_uf_find(w.parent, g);
-        sm.lab[nbase + k] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
+        sm.lab[ord] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
       }
     }
   }
@@ -522,11 +550,12 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
     const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
     const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
     const uint64_t occ = Te | To | Be | Bo;
-    for (uint64_t t = mine; t; t &= t - 1) {
+    int ord = ord0;
+    for (uint64_t t = mine; t; t &= t - 1, ++ord) {
       const int k = __ffsll((long long)t) - 1;
       const int root = (int)(__ldg(p++) & 0x7fffu);
       const int lab = sm.lab[root];
-      if (root != nbase + k) sm.lab[nbase + k] = lab;
+      if (root != ord) sm.lab[ord] = lab;
       if (do_stats) {
         // blocks of the run: occupied blocks from k up to the next run start of the ROW (it may lie in another quarter)
         const uint64_t above = rs & ~((2ull << k) - 1ull);
@@ -554,14 +583,15 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
     const int b = wp * 8 + i;
     const uint2 q2 = sm.rs[b];
     const uint64_t rsb = ((uint64_t)q2.y << 32) | q2.x;
+    const int off = sm.rowoff[b];
     const uint4 t4 = sm.pix[2 * b], b4 = sm.pix[2 * b + 1];
     const uint64_t Te = ((uint64_t)t4.y << 32) | t4.x, To = ((uint64_t)t4.w << 32) | t4.z;
     const uint64_t Be = ((uint64_t)b4.y << 32) | b4.x, Bo = ((uint64_t)b4.w << 32) | b4.z;
     const uint32_t te = (uint32_t)(Te >> (2 * lane)) & 3u, to = (uint32_t)(To >> (2 * lane)) & 3u;
     const uint32_t be = (uint32_t)(Be >> (2 * lane)) & 3u, bo = (uint32_t)(Bo >> (2 * lane)) & 3u;
     int l0 = 0, l1 = 0;
-    if ((te | to | be | bo) & 1u) l0 = sm.lab[b * 64 + cw_run_start(rsb, 2 * lane)];
-    if ((te | to | be | bo) & 2u) l1 = sm.lab[b * 64 + cw_run_start(rsb, 2 * lane + 1)];
+    if ((te | to | be | bo) & 1u) l0 = sm.lab[off + cw_run_index(rsb, 2 * lane)];
+    if ((te | to | be | bo) & 2u) l1 = sm.lab[off + cw_run_index(rsb, 2 * lane + 1)];
     int4 a, c;
     a.x = (te & 1u) ? l0 : 0; a.y = (to & 1u) ? l0 : 0; a.z = (te & 2u) ? l1 : 0; a.w = (to & 2u) ? l1 : 0;
     c.x = (be & 1u) ? l0 : 0; c.y = (bo & 1u) ? l0 : 0; c.z = (be & 2u) ? l1 : 0; c.w = (bo & 2u) ? l1 : 0;

@@ -820,10 +820,11 @@ static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
   uint4* pix = reinterpret_cast<uint4*>(take(strips * 128 * 16));
   uint2* rs = reinterpret_cast<uint2*>(take(strips * 64 * 8));
   uint16_t* roots = reinterpret_cast<uint16_t*>(take(strips * kStripBlocks * 2));
+  uint16_t* parent_fb = reinterpret_cast<uint16_t*>(take(strips * kStripBlocks * 2));
   int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
   uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
   unsigned int* ticket = reinterpret_cast<unsigned int*>(take(256));
-  if (w) { w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots;
+  if (w) { w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots; w->parent_fb = parent_fb;
            w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; w->ticket = ticket; }
   return off;
 }

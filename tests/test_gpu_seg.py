@@ -187,6 +187,30 @@ def test_ccl_random_masks_vs_cv2(cuda_device):
         assert np.array_equal(stats[stat_off[i]:stat_off[i + 1]], st[1:]), i
 
 
+def test_ccl_more_runs_than_shared_parents(cuda_device):
+    """Strips with more than 2048 runs (every 2x2 block its own run: pixels on even columns only) keep their union-find
+    parents in the global scratch array instead of shared memory; labels, counts and stats stay cv2's."""
+    import cv2
+    rng = np.random.default_rng(9)
+    yy, xx = np.mgrid[0:128, 0:700]
+    stripes = (xx % 2 == 0).astype(np.uint8)                                   # 64 runs per block row, 4096 per strip
+    masks = [stripes, stripes * (yy % 4 < 2), stripes * (rng.random((128, 700)) < 0.7),
+             np.maximum(stripes * (yy < 70), (rng.random((128, 700)) < 0.3) * (yy >= 60)).astype(np.uint8),
+             ((xx + yy) % 2 == 0).astype(np.uint8), (xx % 4 == 0).astype(np.uint8)]
+    masks = [np.ascontiguousarray(m, dtype=np.uint8) for m in masks]
+    batch, planes = _pack_masks(masks)
+    labels, meta, stats = S.ccl_label_stats(batch, planes, 400_000)
+    n = batch.n_lines
+    stat_off = meta[:8 * (n + 1)].view(torch.int64).cpu().numpy()
+    num = meta[8 * (n + 1):].view(torch.int32).cpu().numpy()
+    stats = stats.cpu().numpy()
+    for i, m in enumerate(masks):
+        cn, ref, st, _ = cv2.connectedComponentsWithStats(m)
+        assert int(num[i]) == cn, i
+        assert np.array_equal(batch.plane(labels, i).cpu().numpy(), ref), i
+        assert np.array_equal(stats[stat_off[i]:stat_off[i + 1]], st[1:]), i
+
+
 def test_ccl_dense_config5(cuda_device):
     import cv2
     masks = [synth_dense_mask(16384, 0.003, 0), synth_dense_mask(16384, 0.01, 1)]
