@@ -228,6 +228,9 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     const sd_line ln = L[cw_find_line(L, n_lines, blk0, lane)];
     const int s = (int)((blk0 - ln.blk_off) >> 12), ns = ln.bw >> 6;
     const uint8_t* src = mask + ln.px_off + s * 128;
+    // all 128 rows of the strip on their way to L2 before the first batch of loads waits (a row = one 128-byte line)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)(i * 32 + lane) * ln.pitch));
     // ---- mask bytes -> Xe / Xo bits (a warp instruction moves 4 rows x 128 B) ----
 #pragma unroll 1
     for (int b = 0; b < 4; ++b) {
