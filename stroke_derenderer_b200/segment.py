@@ -525,6 +525,7 @@ class Segmenter:
         self.margin = margin
         self.staging = PinnedStaging()
         self._streams = None
+        self._rows_per_px = 0.0          # densest batch seen so far (islands per pixel): sizes the stats reserve of the next one
 
     @classmethod
     def for_engine(cls, engine: UNetEngine, bin_thr: float = 0.5) -> "Segmenter":
@@ -585,14 +586,18 @@ class Segmenter:
             n = batch.n_lines
             # labels and the cv2 stats rows in ONE pass (no second read of the labels); counts, row offsets and a
             # first slice of the rows come back in one D2H + one sync
-            cap = stats_capacity(batch)
+            # the reserve follows the densest batch seen so far (+50 %): the masks of one job look alike, so only the
+            # first dense batch pays the second run
+            want = int(1.5 * self._rows_per_px * batch.px_total) + 1024
+            cap = max(stats_capacity(batch), want)
             labels, meta, stats = ccl_label_stats(batch, planes, cap)
-            spec = min(cap, self.SPEC_ROWS)
+            spec = min(cap, max(self.SPEC_ROWS, want))
             h_meta = copy_d2h(self.staging.get((key, "meta"), meta.numel()), meta, self.device)
             h_spec = copy_d2h(self.staging.get((key, "spec"), spec * 20), stats[:spec], self.device)
             stream.synchronize()
             stat_off = h_meta[:8 * (n + 1)].view(np.int64).copy()
             rows = int(stat_off[-1])
+            self._rows_per_px = max(self._rows_per_px, rows / max(batch.px_total, 1))
             if rows > cap:                            # denser than the reserve: once more with the exact room
                 labels, meta, stats = ccl_label_stats(batch, planes, rows)
                 cap, spec = rows, 0
