@@ -31,6 +31,9 @@
 namespace sd {
 
 constexpr int kCw = 4;                       // warps (strips) per CTA
+#ifndef SD_CCL_OCC_DEFAULT
+#define SD_CCL_OCC_DEFAULT 8                 // label CTAs per SM the default instantiation is compiled for (SD_CCL_OCC overrides)
+#endif
 constexpr int kBigCoord = 0x3fffffff;        // stats rows keep (kBigCoord - max) so that every field is a min / add
 constexpr int kStatFill = 0x7f7f7f7f;        // cudaMemsetAsync(0x7f) start value of every stats field
 
@@ -41,7 +44,7 @@ struct CclWarpWork {
   uint4* pix;           // [strips][128]     {Xe.lo, Xe.hi, Xo.lo, Xo.hi} of every pixel row of the strip
   uint2* rs;            // [strips][64]      run-start mask of every block row
   uint16_t* roots;      // [strips][4096]    one entry per run, block-row major: ordinal of its root run | touch << 15
-  uint16_t* parent_fb;  // [strips][4096]    local parents of a strip with more than kMaxSmemRuns runs (rare: noise)
+  uint16_t* parent_fb;  // [strips][4096]    local parents of a strip with more runs than fit in shared memory (rare: noise)
   int* bnd_root;        // [strips][2][64]   global index of the root of each seam block (left / right column), -1 if none
   uint32_t* bnd_bits;   // [strips][2][4]    seam pixel columns: bit L of word r = pixel row 4L + r
   unsigned int* ticket; // [1]               lines finished (the last line CTA builds the stats offsets)
@@ -70,10 +73,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Union-find over the runs of one strip.  Parents are 16-bit and indexed by run ordinal: 4 KB of shared memory per strip
-// for up to kMaxSmemRuns runs, which is what bounds the number of resident warps (the worst case, 4096 runs, is served
+// for up to MAXRUNS = 2048 runs, which is what bounds the number of resident warps (the worst case, 4096 runs, is served
 // from global memory through the same generic pointer).
 typedef unsigned short cw_node_t;
-constexpr int kMaxSmemRuns = 2048;
 // ordinal (within its block row, 0-based) of the run that owns block k: run starts at or below k, minus one
 __device__ __forceinline__ int cw_run_index(uint64_t rs, int k) { return __popcll(rs & ((2ull << k) - 1ull)) - 1; }
 // find with path halving.  Safe while unions are in flight because links are only ever created by a compare-and-swap
@@ -159,9 +161,9 @@ __device__ __forceinline__ int cw_run_position(const uint16_t* rowoff, const uin
   return lo * 64 + __ffsll((long long)m) - 1;
 }
 
-struct __align__(16) CwLabelSmem {
+template <int MAXRUNS> struct __align__(16) CwLabelSmem {
   union {
-    cw_node_t parent[kMaxSmemRuns];             // by run ordinal
+    cw_node_t parent[MAXRUNS];                  // by run ordinal
     struct { uint8_t e[128][8], o[128][8]; } x; // Xe / Xo of every pixel row, one byte per 16-pixel load (until they are in registers)
   };
   uint64_t rs[64];                              // run starts of every block row
@@ -216,11 +218,17 @@ __device__ __forceinline__ void cw_seam_row(const CclWarpWork& w, int64_t sg, in
   if (br < 63 && a1 && cw_col_bit(Rb, 2 * br + 2)) cw_uf_union(w.parent, a, bp);
 }
 
-__global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t* __restrict__ mask, const sd_line* __restrict__ L,
-                                                                  int n_lines, int n_strips, CclWarpWork w) {
+// MINB = resident CTAs per SM the register allocation aims at (8 -> 63 registers, no spills, 32 warps per SM; 10 -> 48
+// registers, 40 warps; 12 -> 40 registers, 48 warps with MAXRUNS = 1536), MAXRUNS = runs whose parents fit in shared memory.
+// Measured (profiles/r02_ccl_occ_merge_ab.json): more resident warps make the kernel SLOWER (36.8 / 46.7 / 50.2 us on 128
+// text lines, 132 / 162 / 164 us on 512): the spills land on the same load/store pipe the union-find already queues on.
+// 8 is the default; SD_CCL_OCC selects the others for A/B runs.
+template <int MINB, int MAXRUNS>
+__global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const uint8_t* __restrict__ mask, const sd_line* __restrict__ L,
+                                                                        int n_lines, int n_strips, CclWarpWork w) {
   extern __shared__ __align__(16) uint8_t cw_smem[];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  CwLabelSmem& sm = reinterpret_cast<CwLabelSmem*>(cw_smem)[wp];
+  CwLabelSmem<MAXRUNS>& sm = reinterpret_cast<CwLabelSmem<MAXRUNS>*>(cw_smem)[wp];
   pdl_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0) *w.ticket = 0u;
   for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(32 * kCw) ccl_warp_label_kernel(const uint8_t*
     __syncwarp();                                                          // every lane has its Xe / Xo words: the parents may overwrite them
     sm.rs[2 * lane] = rsa; sm.rs[2 * lane + 1] = rsb;
     sm.rowoff[2 * lane] = (uint16_t)oa; sm.rowoff[2 * lane + 1] = (uint16_t)ob;
-    cw_node_t* const par = n_runs <= kMaxSmemRuns ? sm.parent : w.parent_fb + (int64_t)strip * kStripBlocks;
+    cw_node_t* const par = n_runs <= MAXRUNS ? sm.parent : w.parent_fb + (int64_t)strip * kStripBlocks;
     // phase A: first contact of every run -> its parent (stores only)
     cw_link_first(par, oa, oU, rsa, rsU, ca);
     cw_link_first(par, ob, oa, rsb, rsa, cb);
@@ -389,12 +397,21 @@ __global__ void __launch_bounds__(256) ccl_seam_merge_kernel(CclWarpWork w, int 
 // CTA = line: seam roots that are still roots after the merges are component roots (root bitmap); then the exclusive
 // scan of the bitmap (label = 1 + #roots before the root), island count; the last CTA to finish turns the counts of all
 // lines into stats row offsets (stat_off[l] = sum over lines < l of (num - 1)).
+// MERGE: the CTA first merges the seams of its own line (lines never share a component, so the seam unions of a line touch
+// only that line's parents): one launch and one dependency edge fewer than ccl_seam_merge_kernel + this kernel.
+template <bool MERGE>
 __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restrict__ L, int n_lines, CclWarpWork w,
                                                         int* __restrict__ num_out, int64_t* __restrict__ stat_off) {
   const int l = blockIdx.x, tid = threadIdx.x;
   const sd_line ln = L[l];
   pdl_launch_dependents();
   pdl_wait();
+  if (MERGE) {
+    const int64_t first = ln.blk_off >> 12;                               // first strip of the line
+    const int n_seam = ((ln.bw >> 6) - 1) * 64;
+    for (int i = tid; i < n_seam; i += blockDim.x) cw_seam_row(w, first + 1 + (i >> 6), i & 63);
+    __syncthreads();                                                      // the unions of this CTA are visible to its mark pass
+  }
   const uint32_t* bitmap = w.bitmap + (ln.blk_off >> 5);
   int* prefix = w.prefix + (ln.blk_off >> 5);
   __shared__ int s_warp[32];

@@ -841,36 +841,60 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// one instantiation of the label kernel: launch geometry for this device, then the launch itself
+template <int MINB, int MAXRUNS>
+static cudaError_t ccl_launch_label(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int strips, const CclWarpWork& w,
+                                    cudaStream_t s) {
+  const int smem_l = kCw * (int)sizeof(CwLabelSmem<MAXRUNS>);
+  static PerDeviceOnce attr_once;
+  static int per_sm_l = 0, sms = 148;
+  if (attr_once.first()) {
+    cudaError_t e = cudaFuncSetAttribute(ccl_warp_label_kernel<MINB, MAXRUNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, ccl_warp_label_kernel<MINB, MAXRUNS>, 32 * kCw, smem_l);
+    if (per_sm_l < 1) per_sm_l = 1;
+  }
+  const int ctas = (strips + kCw - 1) / kCw;
+  ccl_warp_label_kernel<MINB, MAXRUNS><<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
+  return cudaGetLastError();
+}
+
 // label (+ stats) with the warp-per-strip kernels
 static int ccl_warp_run(const uint8_t* d_mask, const sd_line* d_lines, int n_lines, int64_t blk_total, int32_t* d_labels,
                         int32_t* d_num, int64_t* d_stat_off, int32_t* d_stats, int64_t cap_rows, void* d_work, cudaStream_t s) {
   CclWarpWork w;
   ccl_warp_carve(reinterpret_cast<void*>(((uintptr_t)d_work + 255) / 256 * 256), blk_total, &w);
   const int strips = (int)(blk_total / kStripBlocks);
-  const int smem_l = kCw * (int)sizeof(CwLabelSmem);
-  static PerDeviceOnce attr_once;
-  static int per_sm_l = 0, sms = 148;
-  if (attr_once.first()) {
-    SD_CUDA_CHECK(cudaFuncSetAttribute(ccl_warp_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, ccl_warp_label_kernel, 32 * kCw, smem_l);
-    if (per_sm_l < 1) per_sm_l = 1;
-  }
-  const int ctas = (strips + kCw - 1) / kCw;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   if (d_stats && cap_rows > 0) SD_CUDA_CHECK(cudaMemsetAsync(d_stats, 0x7f, (size_t)cap_rows * 20, s));
   // SD_CCL_STAGE=k (debug / profiling): stop after the k-th kernel of the chain, so that CUDA-event times of the call
   // for k = 1..4 give every kernel's steady-state share (tools/ccl_bench.py --stages)
   const char* stage_env = getenv("SD_CCL_STAGE");
   const int stage = stage_env ? atoi(stage_env) : 99;
-  ccl_warp_label_kernel<<<std::min(ctas, sms * per_sm_l), 32 * kCw, smem_l, s>>>(d_mask, d_lines, n_lines, strips, w);
-  SD_LAUNCH_CHECK("ccl_warp_label_kernel");
+  // SD_CCL_OCC = resident label CTAs per SM the kernel is compiled for (8 / 10 / 12, see ccl_warp_label_kernel);
+  // SD_CCL_MERGE=1 folds the seam merges into the line kernel (A/B switches; the defaults are the measured optimum)
+  const char* occ_env = getenv("SD_CCL_OCC");
+  const int occ = occ_env ? atoi(occ_env) : SD_CCL_OCC_DEFAULT;
+  const char* merge_env = getenv("SD_CCL_MERGE");
+  const bool merge_in_line = merge_env ? atoi(merge_env) != 0 : false;   // measured slower (profiles/r02_ccl_occ_merge_ab.json)
+  cudaError_t le;
+  if (occ >= 12) le = ccl_launch_label<12, 1536>(d_mask, d_lines, n_lines, strips, w, s);
+  else if (occ >= 10) le = ccl_launch_label<10, 2048>(d_mask, d_lines, n_lines, strips, w, s);
+  else le = ccl_launch_label<8, 2048>(d_mask, d_lines, n_lines, strips, w, s);
+  if (le != cudaSuccess) { set_error("ccl_warp_label_kernel: %s", cudaGetErrorString(le)); return SD_ECUDA; }
+  count_launch();
   if (stage < 2) return SD_OK;
-  launch_pdl(ccl_seam_merge_kernel, dim3((unsigned)ceil_div((int64_t)strips * 64, 256)), dim3(256), 0, s, w, strips);
-  SD_LAUNCH_CHECK("ccl_seam_merge_kernel");
+  if (!merge_in_line) {
+    launch_pdl(ccl_seam_merge_kernel, dim3((unsigned)ceil_div((int64_t)strips * 64, 256)), dim3(256), 0, s, w, strips);
+    SD_LAUNCH_CHECK("ccl_seam_merge_kernel");
+  }
   if (stage < 3) return SD_OK;
-  launch_pdl(ccl_line_kernel, dim3(n_lines), dim3(1024), 0, s, d_lines, n_lines, w, d_num, d_stat_off);
+  if (merge_in_line) launch_pdl(ccl_line_kernel<true>, dim3(n_lines), dim3(1024), 0, s, d_lines, n_lines, w, d_num, d_stat_off);
+  else launch_pdl(ccl_line_kernel<false>, dim3(n_lines), dim3(1024), 0, s, d_lines, n_lines, w, d_num, d_stat_off);
   SD_LAUNCH_CHECK("ccl_line_kernel");
   if (stage < 4) return SD_OK;
   launch_pdl(ccl_strip_write2_kernel, dim3(strips), dim3(256), 0, s, d_lines, n_lines, w, d_labels, (const int64_t*)d_stat_off, d_stats, cap_rows);

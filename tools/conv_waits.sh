@@ -3,7 +3,8 @@
 # UNet pass, the cycles each warp role spent waiting (code 1 producer, 2 MMA<-epilogue, 3 MMA<-TMA, 4 epilogue<-MMA).
 set -e
 rm -rf /tmp/sdstats && cp -r . /tmp/sdstats && cd /tmp/sdstats
-SD_EXTRA_NVCC_FLAGS=-DSD_CONV_STATS python -m stroke_derenderer_b200.build --force > /dev/null
+export SD_EXTRA_NVCC_FLAGS=-DSD_CONV_STATS      # exported: the build digest covers the flags, the run below must see the same ones
+python -m stroke_derenderer_b200.build --force > /dev/null 2>&1
 "$@" python tools/conv_waits.py 2> /tmp/waits.err | tail -1 > /tmp/waits.json || { tail -5 /tmp/waits.err; exit 1; }
 python - <<'PY'
 import json
