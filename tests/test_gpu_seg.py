@@ -211,6 +211,32 @@ def test_ccl_more_runs_than_shared_parents(cuda_device):
         assert np.array_equal(stats[stat_off[i]:stat_off[i + 1]], st[1:]), i
 
 
+def test_ccl_build_switches_give_the_same_labels(cuda_device, monkeypatch):
+    """The A/B switches of the CCL chain (label kernel compiled for 10 / 12 CTAs per SM, the latter with 1536 shared
+    parents per strip; seam merges folded into the line kernel) are read per call: every variant returns cv2's labels,
+    counts and stats, including on a strip whose runs no longer fit in the smaller parent table."""
+    import cv2
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[0:128, 0:700]
+    masks = [ink_mask(synth_line(3072, seed=77)), (rng.random((128, 1300)) < 0.3).astype(np.uint8),
+             np.ascontiguousarray(((xx % 2 == 0) & (yy % 8 < 3)), dtype=np.uint8),        # 1 536 < runs per strip <= 2 048
+             synth_dense_mask(4096, 0.01, 3)]
+    refs = [cv2.connectedComponentsWithStats(m) for m in masks]
+    batch, planes = _pack_masks(masks)
+    for occ, merge in (("10", "0"), ("12", "0"), ("12", "1"), ("8", "1")):
+        monkeypatch.setenv("SD_CCL_OCC", occ)
+        monkeypatch.setenv("SD_CCL_MERGE", merge)
+        labels, meta, stats = S.ccl_label_stats(batch, planes, 200_000)
+        n = batch.n_lines
+        meta_h = meta.cpu().numpy()
+        stat_off, num = meta_h[:8 * (n + 1)].view(np.int64), meta_h[8 * (n + 1):].view(np.int32)
+        st = stats.cpu().numpy()
+        for i, (rn, rl, rs, _) in enumerate(refs):
+            assert int(num[i]) == rn, (occ, merge, i)
+            assert np.array_equal(batch.plane(labels, i).cpu().numpy(), rl), (occ, merge, i)
+            assert np.array_equal(st[stat_off[i]:stat_off[i + 1]], rs[1:]), (occ, merge, i)
+
+
 def test_ccl_dense_config5(cuda_device):
     import cv2
     masks = [synth_dense_mask(16384, 0.003, 0), synth_dense_mask(16384, 0.01, 1)]
