@@ -59,6 +59,12 @@ __host__ __device__ inline act_t f2act(float v) { return __float2bfloat16_rn(v);
 __host__ __device__ inline float act2f(act_t v) { return __bfloat162float(v); }
 __device__ __forceinline__ act2_t floats2act2(float a, float b) { return __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ float2 act22float2(act2_t v) { return __bfloat1622float2(v); }
+// (max(a, 0), max(b, 0)) rounded to nearest, a in the low half: ONE instruction (the ReLU rides on the convert)
+__device__ __forceinline__ uint32_t floats2act2_relu_u32(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
 #else
 typedef __half act_t;
 typedef __half2 act2_t;
@@ -69,7 +75,27 @@ __host__ __device__ inline act_t f2act(float v) { return __float2half_rn(v); }
 __host__ __device__ inline float act2f(act_t v) { return __half2float(v); }
 __device__ __forceinline__ act2_t floats2act2(float a, float b) { return __floats2half2_rn(a, b); }
 __device__ __forceinline__ float2 act22float2(act2_t v) { return __half22float2(v); }
+// (max(a, 0), max(b, 0)) rounded to nearest, a in the low half: ONE instruction (the ReLU rides on the convert)
+__device__ __forceinline__ uint32_t floats2act2_relu_u32(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
 #endif
+
+__device__ __forceinline__ uint32_t floats2act2_u32(float a, float b) {
+  act2_t h = floats2act2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Division of work-item indices by a run-time constant without the ~25-instruction integer divide: q = (x * m) >> 40
+// with m = floor(2^40 / d) + 1, exact for x, d < 2^20 (work-item counts and tile-grid dimensions are far below).
+struct FastDiv {
+  uint32_t d; uint64_t m;
+  __host__ __device__ explicit FastDiv(uint32_t d_ = 1) : d(d_ ? d_ : 1), m((1ull << 40) / (d_ ? d_ : 1) + 1ull) {}
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t x) const { return (uint32_t)(((uint64_t)x * m) >> 40); }
+  __host__ __device__ __forceinline__ void divmod(uint32_t x, uint32_t& q, uint32_t& r) const { q = div(x); r = x - q * d; }
+};
 
 // cudaFuncSetAttribute applies to the current device only: one flag per device for each call site
 // (`static PerDeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`), so that a process driving several

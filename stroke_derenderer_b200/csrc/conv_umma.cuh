@@ -191,6 +191,44 @@ __device__ __forceinline__ uint32_t sw128(uint32_t base, int r, int ch) {
   return base + (uint32_t)r * 128u + ((uint32_t)(ch ^ (r & 7)) << 4);
 }
 
+// ---- store epilogue arithmetic -----------------------------------------------------------------------------------
+// The four epilogue warps sit one per scheduler, so nothing hides their latencies: on the short-K layers (Conv2.x, Up2,
+// Up3, the level-1 bands) the epilogue, not the tensor pipe, was the critical path (ncu source view: 23 % of the stall
+// samples of Conv2.0 waited on scalar shared-memory bias loads, 14 % of its instructions were the ReLU).  So: bias as
+// float4 broadcast loads (8 instead of 32 per 32 columns) or constant-bank operands, ReLU folded into the convert
+// (cvt.rn.relu), one 16-byte shared store per 8 channels.
+// 32 accumulator columns of this thread's pixel row -> chunks 4*cc .. 4*cc+3 of its 128-byte row in the staged tile
+template <bool RELU>
+__device__ __forceinline__ void epi_pack32(const float (&v)[32], const float* __restrict__ bias32, uint32_t row_base, int row, int cc) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias32);        // shared memory, 16-byte aligned
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b0 = b4[2 * j4], b1 = b4[2 * j4 + 1];
+    const int c0 = j4 * 8;
+    uint4 pk;
+    if (RELU) {
+      pk.x = floats2act2_relu_u32(v[c0] + b0.x, v[c0 + 1] + b0.y); pk.y = floats2act2_relu_u32(v[c0 + 2] + b0.z, v[c0 + 3] + b0.w);
+      pk.z = floats2act2_relu_u32(v[c0 + 4] + b1.x, v[c0 + 5] + b1.y); pk.w = floats2act2_relu_u32(v[c0 + 6] + b1.z, v[c0 + 7] + b1.w);
+    } else {
+      pk.x = floats2act2_u32(v[c0] + b0.x, v[c0 + 1] + b0.y); pk.y = floats2act2_u32(v[c0 + 2] + b0.z, v[c0 + 3] + b0.w);
+      pk.z = floats2act2_u32(v[c0 + 4] + b1.x, v[c0 + 5] + b1.y); pk.w = floats2act2_u32(v[c0 + 6] + b1.z, v[c0 + 7] + b1.w);
+    }
+    st_shared_v4(row_base + ((((uint32_t)(cc * 4 + j4)) ^ (uint32_t)(row & 7)) << 4), pk);
+  }
+}
+// the same with the bias in the constant bank (kernel parameters; `bias32` must be indexed with compile-time offsets
+// after unrolling so that every add takes its bias as an immediate constant operand)
+__device__ __forceinline__ void epi_pack32_const_relu(const float (&v)[32], const float* bias32, uint32_t row_base, int row, int cc) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const int c0 = j4 * 8;
+    uint4 pk;
+    pk.x = floats2act2_relu_u32(v[c0] + bias32[c0], v[c0 + 1] + bias32[c0 + 1]); pk.y = floats2act2_relu_u32(v[c0 + 2] + bias32[c0 + 2], v[c0 + 3] + bias32[c0 + 3]);
+    pk.z = floats2act2_relu_u32(v[c0 + 4] + bias32[c0 + 4], v[c0 + 5] + bias32[c0 + 5]); pk.w = floats2act2_relu_u32(v[c0 + 6] + bias32[c0 + 6], v[c0 + 7] + bias32[c0 + 7]);
+    st_shared_v4(row_base + ((((uint32_t)(cc * 4 + j4)) ^ (uint32_t)(row & 7)) << 4), pk);
+  }
+}
+
 constexpr int kMiscBytes = 4096;       // barriers | tmem slot | bias | psi/head vector | gate scale | pixel index
 constexpr int kMaxSmem = 232448;       // 227 KB opt-in limit per CTA
 
@@ -273,12 +311,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   const int n_work = m_groups * p.n_tiles * p.n_phases;
   const int kb_per_tap = p.c0_blocks + p.c1_blocks;
   const int num_kb = p.n_taps * kb_per_tap;
+  // work-item and tile indices are decomposed with multiply-shift dividers (the epilogue warps are the critical path
+  // of the short-K layers; four integer divides per M tile were 8 % of their stall samples)
+  const FastDiv fd_tx((uint32_t)p.tiles_x), fd_ty((uint32_t)p.tiles_y), fd_nt((uint32_t)p.n_tiles), fd_mg((uint32_t)m_groups);
   // M tile index -> pixel origin; a phantom tile (odd tail of an MT group) lands beyond the batch, where the
   // TMA unit zero-fills loads and clips stores
   auto origin = [&](int mt, int& x0, int& y0, int& n0) {
-    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
-    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+    uint32_t rest, tx, tn, ty;
+    fd_tx.divmod((uint32_t)mt, rest, tx); fd_ty.divmod(rest, tn, ty);
+    x0 = (int)tx * p.box_w; y0 = (int)ty * p.box_h; n0 = (int)tn * p.box_n;
   };
 
   if (warp == 0) {
@@ -286,8 +327,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
-        const int mg = rest % m_groups; const int ph = rest / m_groups;
+        uint32_t nt_u, rest_u, mg_u, ph_u;
+        fd_nt.divmod((uint32_t)w, rest_u, nt_u); fd_mg.divmod(rest_u, ph_u, mg_u);
+        const int nt = (int)nt_u, mg = (int)mg_u, ph = (int)ph_u;
         int x0[MT], y0[MT], n0[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) origin(mg * MT + m, x0[m], y0[m], n0[m]);
@@ -350,8 +392,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     int cur_nt = -1;
     uint32_t xphase[2] = {0u, 0u};                // gate: parity of the two skip-tensor buffers
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
-      const int mg = rest % m_groups; const int ph = rest / m_groups;
+      uint32_t nt_u, rest_u, mg_u, ph_u;
+      fd_nt.divmod((uint32_t)w, rest_u, nt_u); fd_mg.divmod(rest_u, ph_u, mg_u);
+      const int nt = (int)nt_u, mg = (int)mg_u, ph = (int)ph_u;
 
       if constexpr (EPI == EPI_STORE) {
         if (nt != cur_nt) {                       // bias slice of this N tile -> smem (uniform branch)
@@ -379,21 +422,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
               tmem_ld32(taddr + c * 32, v);
               // 128 rows x 128 B, 16-B chunk j of row r lives at chunk (j ^ (r & 7))
               const uint32_t row_base = out_base + (uint32_t)row * 128u;
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int col = j4 * 8 + j * 2;
-                  float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
-                  if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                  act2_t h = floats2act2(a, b);
-                  pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                const uint32_t chunk = (uint32_t)(cc * 4 + j4);
-                const uint32_t addr = row_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-              }
+              if (p.relu) epi_pack32<true>(v, s_bias + c * 32, row_base, row, cc);
+              else epi_pack32<false>(v, s_bias + c * 32, row_base, row, cc);
             }
             if (m == MT - 1 && hb == BN / 64 - 1) {
               tc_fence_before();
@@ -408,12 +438,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
             if (p.pool) {
               // fused MaxPool2x2: the staged tile holds whole 2x2 windows (box dims are even); 32 pooled pixels x 8 chunks
               const int pw = p.box_w >> 1, phh = p.box_h >> 1;
+              const int pw_sh = 31 - __clz(pw), ph_sh = 31 - __clz(phh);
               const uint32_t pool_base = out_base + 16384u;
 #pragma unroll
               for (int task = et; task < 256; task += 128) {
                 const int pp = task >> 3, ch = task & 7;
-                const int px = pp % pw; const int r2 = pp / pw;
-                const int py = r2 % phh, pn = r2 / phh;
+                const int px = pp & (pw - 1); const int r2 = pp >> pw_sh;       // box dims are powers of two
+                const int py = r2 & (phh - 1), pn = r2 >> ph_sh;
                 const int m00 = (pn * p.box_h + 2 * py) * p.box_w + 2 * px, m10 = m00 + p.box_w;
                 const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, m00, ch)), ld_shared_v4(sw128(out_base, m00 + 1, ch))),
                                          hmax2_v4(ld_shared_v4(sw128(out_base, m10, ch)), ld_shared_v4(sw128(out_base, m10 + 1, ch))));
@@ -430,8 +461,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
         }
       } else {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-        const int tx = mg % p.tiles_x; const int r2 = mg / p.tiles_x;
-        const int ty = r2 % p.tiles_y; const int tn = r2 / p.tiles_y;
+        uint32_t r2_u, tx_u, tn_u, ty_u;
+        fd_tx.divmod((uint32_t)mg, r2_u, tx_u); fd_ty.divmod(r2_u, tn_u, ty_u);
+        const int tx = (int)tx_u, ty = (int)ty_u, tn = (int)tn_u;
         const int n = tn * p.box_n + ln;
         int y = ty * p.box_h + lh, x = tx * p.box_w + lw;
         const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;     // gate / head never upsample
@@ -672,10 +704,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
   const int n_work = m_groups * p.n_tiles * p.n_phases;
   const int kb_per_tap = p.c0_blocks + p.c1_blocks;
   const int num_kb = p.n_taps * kb_per_tap;
+  const FastDiv fd_tx((uint32_t)p.tiles_x), fd_ty((uint32_t)p.tiles_y), fd_nt((uint32_t)p.n_tiles), fd_mg((uint32_t)m_groups);
   auto origin = [&](int mt, int& x0, int& y0, int& n0) {
-    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
-    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+    uint32_t rest, tx, tn, ty;
+    fd_tx.divmod((uint32_t)mt, rest, tx); fd_ty.divmod(rest, tn, ty);
+    x0 = (int)tx * p.box_w; y0 = (int)ty * p.box_h; n0 = (int)tn * p.box_n;
   };
 
   if (warp == 0) {
@@ -683,8 +716,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = pair; w < n_work; w += n_pairs) {
-        const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
-        const int mg = rest % m_groups; const int ph = rest / m_groups;
+        uint32_t nt_u, rest_u, mg_u, ph_u;
+        fd_nt.divmod((uint32_t)w, rest_u, nt_u); fd_mg.divmod(rest_u, ph_u, mg_u);
+        const int nt = (int)nt_u, mg = (int)mg_u, ph = (int)ph_u;
         int x0, y0, n0;
         origin(mg * 2 + (int)rank, x0, y0, n0);
         const int brow = ph * p.cout + nt * BN + (int)rank * 128;
@@ -738,8 +772,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
     int as = 0; uint32_t aphase = 0;
     int cur_nt = -1;
     for (int w = pair; w < n_work; w += n_pairs) {
-      const int nt = w % p.n_tiles; const int rest = w / p.n_tiles;
-      const int mg = rest % m_groups; const int ph = rest / m_groups;
+      uint32_t nt_u, rest_u, mg_u, ph_u;
+      fd_nt.divmod((uint32_t)w, rest_u, nt_u); fd_mg.divmod(rest_u, ph_u, mg_u);
+      const int nt = (int)nt_u, mg = (int)mg_u, ph = (int)ph_u;
       if (nt != cur_nt) {
         epi_bar();
         for (int i = et; i < BN; i += 128) s_bias[i] = __ldg(p.bias + nt * BN + i);
@@ -761,21 +796,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
           float v[32];
           tmem_ld32(taddr + c * 32, v);
           const uint32_t row_base = out_base + (uint32_t)row * 128u;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = j4 * 8 + j * 2;
-              float a = v[col] + s_bias[c * 32 + col], b = v[col + 1] + s_bias[c * 32 + col + 1];
-              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              act2_t h = floats2act2(a, b);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            const uint32_t chunk = (uint32_t)(cc * 4 + j4);
-            const uint32_t addr = row_base + ((chunk ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-          }
+          if (p.relu) epi_pack32<true>(v, s_bias + c * 32, row_base, row, cc);
+          else epi_pack32<false>(v, s_bias + c * 32, row_base, row, cc);
         }
         if (hb == BN / 64 - 1) {
           tc_fence_before();
@@ -789,12 +811,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
         }
         if (p.pool) {
           const int pw = p.box_w >> 1, phh = p.box_h >> 1;
+          const int pw_sh = 31 - __clz(pw), ph_sh = 31 - __clz(phh);
           const uint32_t pool_base = out_base + 16384u;
 #pragma unroll
           for (int task = et; task < 256; task += 128) {
             const int pp = task >> 3, ch = task & 7;
-            const int px = pp % pw; const int r2 = pp / pw;
-            const int py = r2 % phh, pn = r2 / phh;
+            const int px = pp & (pw - 1); const int r2 = pp >> pw_sh;           // box dims are powers of two
+            const int py = r2 & (phh - 1), pn = r2 >> ph_sh;
             const int m00 = (pn * p.box_h + 2 * py) * p.box_w + 2 * px, m10 = m00 + p.box_w;
             const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, m00, ch)), ld_shared_v4(sw128(out_base, m00 + 1, ch))),
                                      hmax2_v4(ld_shared_v4(sw128(out_base, m10, ch)), ld_shared_v4(sw128(out_base, m10 + 1, ch))));
@@ -1036,20 +1059,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
             tmem_ld32(taddr + c * 32, v);
             tmem_st32_zero(taddr + c * 32);
             const uint32_t rbase = row_buf + (uint32_t)row * 128u;
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int col = j4 * 8 + j * 2;
-                float a = fmaxf(v[col] + p.bias_c[c * 32 + col], 0.f), b2 = fmaxf(v[col + 1] + p.bias_c[c * 32 + col + 1], 0.f);
-                act2_t h = floats2act2(a, b2);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              const uint32_t chunk = (uint32_t)(c * 4 + j4);
-              const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-            }
+            epi_pack32_const_relu(v, p.bias_c + c * 32, rbase, row, c);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -1184,10 +1194,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
 
   const int n_work = p.m_tiles;
   const int cbs = p.c0_blocks;                           // 64-channel blocks of the (single) source
+  const FastDiv fd_tx((uint32_t)p.tiles_x), fd_ty((uint32_t)p.tiles_y);
   auto origin = [&](int mt, int& x0, int& y0, int& n0) {
-    const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
-    const int ty = rest % p.tiles_y; const int tn = rest / p.tiles_y;
-    x0 = tx * p.box_w; y0 = ty * p.box_h; n0 = tn * p.box_n;
+    uint32_t rest, tx, tn, ty;
+    fd_tx.divmod((uint32_t)mt, rest, tx); fd_ty.divmod(rest, tn, ty);
+    x0 = (int)tx * p.box_w; y0 = (int)ty * p.box_h; n0 = (int)tn * p.box_n;
   };
 
   if (warp == 0) {
@@ -1271,20 +1282,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
           float v[32];
           tmem_ld32(taddr + c * 32, v);
           const uint32_t rbase = out_base + (uint32_t)row * 128u;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = j4 * 8 + j * 2;
-              float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
-              act2_t h = floats2act2(a, b);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            const uint32_t chunk = (uint32_t)(c * 4 + j4);
-            const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-          }
+          epi_pack32<true>(v, s_bias + c * 32, rbase, row, c);
         }
         if (slot == 3) {
           tc_fence_before();
@@ -1386,6 +1384,7 @@ __global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kern
 
   const int segs = p.W / 128;
   const int n_work = p.B * p.H * segs;
+  const FastDiv fd_segs((uint32_t)segs), fd_h((uint32_t)p.H);     // a work item is one 128-pixel row segment: its index math must be cheap
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1413,8 +1412,9 @@ __global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kern
     const int r = threadIdx.x - 32;
     int stage = 0; uint32_t phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int sx = w % segs; const int rest = w / segs;
-      const int y = rest % p.H, n = rest / p.H;
+      uint32_t rest_u, sx_u, n_u, y_u;
+      fd_segs.divmod((uint32_t)w, rest_u, sx_u); fd_h.divmod(rest_u, n_u, y_u);
+      const int sx = (int)sx_u, y = (int)y_u, n = (int)n_u;
       const int x = sx * 128 + r;
       uint4 v[9];
 #pragma unroll
@@ -1438,8 +1438,9 @@ __global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kern
     const int et = threadIdx.x - 160;
     int as = 0; uint32_t aphase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int sx = w % segs; const int rest = w / segs;
-      const int y = rest % p.H, n = rest / p.H;
+      uint32_t rest_u, sx_u, n_u, y_u;
+      fd_segs.divmod((uint32_t)w, rest_u, sx_u); fd_h.divmod(rest_u, n_u, y_u);
+      const int sx = (int)sx_u, y = (int)y_u, n = (int)n_u;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
       mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
       tc_fence_after();
@@ -1450,20 +1451,7 @@ __global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kern
         float v[32];
         tmem_ld32(taddr + c * 32, v);
         const uint32_t rbase = out_base + (uint32_t)row * 128u;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = j4 * 8 + j * 2;
-            float a = fmaxf(v[col] + s_bias[c * 32 + col], 0.f), b = fmaxf(v[col + 1] + s_bias[c * 32 + col + 1], 0.f);
-            act2_t h = floats2act2(a, b);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          const uint32_t chunk = (uint32_t)(c * 4 + j4);
-          const uint32_t addr = rbase + ((chunk ^ (uint32_t)(row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-        }
+        epi_pack32<true>(v, s_bias + c * 32, rbase, row, c);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
