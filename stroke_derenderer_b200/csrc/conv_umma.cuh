@@ -170,6 +170,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // named barrier for the 4 epilogue warps only (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
@@ -235,6 +236,9 @@ constexpr int kMaxSmem = 232448;       // 227 KB opt-in limit per CTA
 // MT = M tiles (128 pixels each) that share one B k-block in shared memory.  A 128 x 128 tile reads
 // 32 KB of operands per 256 MMA cycles = the full 128 B/clk of shared-memory bandwidth and stalls the
 // tensor pipe; 128 x 256 (BN = 256) or 2 x (128 x 128) (MT = 2) needs 96 B/clk.
+#ifndef SD_EPI_WARPS
+#define SD_EPI_WARPS 8
+#endif
 template <int BN, int EPI, int MT = 1> struct ConvCfg {
   static constexpr int kABytes = 128 * 128;             // 128 px x 64 halves, per M tile
   static constexpr int kBBytes = BN * 128;
@@ -247,6 +251,14 @@ template <int BN, int EPI, int MT = 1> struct ConvCfg {
   static constexpr int kTmemCols = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // 64,128,256,512: powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + kMiscBytes;
   static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  // store epilogue: EIGHT warps, two per TMEM lane quarter (each takes 32 of the 64 staged channels of its pixel rows), so
+  // every scheduler holds two epilogue warps that hide each other's TMEM-load / shared-memory / barrier latencies; with
+  // four (one per scheduler) the epilogue was the critical path of the short-K layers.  Gate / head: four
+  // (thread = pixel row reduces over all columns).
+  static constexpr int kEpiWarps = (EPI == EPI_STORE) ? SD_EPI_WARPS : 4;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
   static_assert(kStages >= 3, "pipeline too shallow");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static_assert(EPI != EPI_STORE || BN % 64 == 0, "store epilogue writes 64-channel boxes");
@@ -256,7 +268,7 @@ template <int BN, int EPI, int MT = 1> struct ConvCfg {
 constexpr int kConvThreads = 192;
 
 template <int BN, int EPI, int MT>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN, EPI, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); mbar_init(xbar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::kEpiThreads); mbar_init(xbar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -382,10 +394,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
     }
     __syncwarp();
   } else {
-    // ======================= epilogue (warps 2..5) =======================
+    // ======================= epilogue (warps 2..5, store: 2..9) =======================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                // accumulator row == pixel within the M tile
-    const int et = threadIdx.x - 64;              // 0..127 within the epilogue group
+    const int et = threadIdx.x - 64;              // 0 .. kEpiThreads-1 within the epilogue group
+    const int eh = (warp - 2) >> 2;               // store epilogue with 8 warps: which 32 of the 64 staged channels
     const int lw = row % p.box_w; int rr = row / p.box_w;
     const int lh = rr % p.box_h; const int ln = rr / p.box_h;
     int as = 0; uint32_t aphase = 0;
@@ -398,10 +411,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
 
       if constexpr (EPI == EPI_STORE) {
         if (nt != cur_nt) {                       // bias slice of this N tile -> smem (uniform branch)
-          epi_bar();                              // everybody is done reading the previous slice
-          for (int i = et; i < BN; i += 128) s_bias[i] = __ldg(p.bias + nt * BN + i);
+          epi_bar_n<Cfg::kEpiThreads>();                              // everybody is done reading the previous slice
+          for (int i = et; i < BN; i += Cfg::kEpiThreads) s_bias[i] = __ldg(p.bias + nt * BN + i);
           cur_nt = nt;
-          epi_bar();
+          epi_bar_n<Cfg::kEpiThreads>();
         }
         mbar_wait(tfull_bar(as), aphase, p.err_flag, 4);
         tc_fence_after();
@@ -414,9 +427,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
           for (int hb = 0; hb < BN / 64; ++hb) {
             // the previous TMA store must have finished READING the staging buffer
             if (et == 0) tma_store_wait_read();
-            epi_bar();
+            epi_bar_n<Cfg::kEpiThreads>();
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
+            for (int cc = (Cfg::kEpiWarps == 8 ? eh : 0); cc < (Cfg::kEpiWarps == 8 ? eh + 1 : 2); ++cc) {
               const int c = hb * 2 + cc;
               float v[32];
               tmem_ld32(taddr + c * 32, v);
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
               mbar_arrive(tempty_bar(as));        // TMEM stage free: the next work item's MMAs may start
             }
             fence_async_smem();                   // generic-proxy smem writes -> visible to the TMA unit
-            epi_bar();
+            epi_bar_n<Cfg::kEpiThreads>();
             if (et == 0) {
               tma_store_4d(&p.tmOut[ph], out_base, nt * BN + hb * 64, x0, y0, n0);
               tma_store_commit();
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
               const int pw_sh = 31 - __clz(pw), ph_sh = 31 - __clz(phh);
               const uint32_t pool_base = out_base + 16384u;
 #pragma unroll
-              for (int task = et; task < 256; task += 128) {
+              for (int task = et; task < 256; task += Cfg::kEpiThreads) {
                 const int pp = task >> 3, ch = task & 7;
                 const int px = pp & (pw - 1); const int r2 = pp >> pw_sh;       // box dims are powers of two
                 const int py = r2 & (phh - 1), pn = r2 >> ph_sh;
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const __grid
                 st_shared_v4(sw128(pool_base, pp, ch), v);
               }
               fence_async_smem();
-              epi_bar();
+              epi_bar_n<Cfg::kEpiThreads>();
               if (et == 0) {
                 tma_store_4d(&p.tmPool, pool_base, nt * BN + hb * 64, x0 >> 1, y0 >> 1, n0);
                 tma_store_commit();
@@ -877,6 +890,9 @@ template <int CB, int EPI> struct BandCfg {
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kWBytes - kOutBytes) / kRowStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kSmemBytes = kStages * kRowStageBytes + kWBytes + kOutBytes + 1024 + kMiscBytes;
+  static constexpr int kEpiWarps = (EPI == EPI_STORE) ? SD_EPI_WARPS : 4;   // as in ConvCfg; the head reduces over all 64 channels per thread
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -891,7 +907,7 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int CB, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = BandCfg<CB, EPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -918,7 +934,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 8; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 8; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::kEpiThreads); }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -932,7 +948,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2) {                                     // all accumulator slots start at zero
+  if (warp >= 2 && warp < 6) {                         // all accumulator slots start at zero
     const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < 16; ++c) tmem_st32_zero(t0 + c * 32);
@@ -1033,6 +1049,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const int eh = (warp - 2) >> 2;                     // store epilogue with 8 warps: which 32 of the row's 64 channels
     int g = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int sx = w % segs; int rest = w / segs;
@@ -1052,26 +1069,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
           const bool pooling = Cfg::kCanPool && p.pool;
           const uint32_t row_buf = out_base + ((pooling && (y & 1)) ? 16384u : 0u);     // rows alternate buffers when pooling
           if (et == 0) tma_store_wait_read();
-          epi_bar();
+          epi_bar_n<Cfg::kEpiThreads>();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = (Cfg::kEpiWarps == 8 ? eh : 0); c < (Cfg::kEpiWarps == 8 ? eh + 1 : 2); ++c) {
             float v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_st32_zero(taddr + c * 32);
             const uint32_t rbase = row_buf + (uint32_t)row * 128u;
-            epi_pack32_const_relu(v, p.bias_c + c * 32, rbase, row, c);
+            if (c == 0) epi_pack32_const_relu(v, p.bias_c, rbase, row, 0);           // two copies: the bias offsets stay compile-time
+            else epi_pack32_const_relu(v, p.bias_c + 32, rbase, row, 1);
           }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(tempty_bar(slot));
           fence_async_smem();
-          epi_bar();
+          epi_bar_n<Cfg::kEpiThreads>();
           if (et == 0) { tma_store_4d(&p.tmOut[0], row_buf, 0, sx * 128, y, n); tma_store_commit(); }
           if (pooling && (y & 1)) {
             // fused MaxPool2x2 over rows y-1 (buffer 0) and y (buffer 1): 64 pooled pixels x 8 chunks
             const uint32_t pool_base = out_base + 32768u;
 #pragma unroll
-            for (int task = et; task < 512; task += 128) {
+            for (int task = et; task < 512; task += Cfg::kEpiThreads) {
               const int pp = task >> 3, ch = task & 7;
               const uint4 v = hmax2_v4(hmax2_v4(ld_shared_v4(sw128(out_base, 2 * pp, ch)), ld_shared_v4(sw128(out_base, 2 * pp + 1, ch))),
                                        hmax2_v4(ld_shared_v4(sw128(out_base + 16384u, 2 * pp, ch)),
@@ -1079,7 +1097,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_band_kernel(const __grid
               st_shared_v4(sw128(pool_base, pp, ch), v);
             }
             fence_async_smem();
-            epi_bar();
+            epi_bar_n<Cfg::kEpiThreads>();
             if (et == 0) { tma_store_4d(&p.tmPool, pool_base, 0, sx * 64, y >> 1, n); tma_store_commit(); }
           }
         } else {
@@ -1136,6 +1154,9 @@ struct Up4Cfg {
   static constexpr int kOutBytes = 16384;
   static constexpr int kStages = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;   // 4
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kMiscBytes;
+  static constexpr int kEpiWarps = SD_EPI_WARPS;        // as in ConvCfg: two epilogue warps per TMEM lane quarter
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -1151,7 +1172,7 @@ __host__ __device__ constexpr Up4Tap up4_tap(int t) {
 }
 __host__ __device__ constexpr int up4_slot_phase(int slot) { return slot == 0 ? 1 : (slot == 1 ? 0 : (slot == 2 ? 2 : 3)); }   // ph = py * 2 + px
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(Up4Cfg::kThreads, 1) conv_up4_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = Up4Cfg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1174,7 +1195,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1266,6 +1287,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const int eh = (warp - 2) >> 2;               // 8 epilogue warps: which 32 of the 64 channels of a phase (ConvCfg::kEpiWarps)
     int as = 0; uint32_t aphase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       int x0, y0, n0;
@@ -1276,9 +1298,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
       for (int slot = 0; slot < 4; ++slot) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + slot * 64);
         if (et == 0) tma_store_wait_read();
-        epi_bar();
+        epi_bar_n<Cfg::kEpiThreads>();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = (Cfg::kEpiWarps == 8 ? eh : 0); c < (Cfg::kEpiWarps == 8 ? eh + 1 : 2); ++c) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
           const uint32_t rbase = out_base + (uint32_t)row * 128u;
@@ -1289,7 +1311,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_up4_kernel(const __grid_
           mbar_arrive(tempty_bar(as));
         }
         fence_async_smem();
-        epi_bar();
+        epi_bar_n<Cfg::kEpiThreads>();
         if (et == 0) { tma_store_4d(&p.tmOut[up4_slot_phase(slot)], out_base, 0, x0, y0, n0); tma_store_commit(); }
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }

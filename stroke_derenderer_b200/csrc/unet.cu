@@ -335,7 +335,7 @@ static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
   using Cfg = ConvCfg<BN, EPI, MT>;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  conv_umma_kernel<BN, EPI, MT><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  conv_umma_kernel<BN, EPI, MT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_umma_kernel");
   return SD_OK;
 }
@@ -345,7 +345,7 @@ static int launch_band(const ConvParams& p, int grid, cudaStream_t s) {
   using Cfg = BandCfg<CB, EPI>;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  conv_band_kernel<CB, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(p);
+  conv_band_kernel<CB, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_band_kernel");
   return SD_OK;
 }
@@ -580,7 +580,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.m_tiles = per_img4 * ((B + box_n4 - 1) / box_n4);
       static PerDeviceOnce attr_once;
       if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_up4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Up4Cfg::kSmemBytes));
-      conv_up4_kernel<<<p.m_tiles < nsm4 ? p.m_tiles : nsm4, kConvThreads, Up4Cfg::kSmemBytes, s>>>(p);
+      conv_up4_kernel<<<p.m_tiles < nsm4 ? p.m_tiles : nsm4, Up4Cfg::kThreads, Up4Cfg::kSmemBytes, s>>>(p);
       SD_LAUNCH_CHECK("conv_up4_kernel");
       return SD_OK;
     };
