@@ -1,4 +1,4 @@
-// Micro-benchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M = 128, K = 16) as a function of N, with both
+// Micro-benchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M = 128 or 64, K = 16) as a function of N, with both
 // operands resident in shared memory (128-byte swizzle, K-major), one CTA per SM, one issuing thread.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu && ./umma_rate
 #include <cstdio>
@@ -14,7 +14,7 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_blocks, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int M, int N, int iters, int a_blocks, long long* out) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   __shared__ uint32_t tmem_slot;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_bl
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     const uint32_t b_base = base + 128 * 1024;                     // B: up to 256 rows x 128 B
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
@@ -57,16 +57,17 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * sizeof(long long));
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 4000;
+  for (int M : {128, 64})
   for (int ctas : {1, 148}) {
     for (int N : {16, 32, 64, 96, 128, 192, 256}) {
-      rate_kernel<<<ctas, 128, 200 * 1024>>>(N, iters, 8, d);
+      rate_kernel<<<ctas, 128, 200 * 1024>>>(M, N, iters, 8, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("N=%d failed: %s\n", N, cudaGetErrorString(e)); return 1; }
       long long h[148]; cudaMemcpy(h, d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
       long long mx = 0; for (int i = 0; i < ctas; ++i) mx = h[i] > mx ? h[i] : mx;
       const double cyc = (double)mx / (iters * 4.0);
-      printf("ctas=%3d N=%3d  %.1f cycles per MMA (K=16)  -> %.0f MAC/clk/SM, smem operand read %.0f B/clk\n", ctas, N, cyc,
-             128.0 * N * 16 / cyc, (128 * 16 * 2 + N * 16 * 2) / cyc);
+      printf("M=%3d ctas=%3d N=%3d  %.1f cycles per MMA (K=16)  -> %.0f MAC/clk/SM, smem operand read %.0f B/clk\n", M, ctas, N, cyc,
+             (double)M * N * 16 / cyc, (M * 16 * 2 + N * 16 * 2) / cyc);
     }
   }
   return 0;
