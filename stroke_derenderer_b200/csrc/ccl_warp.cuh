@@ -37,7 +37,24 @@ constexpr int kCw = 4;                       // warps (strips) per CTA
 constexpr int kBigCoord = 0x3fffffff;        // stats rows keep (kBigCoord - max) so that every field is a min / add
 constexpr int kStatFill = 0x7f7f7f7f;        // cudaMemsetAsync(0x7f) start value of every stats field
 
+// -DSD_BOUNDS_CHECK (SD_EXTRA_NVCC_FLAGS): every index the CCL kernels compute is checked against the extent of the array
+// it addresses; a violation prints the site and traps.  compute-sanitizer is closed on the pool this was developed on
+// (profiles/r02_sanitize.md): tools/bounds_check.sh runs the CCL parity tests under this build instead.
+#ifdef SD_BOUNDS_CHECK
+#define CW_CHECK(cond)                                                                                        \
+  do {                                                                                                        \
+    if (!(cond)) {                                                                                            \
+      printf("CW_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                               \
+    }                                                                                                         \
+  } while (0)
+#else
+#define CW_CHECK(cond) do { } while (0)
+#endif
+
 struct CclWarpWork {
+  int64_t blk_total;    // extent of the block space (bounds checks)
+  int n_strips;
   int* parent;          // [blk_total]       sparse: seam-touching local roots only (global block index -> parent)
   uint32_t* bitmap;     // [blk_total / 32]  bit = block is the root (first block) of a component
   int* prefix;          // [blk_total / 32]  exclusive count of root bits before this word, per line
@@ -135,6 +152,7 @@ __device__ __forceinline__ void cw_link_first(cw_node_t* parent, int off, int of
     if (cu) { const int j = __ffsll((long long)cu) - 1; c.vu &= ~(1ull << j); node = offU + cw_run_index(rsU, j); }
     else if (cl) { const int j = __ffsll((long long)cl) - 1; c.vl &= ~(1ull << j); node = offU + cw_run_index(rsU, j - 1); }
     else if (cr) { const int j = __ffsll((long long)cr) - 1; c.vr &= ~(1ull << j); node = offU + cw_run_index(rsU, j + 1); }
+    CW_CHECK(node >= 0 && node <= off && off < kStripBlocks);            // a link points to a smaller ordinal (or to itself)
     parent[off] = (cw_node_t)node;
   }
 }
@@ -146,6 +164,7 @@ __device__ __forceinline__ void cw_union_rest(cw_node_t* parent, int off, int of
     if (vu) { k = __ffsll((long long)vu) - 1; vu &= vu - 1; dk = 0; }
     else if (vl) { k = __ffsll((long long)vl) - 1; vl &= vl - 1; dk = -1; }
     else { k = __ffsll((long long)vr) - 1; vr &= vr - 1; dk = 1; }
+    CW_CHECK(k + dk >= 0 && k + dk < 64 && cw_run_index(rs, k) >= 0 && cw_run_index(rsU, k + dk) >= 0);
     cw_union(parent, off + cw_run_index(rs, k), offU + cw_run_index(rsU, k + dk));
   }
 }
@@ -211,6 +230,7 @@ __device__ __forceinline__ void cw_seam_row(const CclWarpWork& w, int64_t sg, in
   const uint4 Lb = __ldcg(reinterpret_cast<const uint4*>(w.bnd_bits + (sg - 1) * 8 + 4));
   const uint4 Rb = __ldcg(reinterpret_cast<const uint4*>(w.bnd_bits + sg * 8));
   if (a < 0) return;
+  CW_CHECK(a < w.blk_total && b0 < w.blk_total && bm < w.blk_total && bp < w.blk_total && sg > 0 && sg < w.n_strips);
   const uint32_t a0 = cw_col_bit(Lb, 2 * br), a1 = cw_col_bit(Lb, 2 * br + 1);
   const uint32_t c0 = cw_col_bit(Rb, 2 * br), c1 = cw_col_bit(Rb, 2 * br + 1);
   if ((a0 | a1) & (c0 | c1)) cw_uf_union(w.parent, a, b0);
@@ -233,8 +253,11 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
   if (blockIdx.x == 0 && threadIdx.x == 0) *w.ticket = 0u;
   for (int strip = blockIdx.x * kCw + wp; strip < n_strips; strip += gridDim.x * kCw) {
     const int64_t blk0 = (int64_t)strip * kStripBlocks;
-    const sd_line ln = L[cw_find_line(L, n_lines, blk0, lane)];
+    const int li = cw_find_line(L, n_lines, blk0, lane);
+    CW_CHECK(li >= 0 && li < n_lines);
+    const sd_line ln = L[li];
     const int s = (int)((blk0 - ln.blk_off) >> 12), ns = ln.bw >> 6;
+    CW_CHECK(s >= 0 && s < ns && ln.pitch == 2 * ln.bw && (ln.bw & 63) == 0);
     const uint8_t* src = mask + ln.px_off + s * 128;
     // all 128 rows of the strip on their way to L2 before the first batch of loads waits (a row = one 128-byte line)
 #pragma unroll
@@ -284,6 +307,7 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     const int n_runs = __shfl_sync(0xffffffffu, inc, 31);
     const int oa = inc - cnt, ob = oa + cnt_a;                            // first ordinals of the two block rows
+    CW_CHECK(n_runs >= 0 && n_runs <= kStripBlocks && oa >= 0 && ob + __popcll(rsb) <= n_runs);
     // the block row above row a belongs to lane L-1 (its row b)
     const uint64_t Ue = cw_shfl_up64(Beb, lane), Uo = cw_shfl_up64(Bob, lane);
     const uint64_t hlU = cw_shfl_up64(hlb, lane), rsU = cw_shfl_up64(rsb, lane);
@@ -307,6 +331,7 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
         bool changed = false;
         for (int j = lane; j < n_runs; j += 32) {
           const int pa = vp[j];
+          CW_CHECK(pa >= 0 && pa <= j);
           const int ga = vp[pa];
           if (ga != pa) { vp[j] = (cw_node_t)ga; changed = true; }
         }
@@ -332,13 +357,17 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
           const int r = cw_find(vp, off);                                // block 0 has no left neighbour: it starts the row's first run
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
           const int pos = cw_run_position(sm.rowoff, sm.rs, r);
+          CW_CHECK(r >= 0 && r < n_runs && pos >= 0 && pos < kStripBlocks);
           left = gbase + (pos >> 6) * ln.bw + (pos & 63);
+          CW_CHECK(left >= ln.blk_off && left < ln.blk_off + 64 * (int64_t)ln.bw && left < w.blk_total);
         }
         if (s < ns - 1 && (occ >> 63)) {
           const int r = cw_find(vp, off + cw_run_index(rs, 63));
           atomicOr(&sm.touch[r >> 5], 1u << (r & 31));
           const int pos = cw_run_position(sm.rowoff, sm.rs, r);
+          CW_CHECK(r >= 0 && r < n_runs && pos >= 0 && pos < kStripBlocks);
           right = gbase + (pos >> 6) * ln.bw + (pos & 63);
+          CW_CHECK(right >= ln.blk_off && right < ln.blk_off + 64 * (int64_t)ln.bw && right < w.blk_total);
         }
         br[row] = left; br[64 + row] = right;
       }
@@ -360,6 +389,7 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
       uint16_t* out = w.roots + (int64_t)strip * kStripBlocks;
       for (int j = lane; j < n_runs; j += 32) {
         const int r = cw_find(vp, j);                                      // every union is done: roots are final
+        CW_CHECK(r >= 0 && r <= j);
         const uint32_t tch = (sm.touch[r >> 5] >> (r & 31)) & 1u;
         out[j] = (uint16_t)(r | (tch << 15));
       }
@@ -372,7 +402,11 @@ __global__ void __launch_bounds__(32 * kCw, MINB) ccl_warp_label_kernel(const ui
         for (uint64_t t = h ? rsb : rsa; t; t &= t - 1, ++o) {
           if (vp[o] != o) continue;
           const int k = __ffsll((long long)t) - 1;
-          if ((sm.touch[o >> 5] >> (o & 31)) & 1u) { const int g = gbase + row * ln.bw + k; w.parent[g] = g; }
+          if ((sm.touch[o >> 5] >> (o & 31)) & 1u) {
+            const int g = gbase + row * ln.bw + k;
+            CW_CHECK(g >= 0 && g < w.blk_total);
+            w.parent[g] = g;
+          }
           else rootbits |= 1ull << k;
         }
         *reinterpret_cast<uint2*>(w.bitmap + (ln.blk_off >> 5) + (int64_t)row * (ln.bw >> 5) + s * 2) =
@@ -423,6 +457,7 @@ __global__ void __launch_bounds__(1024) ccl_line_kernel(const sd_line* __restric
     const int n_bnd = (ln.bw >> 6) * 128;
     for (int i = tid; i < n_bnd; i += blockDim.x) {
       const int k = __ldcg(w.bnd_root + first + i);
+      CW_CHECK(k < w.blk_total && first + i < (int64_t)w.n_strips * 128);
       if (k >= 0 && __ldcg(w.parent + k) == k) atomicOr(&w.bitmap[k >> 5], 1u << (k & 31));
     }
   }
@@ -537,8 +572,10 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
   }
   __syncthreads();
   const int li = sm.line;
+  CW_CHECK(li >= 0 && li < n_lines && strip < w.n_strips);
   const sd_line ln = L[li];
   const int s = (int)((blk0 - ln.blk_off) >> 12);
+  CW_CHECK(s >= 0 && s < (ln.bw >> 6));
   const int gbase = (int)ln.blk_off + s * 64;
   const int br = tid >> 2, q = tid & 3;
   const uint2 r2 = sm.rs[br];
@@ -556,6 +593,7 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
         const int k = __ffsll((long long)t) - 1;
         int g = gbase + br * ln.bw + k;
         if (rr >> 15) g = cw_uf_find(w.parent, g);
+        CW_CHECK(ord >= 0 && ord < kStripBlocks && g >= ln.blk_off && g < ln.blk_off + 64 * (int64_t)ln.bw);
         sm.lab[ord] = 1 + __ldg(w.prefix + (g >> 5)) + __popc(__ldg(w.bitmap + (g >> 5)) & ((1u << (g & 31)) - 1u));
       }
     }
@@ -574,7 +612,9 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
     for (uint64_t t = mine; t; t &= t - 1, ++ord) {
       const int k = __ffsll((long long)t) - 1;
       const int root = (int)(__ldg(p++) & 0x7fffu);
+      CW_CHECK(root >= 0 && root <= ord && ord < kStripBlocks);
       const int lab = sm.lab[root];
+      CW_CHECK(lab >= 1);
       if (root != ord) sm.lab[ord] = lab;
       if (do_stats) {
         // blocks of the run: occupied blocks from k up to the next run start of the ROW (it may lie in another quarter)
@@ -610,8 +650,8 @@ __global__ void __launch_bounds__(256) ccl_strip_write2_kernel(const sd_line* __
     const uint32_t te = (uint32_t)(Te >> (2 * lane)) & 3u, to = (uint32_t)(To >> (2 * lane)) & 3u;
     const uint32_t be = (uint32_t)(Be >> (2 * lane)) & 3u, bo = (uint32_t)(Bo >> (2 * lane)) & 3u;
     int l0 = 0, l1 = 0;
-    if ((te | to | be | bo) & 1u) l0 = sm.lab[off + cw_run_index(rsb, 2 * lane)];
-    if ((te | to | be | bo) & 2u) l1 = sm.lab[off + cw_run_index(rsb, 2 * lane + 1)];
+    if ((te | to | be | bo) & 1u) { CW_CHECK(cw_run_index(rsb, 2 * lane) >= 0 && off + cw_run_index(rsb, 2 * lane) < kStripBlocks); l0 = sm.lab[off + cw_run_index(rsb, 2 * lane)]; }
+    if ((te | to | be | bo) & 2u) { CW_CHECK(cw_run_index(rsb, 2 * lane + 1) >= 0 && off + cw_run_index(rsb, 2 * lane + 1) < kStripBlocks); l1 = sm.lab[off + cw_run_index(rsb, 2 * lane + 1)]; }
     int4 a, c;
     a.x = (te & 1u) ? l0 : 0; a.y = (to & 1u) ? l0 : 0; a.z = (te & 2u) ? l1 : 0; a.w = (to & 2u) ? l1 : 0;
     c.x = (be & 1u) ? l0 : 0; c.y = (bo & 1u) ? l0 : 0; c.z = (be & 2u) ? l1 : 0; c.w = (bo & 2u) ? l1 : 0;

@@ -824,7 +824,7 @@ static size_t ccl_warp_carve(void* base, int64_t blk_total, CclWarpWork* w) {
   int* bnd_root = reinterpret_cast<int*>(take(strips * 128 * 4));
   uint32_t* bnd_bits = reinterpret_cast<uint32_t*>(take(strips * 8 * 4));
   unsigned int* ticket = reinterpret_cast<unsigned int*>(take(256));
-  if (w) { w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots; w->parent_fb = parent_fb;
+  if (w) { w->blk_total = blk_total; w->n_strips = (int)strips; w->parent = parent; w->bitmap = bitmap; w->prefix = prefix; w->pix = pix; w->rs = rs; w->roots = roots; w->parent_fb = parent_fb;
            w->bnd_root = bnd_root; w->bnd_bits = bnd_bits; w->ticket = ticket; }
   return off;
 }
