@@ -123,6 +123,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// One lane of a CONVERGED warp, chosen by the hardware.  The producer and MMA-issuer warps must pick their single issuing
+// thread this way: under `if (lane == 0)` the compiler cannot prove that one thread is active and wraps EVERY tcgen05.mma /
+// TMA instruction (uniform-datapath instructions) in an ELECT / BRA.U.ANY loop over the active lanes — ~50 cycles of issue
+// per MMA, which made the issuing thread the bottleneck of every kernel whose MMAs are shorter than that (N <= 128:
+// 64 tensor cycles; measured with tools/micro/umma_rate.cu, profiles/r02_umma_rate.txt).  After elect.sync it emits the
+// bare instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         uint32_t nt_u, rest_u, mg_u, ph_u;
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma
     __syncwarp();
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -726,7 +738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int w = pair; w < n_work; w += n_pairs) {
         uint32_t nt_u, rest_u, mg_u, ph_u;
@@ -753,7 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
     __syncwarp();
   } else if (warp == 1) {
     // ======================= MMA issuer (leader CTA only) =======================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int w = pair; w < n_work; w += n_pairs) {
@@ -964,7 +976,7 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
   // per CTA, the output rows of its work items are numbered consecutively: g -> slot g & 7, use (g >> 3)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // one-time: weights -> smem, block (dx, cb, kyr) <- tap (ky = 2 - kyr, kx = dx), 64 rows x 128 B each
       mbar_expect_tx(w_bar, Cfg::kWBytes);
       for (int dx = 0; dx < 3; ++dx)
@@ -988,7 +1000,7 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(w_bar, 0, p.err_flag, 5);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
@@ -1223,7 +1235,7 @@ __global__ void __launch_bounds__(Up4Cfg::kThreads, 1) conv_up4_kernel(const __g
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         int x0, y0, n0;
@@ -1246,7 +1258,7 @@ __global__ void __launch_bounds__(Up4Cfg::kThreads, 1) conv_up4_kernel(const __g
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -1409,7 +1421,7 @@ __global__ void __launch_bounds__(kC1Threads, kC1CtasPerSm) conv_first_umma_kern
   const FastDiv fd_segs((uint32_t)segs), fd_h((uint32_t)p.H);     // a work item is one 128-pixel row segment: its index math must be cheap
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       const uint64_t bdesc = umma_desc_none(w_base, 128, kC1GroupBytes);
