@@ -628,16 +628,21 @@ __global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even CTA of the pair
 
-struct Conv2Cfg {
+// BN = 256 (Cout % 256 == 0 layers) or 128 (the level-2 layers, ONE M tile per CTA: per MMA a CTA reads 4 KB of A and its
+// 2-KB half of B instead of the 4 + 4 KB of the single-CTA MT = 2 form, and a k-block fills 24 KB instead of 48 KB:
+// those layers are bound by shared-memory bandwidth).
+template <int BN> struct Conv2CfgT {
   static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = 128 * 128;             // this CTA's half of the 256-row B k-block
+  static constexpr int kBBytes = (BN / 2) * 128;        // this CTA's half of the BN-row B k-block
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 128 * 64 * 2 + 4096;
   static constexpr int kFit = (kMaxSmem - 1024 - kMiscBytes - kOutBytes) / kStageBytes;
-  static constexpr int kStages = kFit > 8 ? 8 : kFit;   // 6
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;   // 6 (BN = 256) / 8 (BN = 128)
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + kMiscBytes;
-  static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = 256
+  static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(BN >> 3) << 17) | ((256u >> 4) << 24);   // M = 256, N = BN
+  static_assert(BN == 256 || BN == 128, "2-SM conv: N = 256 or 128");
 };
+using Conv2Cfg = Conv2CfgT<256>;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -671,9 +676,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive o
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) conv_umma2_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = Conv2Cfg;
-  constexpr int BN = 256;
+  using Cfg = Conv2CfgT<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -746,7 +751,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) con
         const int nt = (int)nt_u, mg = (int)mg_u, ph = (int)ph_u;
         int x0, y0, n0;
         origin(mg * 2 + (int)rank, x0, y0, n0);
-        const int brow = ph * p.cout + nt * BN + (int)rank * 128;
+        const int brow = ph * p.cout + nt * BN + (int)rank * (BN / 2);
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const int dx = p.dx[ph][tap], dy = p.dy[ph][tap];
           for (int cb = 0; cb < kb_per_tap; ++cb) {

@@ -245,6 +245,8 @@ struct sd_engine {
   PFN_tmapEncodeTiled encode = nullptr;
   int num_sms = 148;
   int cta2 = 1;                        // Cout % 256 == 0 layers on SM pairs (cluster of 2, tcgen05 cta_group::2); SD_CTA2=0: one CTA per tile
+  int cta2_n128 = 0;                   // SD_CTA2_N128=1: Cout = 128 layers on SM pairs too (N = 128, one M tile per CTA).  Measured neutral
+                                       // (Up3 / Up_conv3.x -2..3 %, Conv2.x +1..3 %, pass unchanged), so the single-CTA MT = 2 kernel stays the default
   int gate_tma = 1;                    // gate epilogue moves the skip tensor with TMA (load, scale in smem, store); SD_GATETMA=0: per-thread row walk
   int up4 = 1;                         // Up2: four sub-pixel phases per work item (SD_UP4=0: generic kernel, phase by phase)
   int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
@@ -358,14 +360,16 @@ static int dispatch_band(const ConvParams& p, int cb, int epi, int grid, cudaStr
   return SD_EINVAL;
 }
 
-// 2-SM variant (cluster of 2, cta_group::2) of the 256-wide store-epilogue conv
+// 2-SM variant (cluster of 2, cta_group::2) of the store-epilogue conv: N = 256, or N = 128 with one M tile per CTA
+template <int BN>
 static int launch_conv2(const ConvParams& p, int n_sms, cudaStream_t s) {
+  using Cfg = Conv2CfgT<BN>;
   static PerDeviceOnce attr_once;
-  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int n_work = ((p.m_tiles + 1) / 2) * p.n_tiles * p.n_phases;
   int pairs = n_sms / 2;
   if (n_work < pairs) pairs = n_work;
-  conv_umma2_kernel<<<2 * pairs, kConvThreads, Conv2Cfg::kSmemBytes, s>>>(p);
+  conv_umma2_kernel<BN><<<2 * pairs, kConvThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_umma2_kernel");
   return SD_OK;
 }
@@ -593,11 +597,11 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
   const int box_n = L.box_n, per_img = p.tiles_x * p.tiles_y;
   const int nsm = e->num_sms;
   op.flops_per_tile = 2.0 * (cs.up ? 4.0 : 1.0) * L.H * L.W * co * K;
-  const bool cta2 = e->cta2 && bn == 256 && epi == EPI_STORE;
+  const bool cta2 = epi == EPI_STORE && ((e->cta2 && bn == 256) || (e->cta2_n128 && bn == 128 && mt == 2));
   if (cta2) {
     op.name += "[2sm]";
-    // each CTA of a pair fetches its own 128-row half of the 256-row B k-block
-    if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], (cs.up ? 4 : 1) * co, K, 128))) return r;
+    // each CTA of a pair fetches its own half (128 / 64 rows) of the B k-block
+    if ((r = make_tmap_w(e, &p.tmB, e->w_umma[slot], (cs.up ? 4 : 1) * co, K, bn / 2))) return r;
   }
   op.run = [e, p, bn, mt, epi, box_n, per_img, nsm, cta2](int B, cudaStream_t s) mutable -> int {
     p.B = B;
@@ -606,7 +610,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
       p.head_b = e->head_b; p.thr = e->thr;
       p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask; p.tile_dst = e->odst;
     }
-    if (cta2) return launch_conv2(p, nsm, s);
+    if (cta2) return bn == 256 ? launch_conv2<256>(p, nsm, s) : launch_conv2<128>(p, nsm, s);
     const int n_work = ((p.m_tiles + mt - 1) / mt) * p.n_tiles * p.n_phases;
     const int grid = n_work < nsm ? n_work : nsm;
     return dispatch_conv(p, bn, mt, epi, grid, s);
@@ -733,6 +737,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
   if (const char* gt = getenv("SD_GATETMA")) e->gate_tma = atoi(gt);
   if (const char* c2 = getenv("SD_CTA2")) e->cta2 = atoi(c2);
+  if (const char* c2 = getenv("SD_CTA2_N128")) e->cta2_n128 = atoi(c2);
   if (!e->band) e->fuse_pool = 0;                   // the level-1 pool is fused in the band kernel only
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
