@@ -53,6 +53,9 @@ struct ConvParams {
   float psi_b;
   const act_t* gate_x;        // skip tensor to scale, NHWC with gate_c channels
   int gate_c;
+  float* psi_out;              // gate epilogue, psi-only form: the gate writes sigma(psi) (one fp32 per pixel) and nothing else;
+                               // the consumer (band kernel, PSI = true) scales the skip rows it stages with it
+  const float* psi_in;         // band kernel, PSI = true: the plane the gate wrote
   // head epilogue
   const float* head_w;         // [cout]
   float head_b, thr;
@@ -497,9 +500,12 @@ __global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma
         // their latency hides behind the wait for the accumulator
         uint4 xpre[8];
         const bool gate_tma = EPI == EPI_GATE && p.gate_tma;
+        const bool psi_only = EPI == EPI_GATE && p.psi_out != nullptr;
         const int gx0 = tx * p.box_w, gy0 = ty * p.box_h, gn0 = tn * p.box_n;
         if constexpr (EPI == EPI_GATE) {
-          if (gate_tma) {
+          if (psi_only) {
+            // nothing to prefetch: the skip tensor is scaled by its consumer
+          } else if (gate_tma) {
             // first 64-channel block of the skip tensor -> buffer 0, in flight while the accumulator is awaited
             if (et == 0) {
               tma_store_wait_read();                    // the previous tile's stores are done reading the buffers
@@ -533,7 +539,9 @@ __global__ void __launch_bounds__((ConvCfg<BN, EPI, MT>::kThreads), 1) conv_umma
           // (A 128-thread "coalesced" sweep over the tile measured slower: each row is a whole number of
           // 128-B lines, so the per-row walk already moves full lines.)
           const float sc = 1.f / (1.f + expf(-(dot + p.psi_b)));
-          if (gate_tma) {
+          if (psi_only) {
+            if (live) p.psi_out[pix] = sc;
+          } else if (gate_tma) {
             const int nhb = p.gate_c >> 6;
 #pragma unroll 1
             for (int hb = 0; hb < nhb; ++hb) {
@@ -900,7 +908,7 @@ constexpr int kRowBoxBytes = 130 * 128;
 // ---------------------------------------------------------------------------------------------
 constexpr int kBandRows = 32;
 
-template <int CB, int EPI> struct BandCfg {
+template <int CB, int EPI, bool PSI = false> struct BandCfg {
   static constexpr int kWBytes = 9 * CB * 8192;        // [dx][cb][ky = 2, 1, 0][64 cout] rows of 128 B
   static constexpr bool kCanPool = (EPI == EPI_STORE) && CB == 1;      // fused MaxPool2x2 (Conv1.3): two row buffers + pooled row
   static constexpr int kOutBytes = (EPI == EPI_STORE ? 16384 : 0) + (kCanPool ? 16384 + 8192 : 0);
@@ -909,8 +917,13 @@ template <int CB, int EPI> struct BandCfg {
   static constexpr int kSmemBytes = kStages * kRowStageBytes + kWBytes + kOutBytes + 1024 + kMiscBytes;
   static constexpr int kEpiWarps = (EPI == EPI_STORE) ? SD_EPI_WARPS : 4;   // as in ConvCfg; the head reduces over all 64 channels per thread
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kThreads = 64 + kEpiThreads;
+  // PSI: four more warps scale the staged rows of source 0 (the skip tensor) by the attention gate's psi plane before the
+  // MMAs read them: the gate then writes 4 bytes per pixel instead of the scaled copy of the skip tensor (Att2: 1.6 GB per
+  // 256 tiles), and x * psi never exists in HBM.  Same arithmetic as the gate's own scaling (fp32 product, one rounding).
+  static constexpr int kScaleThreads = PSI ? 128 : 0;
+  static constexpr int kThreads = 64 + kEpiThreads + kScaleThreads;
   static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(!PSI || (CB == 2 && EPI == EPI_STORE), "psi scaling is built for the concat consumer (Up_conv2.0)");
 };
 
 __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
@@ -923,9 +936,9 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CB, int EPI>
-__global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = BandCfg<CB, EPI>;
+template <int CB, int EPI, bool PSI>
+__global__ void __launch_bounds__((BandCfg<CB, EPI, PSI>::kThreads), 1) conv_band_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = BandCfg<CB, EPI, PSI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -939,6 +952,7 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
   auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (24 + s); };
   const uint32_t w_bar = bar_base + 8u * 32;
+  auto scaled_bar = [&](int s) { return bar_base + 8u * (33 + s); };     // PSI: stage s has been scaled (or needs no scaling)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 384);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -952,6 +966,7 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), Cfg::kEpiThreads); }
+    if (PSI) for (int s = 0; s < Cfg::kStages; ++s) mbar_init(scaled_bar(s), 128);
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1035,7 +1050,7 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
           const uint32_t idesc2 = kIdescBase | ((uint32_t)(n2 * 8) << 17) | ((128u >> 4) << 24);
           const uint32_t d1 = tmem_base + (uint32_t)(s_lo * 64);
           for (int cb = 0; cb < CB; ++cb) {
-            mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+            mbar_wait(PSI ? scaled_bar(stage) : full_bar(stage), phase, p.err_flag, 3);
             tc_fence_after();
             const uint32_t a_addr = smem_base + stage * kRowStageBytes;
 #pragma unroll
@@ -1062,6 +1077,51 @@ __global__ void __launch_bounds__((BandCfg<CB, EPI>::kThreads), 1) conv_band_ker
       }
     }
     __syncwarp();
+  } else if (PSI && warp >= 2 + Cfg::kEpiWarps) {
+    // ======================= psi scalers (4 warps): thread = staged pixel row =======================
+    // Walks the producer's stage sequence.  Source-0 stages (the skip tensor): wait for the TMA box, multiply the 64
+    // channels of pixel row r by psi of that pixel (fp32 product, one rounding: what the gate's own scaling did), make the
+    // generic-proxy writes visible to the tensor pipe, arrive.  Source-1 stages: arrive as soon as the box has landed.
+    const int t = threadIdx.x - 64 - Cfg::kEpiThreads;  // 0..127
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sx = w % segs; int rest = w / segs;
+      const int b = rest % bands; const int n = rest / bands;
+      const int y0 = b * kBandRows, y1 = min(y0 + kBandRows, p.H);
+      for (int i = max(y0 - 1, 0); i <= min(y1, p.H - 1); ++i) {
+        // psi of this thread's halo pixel(s): columns sx*128 - 1 + r, r = t (and t + 128 for the two last halo rows); columns
+        // outside the image hold zero-filled data, any finite factor does
+        const float* prow = p.psi_in + ((int64_t)n * p.H + i) * p.W;
+        const float sc0 = __ldg(prow + min(max(sx * 128 - 1 + t, 0), p.W - 1));
+        const float sc1 = t < 2 ? __ldg(prow + min(sx * 128 + 127 + t, p.W - 1)) : 0.f;
+        for (int cb = 0; cb < CB; ++cb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 7);
+          if (cb == 0) {
+            const uint32_t a_addr = smem_base + stage * kRowStageBytes;
+#pragma unroll 1
+            for (int rr = 0; rr < (t < 2 ? 2 : 1); ++rr) {
+              const int r = t + rr * 128;
+              const float sc = rr ? sc1 : sc0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t addr = sw128(a_addr, r, j);
+                uint4 v = ld_shared_v4(addr);
+                act2_t* h = reinterpret_cast<act2_t*>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = act22float2(h[k]);
+                  h[k] = floats2act2(f.x * sc, f.y * sc);
+                }
+                st_shared_v4(addr, v);
+              }
+            }
+            fence_async_smem();                         // generic-proxy writes -> visible to the tensor pipe
+          }
+          mbar_arrive(scaled_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;

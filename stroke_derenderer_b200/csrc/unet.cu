@@ -169,6 +169,22 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConv a) {
   }
 }
 
+// debug / tap reader: a1 = x1 * psi with the arithmetic of the gate epilogue (fp32 product, one rounding)
+__global__ void scale_by_psi_kernel(const uint4* __restrict__ x, const float* __restrict__ psi, uint4* __restrict__ out, int64_t px,
+                                    int chunks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= px * chunks) return;
+  const float sc = psi[i / chunks];
+  uint4 v = x[i];
+  act2_t* h = reinterpret_cast<act2_t*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f = act22float2(h[k]);
+    h[k] = floats2act2(f.x * sc, f.y * sc);
+  }
+  out[i] = v;
+}
+
 __global__ void gate_apply_kernel(const float* __restrict__ q, const float* __restrict__ psi_w, float psi_b,
                                   const act_t* __restrict__ x, act_t* __restrict__ out, int64_t M, int fint, int fl) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,6 +263,9 @@ struct sd_engine {
   int cta2 = 1;                        // Cout % 256 == 0 layers on SM pairs (cluster of 2, tcgen05 cta_group::2); SD_CTA2=0: one CTA per tile
   int cta2_n128 = 0;                   // SD_CTA2_N128=1: Cout = 128 layers on SM pairs too (N = 128, one M tile per CTA).  Measured neutral
                                        // (Up3 / Up_conv3.x -2..3 %, Conv2.x +1..3 %, pass unchanged), so the single-CTA MT = 2 kernel stays the default
+  int psi_fused = 1;                   // level-1 gate (Att2) writes only psi; Up_conv2.0's band kernel scales the skip rows it stages (SD_PSI_FUSED=0: the gate writes x * psi)
+  float* psi1 = nullptr;               // [max_tiles][H][W] fp32: sigma(psi) of the level-1 gate
+  bool psi_live = false;               // this engine runs the psi-only gate: tap a1 is materialised on demand
   int gate_tma = 1;                    // gate epilogue moves the skip tensor with TMA (load, scale in smem, store); SD_GATETMA=0: per-thread row walk
   int up4 = 1;                         // Up2: four sub-pixel phases per work item (SD_UP4=0: generic kernel, phase by phase)
   int fuse_pool = 1;                   // MaxPool2x2 fused into the preceding conv's epilogue (SD_FUSEPOOL=0: separate kernel)
@@ -342,12 +361,12 @@ static int launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
   return SD_OK;
 }
 
-template <int CB, int EPI>
+template <int CB, int EPI, bool PSI = false>
 static int launch_band(const ConvParams& p, int grid, cudaStream_t s) {
-  using Cfg = BandCfg<CB, EPI>;
+  using Cfg = BandCfg<CB, EPI, PSI>;
   static PerDeviceOnce attr_once;
-  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  conv_band_kernel<CB, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(p);
+  if (attr_once.first()) SD_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<CB, EPI, PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  conv_band_kernel<CB, EPI, PSI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(p);
   SD_LAUNCH_CHECK("conv_band_kernel");
   return SD_OK;
 }
@@ -445,6 +464,8 @@ struct ConvSpec {
   int epi;                          // EPI_*
   int att = -1;                     // gate: index 0..3 (psi slot / bias), x source = in1
   const Act* pool_out = nullptr;    // store epilogue: also write MaxPool2x2(out) here (fused pool)
+  float* psi_out = nullptr;         // gate: write only sigma(psi) here (the consumer scales the skip tensor)
+  const float* psi_in = nullptr;    // band conv with two sources: scale the staged rows of in0 by this plane
 };
 
 static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
@@ -483,17 +504,23 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     } else {
       p.head_w = e->w_f32[SD_HEAD];
     }
+    const bool psi = cs.psi_in != nullptr;
+    if (psi) {
+      SD_REQUIRE(cb == 2 && cs.epi == EPI_STORE, "add_umma_conv(%s): psi scaling needs the two-source store form", cs.name);
+      p.psi_in = cs.psi_in;
+    }
     Op op;
-    op.name = std::string(cs.name) + "[band]" + (p.pool ? "+pool" : "");
+    op.name = std::string(cs.name) + "[band" + (psi ? ",psi" : "") + "]" + (p.pool ? "+pool" : "");
     const int epi = cs.epi, nsm = e->num_sms, segs = L.W / 128, H = L.H;
     op.flops_per_tile = 2.0 * L.H * L.W * co * 9 * cin_total;
-    op.run = [e, p, cb, epi, nsm, segs, H](int B, cudaStream_t s) mutable -> int {
+    op.run = [e, p, cb, epi, nsm, segs, H, psi](int B, cudaStream_t s) mutable -> int {
       p.B = B;
       if (epi == EPI_HEAD) {
         p.head_b = e->head_b; p.thr = e->thr;
         p.prob_f32 = e->o32; p.prob_f16 = e->o16; p.mask_u8 = e->omask; p.tile_dst = e->odst;
       }
       const int n_work = B * ((H + kBandRows - 1) / kBandRows) * segs;
+      if (psi) return launch_band<2, EPI_STORE, true>(p, n_work < nsm ? n_work : nsm, s);
       return dispatch_band(p, cb, epi, n_work < nsm ? n_work : nsm, s);
     };
     e->ops.push_back(op);
@@ -545,6 +572,7 @@ static int add_umma_conv(sd_engine* e, const ConvSpec& cs) {
     p.psi_w = e->w_f32[SD_ATT5_PSI + 6 * cs.att]; p.psi_b = e->psi_b[cs.att];
     p.gate_x = cs.in1->p; p.gate_c = cs.in1->C;
     p.gate_tma = e->gate_tma;
+    p.psi_out = cs.psi_out;
     if ((r = make_tmap_out(e, &p.tmOut[0], *cs.out, L, false, 0))) return r;
   }
   if (cs.epi == EPI_HEAD) { p.head_w = e->w_f32[SD_HEAD]; }
@@ -736,6 +764,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if (const char* fp = getenv("SD_FUSEPOOL")) e->fuse_pool = atoi(fp);
   if (const char* u4 = getenv("SD_UP4")) e->up4 = atoi(u4);
   if (const char* gt = getenv("SD_GATETMA")) e->gate_tma = atoi(gt);
+  if (const char* pf = getenv("SD_PSI_FUSED")) e->psi_fused = atoi(pf);
   if (const char* c2 = getenv("SD_CTA2")) e->cta2 = atoi(c2);
   if (const char* c2 = getenv("SD_CTA2_N128")) e->cta2_n128 = atoi(c2);
   if (!e->band) e->fuse_pool = 0;                   // the level-1 pool is fused in the band kernel only
@@ -835,6 +864,7 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
     if ((r = alloc_act(e, A[SD_TAP_D2], 0, 64))) return r;
     if ((r = dev_alloc(e, (void**)&e->qbuf, (size_t)e->max_tiles * H * W * 32 * sizeof(float)))) return r;
   }
+  if (impl == 0 && e->psi_fused && (r = dev_alloc(e, (void**)&e->psi1, (size_t)e->cap_tiles * H * W * sizeof(float)))) return r;
 
   // ---- schedule ----
   Op first;
@@ -958,8 +988,21 @@ extern "C" int sd_engine_finalize(sd_engine* e, int impl) {
   if ((r = conv("Up_conv3.3", SD_UPCONV3_1, &e->u3a, nullptr, &A[SD_TAP_D3], false))) return r;
 
   if ((r = conv("Up2", SD_UP2, &A[SD_TAP_D3], nullptr, &A[SD_TAP_D2U], true))) return r;
-  if ((r = gate("Att2", 3, &A[SD_TAP_D2U], &A[SD_TAP_X1], &A[SD_TAP_A1]))) return r;
-  if ((r = conv("Up_conv2.0", SD_UPCONV2_0, &A[SD_TAP_A1], &A[SD_TAP_D2U], &e->u2a, false))) return r;
+  // level-1 gate: psi-only form when its consumer is the band kernel (which scales the skip rows it stages); x1 * psi
+  // then never exists in HBM (sd_unet_read_tap materialises it on demand)
+  e->psi_live = impl == 0 && e->psi_fused && e->band && e->psi1;
+  if (e->psi_live) {
+    ConvSpec cg{"Att2", SD_ATT5_G + 6 * 3, &A[SD_TAP_D2U], &A[SD_TAP_X1], &A[SD_TAP_A1], false, EPI_GATE, 3};
+    cg.psi_out = e->psi1;
+    if ((r = add_umma_conv(e, cg))) return r;
+    e->ops.back().name += "[psi]";
+    ConvSpec cu{"Up_conv2.0", SD_UPCONV2_0, &A[SD_TAP_X1], &A[SD_TAP_D2U], &e->u2a, false, EPI_STORE, -1};
+    cu.psi_in = e->psi1;
+    if ((r = add_umma_conv(e, cu))) return r;
+  } else {
+    if ((r = gate("Att2", 3, &A[SD_TAP_D2U], &A[SD_TAP_X1], &A[SD_TAP_A1]))) return r;
+    if ((r = conv("Up_conv2.0", SD_UPCONV2_0, &A[SD_TAP_A1], &A[SD_TAP_D2U], &e->u2a, false))) return r;
+  }
   if (impl == 0) {
     ConvSpec cs{"Up_conv2.3+head", SD_UPCONV2_1, &e->u2a, nullptr, nullptr, false, EPI_HEAD, -1};
     if ((r = add_umma_conv(e, cs))) return r;
@@ -1050,6 +1093,12 @@ extern "C" int sd_unet_read_tap(sd_engine* e, int tap, int n_tiles, void* d_out,
   if (!d_out) return SD_OK;
   const size_t need = (size_t)n_tiles * a.H * a.W * a.C * sizeof(act_t);
   SD_REQUIRE(out_bytes >= need, "sd_unet_read_tap: buffer too small (%zu < %zu)", out_bytes, need);
+  if (tap == SD_TAP_A1 && e->psi_live) {      // psi-only gate: x1 * psi exists only inside the consumer; rebuild it for the reader
+    const int64_t px = (int64_t)n_tiles * a.H * a.W;
+    scale_by_psi_kernel<<<ceil_div(px * (a.C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(e->act[SD_TAP_X1].p), e->psi1, reinterpret_cast<uint4*>(a.p), px, a.C / 8);
+    SD_LAUNCH_CHECK("scale_by_psi_kernel");
+  }
   SD_CUDA_CHECK(cudaMemcpyAsync(d_out, a.p, need, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SD_OK;
 }
