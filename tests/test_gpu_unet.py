@@ -125,6 +125,36 @@ def test_fused_glue_equals_glue_of_tile_masks(cuda_device, parity_state):
         e.close()
 
 
+def test_engine_switches_are_bit_identical(cuda_device, parity_state, monkeypatch):
+    """The engine switches read at creation select different kernels for the same arithmetic: the psi-only level-1 gate whose
+    consumer scales the skip rows (default) vs the gate that writes x * psi (SD_PSI_FUSED=0), and the level-2 layers on SM
+    pairs (SD_CTA2_N128=1) vs the single-CTA form.  Probabilities and masks must agree bit for bit, on full and partial
+    batches, and the on-demand `a1` tap of the psi-only engine must equal the tensor the other engine wrote."""
+    x = UNetEngine.pack_input(torch.from_numpy(_tiles(9, seed=5)).cuda())
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = UNetEngine(parity_state, device=0, max_tiles=9, impl=0)
+        try:
+            full = e.forward(x, want_prob32=True, want_mask=True)
+            out = [full["prob32"].clone(), full["mask"].clone()]
+            part = e.forward(x[:4].contiguous(), want_prob32=True)
+            out.append(part["prob32"].clone())
+            out.append(e.read_tap("a1", 4).clone())
+        finally:
+            e.close()
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+        return out
+
+    base = run({})
+    for env in ({"SD_PSI_FUSED": "0"}, {"SD_CTA2_N128": "1"}, {"SD_PSI_FUSED": "0", "SD_CTA2_N128": "1"}):
+        other = run(env)
+        for a, b in zip(base, other):
+            assert torch.equal(a, b), env
+
+
 def test_batch_invariance(cuda_device, parity_state):
     """Tiles are independent images: a tile's probabilities must not depend on what else is in the batch or on
     its position in it (catches cross-tile leaks in the persistent kernels: accumulator rings, pooled row pairs,

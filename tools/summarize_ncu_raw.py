@@ -1,5 +1,5 @@
 """Summarise an `ncu -i x.ncu-rep --page raw --csv` dump: one row per launch with duration, tensor-pipe
-activity, DRAM traffic and throughput.  Usage: summarize_ncu_raw.py raw.csv out.md [names.json]
+activity, DRAM traffic and throughput.  Usage: summarize_ncu_raw.py raw.csv out.md [names.json [traffic.json kernel_regex [tiles_per_pass]]]
 names.json (optional): list of stage names in launch order (e.g. the engine's layer list)."""
 import csv
 import json
@@ -72,7 +72,8 @@ def main():
                 mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[idx[c]], 1.0)
                 b += num(r[idx[c]]) * mul
             tot += b; n += 1
-        json.dump({"kernels": rx.pattern, "launches": n, "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(n, 1),
+        tiles = int(sys.argv[6]) if len(sys.argv) > 6 else 256      # tiles of the captured pass (bench.py scales by it)
+        json.dump({"kernels": rx.pattern, "launches": n, "dram_bytes_total": tot, "dram_bytes_per_launch": tot / max(n, 1), "tiles_per_pass": tiles,
                    "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum"},
                   open(sys.argv[4], "w"), indent=1)
 
