@@ -211,3 +211,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "tiles/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_fastdiv_identity():
+    """csrc/common.cuh FastDiv: q = (x * (2^40 // d + 1)) >> 40 is floor(x / d) for every x, d < 2^20 (the conv kernels
+    decompose work-item and tile indices with it); checked on the edges and on random pairs."""
+    rng = np.random.default_rng(0)
+    ds = np.concatenate([np.arange(1, 300), rng.integers(1, 1 << 20, 4000), [(1 << 20) - 1, 12288, 24576, 49152, 98304]]).astype(object)
+    xs = np.concatenate([np.arange(0, 300), rng.integers(0, 1 << 20, 4000), [(1 << 20) - 1]]).astype(object)
+    for d in ds:
+        m = (1 << 40) // int(d) + 1
+        for x in (0, 1, int(d) - 1, int(d), int(d) + 1, 2 * int(d) - 1, (1 << 20) - 1):
+            x = min(x, (1 << 20) - 1)
+            assert (x * m) >> 40 == x // int(d), (x, d)
+    for x, d in zip(xs, ds[:len(xs)]):
+        m = (1 << 40) // int(d) + 1
+        assert (int(x) * m) >> 40 == int(x) // int(d), (x, d)
