@@ -688,7 +688,9 @@ static void add_pool(sd_engine* e, const char* name, const Act* in, const Act* o
 // ===========================================================================
 extern "C" int sd_engine_create(int device, int max_tiles, int tile_h, int tile_w, sd_engine** out) {
   SD_REQUIRE(out, "sd_engine_create: null out");
-  SD_REQUIRE(max_tiles > 0, "sd_engine_create: max_tiles %d", max_tiles);
+  // 2048 tiles = 150 GB of activations, more than fits beside the weights; it also keeps every work-item count below 2^20,
+  // the domain of the kernels' multiply-shift dividers (common.cuh FastDiv)
+  SD_REQUIRE(max_tiles > 0 && max_tiles <= 2048, "sd_engine_create: max_tiles %d (1..2048)", max_tiles);
   SD_REQUIRE(tile_h == SD_TILE_H && tile_w == SD_TILE_W, "sd_engine_create: only %dx%d tiles are supported (got %dx%d)",
              SD_TILE_H, SD_TILE_W, tile_h, tile_w);
   int ndev = 0;
